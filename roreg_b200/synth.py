@@ -1,0 +1,61 @@
+"""Synthetic cloud pairs for parity tests and bench.py.
+
+There is no network for the 3DMatch / ETH datasets and the FCGF backbone (MinkowskiEngine)
+cannot run here, so every test and the bench use seeded synthetic pairs that have the
+shapes, dtypes, value ranges and group structure of the reference's cached features:
+  * keypoints  [N,3] float64 in metres                       (dataops/dataset.py:109-116)
+  * descriptors [N,32,60] float32, unit L2 norm over the 32 axis per (n,g)
+                                                               (network/group_feat.py:42)
+Convention (dataops/dataset.py:27-30):  R_gt . pts(id1) + t_gt = pts(id0).
+Cloud id0 is cloud id1 rotated by R_gt = R_res . Rgroup[a]; by the equivariance law
+F(R_a x)[:,:,g] = F(x)[:,:,P[a][g]] its descriptors are the id1 descriptors with the group
+axis permuted by P[a] (plus noise), so Des2R(feats1, feats0) -> a  (test/estimator.py:110).
+"""
+import numpy as np
+from . import group as _group
+
+
+def _unit(x, axis):
+    return x / np.maximum(np.linalg.norm(x, axis=axis, keepdims=True), 1e-12)
+
+
+def small_rotation(rng, max_deg):
+    ax = _unit(rng.standard_normal(3), 0)
+    th = np.deg2rad(max_deg) * rng.random()
+    K = np.array([[0, -ax[2], ax[1]], [ax[2], 0, -ax[0]], [-ax[1], ax[0], 0]])
+    return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * (K @ K)
+
+
+def make_pair(seed, n=5000, overlap=0.6, sigma_desc=0.08, sigma_xyz=0.01, max_res_deg=15.0,
+              tables=None, with_fcgf=False):
+    """Returns dict: keys0, keys1 [n,3] f64; feats0, feats1 [n,32,60] f32; gt [3,4] f64;
+    a (coarse rotation index); corr0 [n] = index in cloud1 of the true partner or -1;
+    optionally fcgf0, fcgf1 (ET inputs, an independent draw with the same structure)."""
+    tb = tables or _group.load()
+    rng = np.random.default_rng(seed)
+    a = int(rng.integers(0, 60))
+    R = small_rotation(rng, max_res_deg) @ tb.rot[a]
+    t = rng.uniform(-1.0, 1.0, 3)
+    keys1 = rng.uniform(0.0, 3.0, (n, 3))
+    feats1 = _unit(rng.standard_normal((n, 32, 60), dtype=np.float32), 1)
+    n_ov = int(round(overlap * n))
+    src = rng.permutation(n)[:n_ov]                       # rows of cloud1 that have a partner
+    keys0 = np.empty((n, 3)); feats0 = np.empty((n, 32, 60), np.float32)
+    keys0[:n_ov] = keys1[src] @ R.T + t + sigma_xyz * rng.standard_normal((n_ov, 3))
+    feats0[:n_ov] = _unit(feats1[src][:, :, tb.perm[a]]
+                          + sigma_desc * rng.standard_normal((n_ov, 32, 60), dtype=np.float32), 1)
+    keys0[n_ov:] = rng.uniform(0.0, 3.0, (n - n_ov, 3)) @ R.T + t
+    feats0[n_ov:] = _unit(rng.standard_normal((n - n_ov, 32, 60), dtype=np.float32), 1)
+    corr0 = np.full(n, -1, np.int64); corr0[:n_ov] = src
+    order = rng.permutation(n)                            # hide the identity ordering
+    out = dict(keys0=np.ascontiguousarray(keys0[order]), keys1=keys1,
+               feats0=np.ascontiguousarray(feats0[order]), feats1=feats1,
+               gt=np.concatenate([R, t[:, None]], 1), a=a, corr0=corr0[order], seed=seed)
+    if with_fcgf:
+        f1 = _unit(rng.standard_normal((n, 32, 60), dtype=np.float32), 1)
+        f0 = np.empty_like(f1)
+        f0[:n_ov] = _unit(f1[src][:, :, tb.perm[a]]
+                          + sigma_desc * rng.standard_normal((n_ov, 32, 60), dtype=np.float32), 1)
+        f0[n_ov:] = _unit(rng.standard_normal((n - n_ov, 32, 60), dtype=np.float32), 1)
+        out["fcgf0"] = np.ascontiguousarray(f0[order]); out["fcgf1"] = f1
+    return out
