@@ -59,3 +59,45 @@ def make_pair(seed, n=5000, overlap=0.6, sigma_desc=0.08, sigma_xyz=0.01, max_re
         f0[n_ov:] = _unit(rng.standard_normal((n - n_ov, 32, 60), dtype=np.float32), 1)
         out["fcgf0"] = np.ascontiguousarray(f0[order]); out["fcgf1"] = f1
     return out
+
+
+class SynthDataset:
+    """Duck type of dataops/dataset.py:41-129 (ThrDMatchPartDataset) over synthetic pairs:
+    `.name`, `.pc_ids`, `.pair_ids`, `.get_kps(id)`, `.get_transform(id0,id1)`.
+    Pair p uses clouds (2p, 2p+1) = (id0, id1)."""
+
+    def __init__(self, seeds, n=256, name="synth/scene", tables=None, with_fcgf=True, **kw):
+        self.name = name
+        self.pairs = [make_pair(s, n=n, tables=tables, with_fcgf=with_fcgf, **kw) for s in seeds]
+        self.pc_ids = [str(i) for i in range(2 * len(seeds))]
+        self.pair_ids = [(str(2 * p), str(2 * p + 1)) for p in range(len(seeds))]
+
+    def _cloud(self, cid):
+        cid = int(cid)
+        return self.pairs[cid // 2], cid % 2
+
+    def get_kps(self, cid):
+        pr, s = self._cloud(cid)
+        return pr[f"keys{s}"]
+
+    def get_feats(self, cid, kind="feats"):
+        pr, s = self._cloud(cid)
+        return pr[f"{kind}{s}"]
+
+    def get_transform(self, id0, id1):
+        return self.pairs[int(id0) // 2]["gt"].astype(np.float32)
+
+    def write_cache(self, cache_root, backbone="FCGF", yoho=True):
+        """Lay the descriptors out as the reference's on-disk contract expects
+        (testset.py:180, test/extractor.py:60)."""
+        import os
+        d_in = f"{cache_root}/{self.name}/{backbone}_Input_Group_feature"
+        d_out = f"{cache_root}/{self.name}/YOHO_Output_Group_feature"
+        os.makedirs(d_in, exist_ok=True)
+        for cid in self.pc_ids:
+            if self.pairs[0].get("fcgf0") is not None:
+                np.save(f"{d_in}/{cid}.npy", self.get_feats(cid, "fcgf"))
+        if yoho:
+            os.makedirs(d_out, exist_ok=True)
+            for cid in self.pc_ids:
+                np.save(f"{d_out}/{cid}.npy", self.get_feats(cid))
