@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py - pair registrations / second on synthetic [5000-keypoint, 32-d, 60-rotation] cloud pairs.
+
+One "step" = one pass of the per-pair hot path (mutual matcher -> Des2R coarse rotations -> coarse-
+rotation-guided RANSAC, 1000 iterations -> two weighted-Kabsch refinements) over a batch of B
+independent synthetic pairs through the batched C-ABI engine (roreg_register_batch).  This is the
+reference's default CLI configuration (`python Test.py`: --ET yohoc, mutual matcher) at BASELINE.json's
+configs[1] size.  Nothing is skipped inside the timed region; the hypotheses are drawn and solved on
+the device.
+
+  value  - pairs/s with descriptors + keypoints already resident in HBM (B x 77 MB > L2, so every step
+           streams its inputs from HBM: no L2 flush needed, stated in config.l2)
+  e2e    - same metric through the same call with HOST (pinned) buffers: per step the descriptors and
+           keypoints are copied host->device and the poses device->host inside the timed region
+           (double-buffered on two streams so copies overlap compute)
+  roofline / cpu_baseline - see DESIGN.md "Measurement"
+
+Multi-GPU (torchrun, one rank per GPU): pairs shard across ranks with no data-path collective
+(weak scaling: B pairs per rank per step); the only collective is the final NCCL all_gather of the
+[steps*B,4,4] poses, inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--n", type=int, default=5000, help="keypoints per cloud")
+    ap.add_argument("--max-iter", type=int, default=1000)
+    ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "0")))
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for j, n in enumerate(names) if any(len(r) > 3 + j and r[3 + j].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_inputs(B, n, rank):
+    from roreg_b200 import synth
+    prs = [synth.make_pair(1000 * (rank + 1) + p, n=n) for p in range(B)]
+    desc = np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])])
+    keys = np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])])
+    pc = np.array([[2 * i, 2 * i + 1] for i in range(B)], np.int32)
+    return prs, desc, keys, pc
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_pipeline(pr, tables, max_iter, ird, seed):
+    """The oracle's restatement of the same pipeline on the host (reference arithmetic, NumPy)."""
+    from oracle import roreg_oracle as O
+    pps, sc = O.mutual_run(pr["feats0"], pr["feats1"])
+    dr = O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm)
+    k0 = pr["keys0"][pps[:, 0]]; k1 = pr["keys1"][pps[:, 1]]
+    T, recall, _ = O.yohoc_ransac(k0, k1, sc, dr, ird, max_iter, rng=np.random.RandomState(seed))
+    return T
+
+
+def cpu_baseline(prs, n_pairs, max_iter, ird):
+    from roreg_b200 import group
+    try:
+        from oracle import oracle_c
+        have_c = oracle_c.available()
+    except Exception:
+        have_c = False
+    tables = group.load()
+    t0 = time.perf_counter()
+    if have_c:
+        for i in range(n_pairs):
+            oracle_c.register_pair(prs[i], tables, max_iter, ird, seed=i)
+        cores = oracle_c.threads()
+        how = "oracle/oracle_c.c (C + OpenMP restatement of the reference arithmetic)"
+    else:
+        for i in range(n_pairs):
+            cpu_pipeline(prs[i], tables, max_iter, ird, i)
+        cores = 1
+        how = "oracle/roreg_oracle.py (NumPy restatement; BLAS-free difference-form kernels run on one core)"
+    dt = time.perf_counter() - t0
+    return {"value": n_pairs / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
+            "sample": f"{n_pairs} pair(s) of the same workload, {dt:.1f} s wall, {how}"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU arithmetic for the path (oracle port) on the host cores."""
+    if rank != 0:
+        return
+    prs, _, _, _ = make_inputs(max(1, args.cpu_sample_pairs), args.n, 0)
+    times = []
+    for s in range(args.warmup + args.steps):
+        cb = cpu_baseline(prs, len(prs), args.max_iter, 0.1)
+        if s >= args.warmup:
+            times.append(len(prs) / cb["value"])
+        if sum(times) > 240:            # bounded: keep the whole arm within a few minutes
+            break
+    val = len(prs) * len(times) / sum(times)
+    cb["value"] = val
+    line = {"impl": "reference", "metric": "pair registrations/sec (5000 kpt, 60-rot)", "value": val, "unit": "pairs/s",
+            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
+            "config": workload_config(args, len(prs)), "cpu_baseline": cb,
+            "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, B):
+    return {"workload": f"mutual matcher + Des2R + yohoc RANSAC ({args.max_iter} iters) + 2x refine, one pair = 2 clouds x "
+                        f"{args.n} keypoints x [32,60] f32 descriptors (BASELINE configs[1], reference default CLI config)",
+            "pairs_per_step": B, "keypoints": args.n, "max_iter": args.max_iter, "ransac_ird": 0.1,
+            "parallelism": f"pairs sharded over {args.gpus} GPU(s), no data-path collective",
+            "l2": "inputs larger than L2 (B x 77 MB streamed per step), no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch
+    import torch.distributed as dist
+    import __graft_entry__
+    if rank == 0:
+        __graft_entry__.build()
+    if world > 1:
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.barrier()
+    from roreg_b200 import ops
+    torch.cuda.set_device(local)
+    ctx = ops.Context(local)
+    B, n, H = args.pairs_per_step, args.n, args.max_iter
+    prs, desc_h, keys_h, pc_h = make_inputs(B, n, rank)
+    desc_pin = torch.from_numpy(desc_h).pin_memory(); keys_pin = torch.from_numpy(keys_h).pin_memory()
+    pc = ctx.dev(pc_h)
+    dev = ctx.device
+    desc_d = [torch.empty_like(desc_pin, device=dev) for _ in range(2)]
+    keys_d = [torch.empty_like(keys_pin, device=dev) for _ in range(2)]
+    desc_d[0].copy_(desc_pin); keys_d[0].copy_(keys_pin)
+    outs = [None, None]
+
+    def step_resident(buf=0, seed=0):
+        outs[buf] = ctx.register_batch(desc_d[buf], keys_d[buf], pc, max_iter=H, ird=0.1, seed=seed, nn_mode=args.nn_mode, out=outs[buf])
+        return outs[buf]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---------------- resident-input throughput ("value") ----------------
+    ctx.set_timing(True)
+    for w in range(max(3, args.warmup)):
+        step_resident(0, w)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local); sampler.start()
+    poses_all = torch.empty((args.steps, B, 4, 4), dtype=torch.float64, device=dev)
+    stage_acc = {k: 0.0 for k in ctx.STAGES}
+    barrier()
+    l0 = ctx.launches
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for s in range(args.steps):
+        o = step_resident(0, 100 + s)
+        poses_all[s].copy_(o["poses"])
+        if s % 4 == 3 or s == args.steps - 1:      # read the per-stage events (host wait on this step only)
+            for k, v in ctx.stage_ms().items():
+                stage_acc[k] += v
+    n_stage_samples = len([s for s in range(args.steps) if s % 4 == 3 or s == args.steps - 1])
+    if world > 1:
+        gathered = torch.empty((world,) + tuple(poses_all.shape), dtype=torch.float64, device=dev)
+        dist.all_gather_into_tensor(gathered, poses_all)       # the path's only collective: final gather of poses
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launches - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * B * args.steps / (ms_max * 1e-3)
+
+    # sanity: every registered pose must agree with the planted ground truth (a wrong-but-fast kernel is not a result)
+    gt = np.stack([pr["gt"] for pr in prs])
+    err = np.abs(poses_all[-1].cpu().numpy()[:, :3] - gt).max()
+    ok = bool(err < 2e-2)
+
+    # ---------------- end-to-end with host buffers ("e2e") ----------------
+    ctx.set_timing(False)
+    copy_stream = torch.cuda.Stream(); comp = torch.cuda.current_stream()
+    poses_pin = torch.empty((B, 4, 4), dtype=torch.float64).pin_memory()
+    ready = [torch.cuda.Event(), torch.cuda.Event()]; done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def h2d(buf):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(done[buf])                  # previous consumer of this buffer finished
+            desc_d[buf].copy_(desc_pin, non_blocking=True); keys_d[buf].copy_(keys_pin, non_blocking=True)
+            ready[buf].record(copy_stream)
+
+    e2e_steps = max(4, min(args.steps, 12))
+    for b in (0, 1):
+        done[b].record(comp)
+    for rep in range(2):                                        # rep 0 = warm-up, rep 1 = timed
+        barrier()
+        t0 = time.perf_counter()
+        h2d(0)
+        for s in range(e2e_steps):
+            buf = s & 1
+            if s + 1 < e2e_steps:
+                h2d((s + 1) & 1)
+            comp.wait_event(ready[buf])
+            o = step_resident(buf, 500 + s)
+            done[buf].record(comp)
+            poses_pin.copy_(o["poses"], non_blocking=True)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(te.item())
+    h2d_bytes = desc_pin.numel() * 4 + keys_pin.numel() * 8
+    d2h_bytes = poses_pin.numel() * 8
+
+    # ---------------- roofline of the dominant stage ----------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0); tc_peak = peaks.get("bf16_tflops_sustained", 1400.0)
+    src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    stage_ms = {k: v / max(1, n_stage_samples) for k, v in stage_acc.items()}
+    dom = max(stage_ms, key=stage_ms.get)
+    kavg = float(o["n_matches"].double().mean().item())
+    alg = {   # algorithmic bytes / flops per LAUNCH GROUP (= per step of B pairs), DESIGN.md "Measurement"
+        "inv_pool": ("hbm", B * (2 * n * 7680 + 2 * n * 128)),
+        "group_corr": ("hbm", B * kavg * (2 * 7680 + 12)),
+        "nn": ("tensor", B * 2.0 * n * n * 32),
+        "score_select": ("hbm", B * (kavg * 52 + H * 96)),
+        "refine": ("hbm", B * kavg * 52 * 4),
+        "hypotheses": ("hbm", B * (kavg * 4 + H * 96)),
+        "compact": ("hbm", B * n * 16),
+    }
+    bound, amount = alg[dom]
+    dur = stage_ms[dom] * 1e-3
+    if bound == "hbm":
+        ach = amount / dur / 1e9; peak = hbm_peak; unit = "GB/s"
+    else:
+        ach = amount / dur / 1e12; peak = tc_peak; unit = "TFLOP/s"
+    roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                "traffic": None, "peak_source": src, "stage_ms_per_step": stage_ms,
+                "note": "algorithmic bytes/flops per step (B pairs) / CUDA-event duration of that stage inside the timed region"}
+
+    if rank == 0:
+        cb = cpu_baseline(prs, min(args.cpu_sample_pairs, B), H, 0.1) if world == 1 else None
+        line = {"metric": "pair registrations/sec (5000 kpt, 60-rot)", "value": value, "unit": "pairs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher, correlation) + f64 (RANSAC, Kabsch)",
+                "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
+                "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                        "steps": e2e_steps},
+                "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
+                "nn_mode": args.nn_mode}
+        if cb:
+            line["cpu_baseline"] = cb
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

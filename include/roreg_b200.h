@@ -1,0 +1,150 @@
+/* roreg_b200.h - C ABI of the B200-native RoReg per-pair registration hot path.
+ *
+ * Drop-in boundary: the reference has no FFI of its own - its hot path is
+ * stock PyTorch / NumPy called from test/{matcher,estimator}.py - so each entry point below names the
+ * reference function (file:line, relative to the reference root) whose arithmetic it replaces.  The
+ * Python mirror of the reference's plugin classes (roreg_b200/test/*.py) binds these with ctypes;
+ * INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 = roreg_status; nothing throws across the boundary;
+ *   - all data pointers are DEVICE pointers unless the name ends in _host; the caller owns every
+ *     buffer; the library owns only the context (group tables in constant/global memory + workspace);
+ *   - calls enqueue on the given cudaStream_t (passed as void*) and do not synchronise;
+ *   - one context per (device, host thread); calls on one context are not re-entrant;
+ *   - descriptors are float32 [n,32,60] (channel-major, group element fastest) exactly as the
+ *     reference's .npy cache stores them (test/extractor.py:60); keypoints are float64 [n,3].
+ */
+#ifndef ROREG_B200_H
+#define ROREG_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ROREG_F 32          /* descriptor channels            */
+#define ROREG_G 60          /* icosahedral group order        */
+#define ROREG_NEI 13        /* group-conv neighbourhood size  */
+
+typedef enum {
+  ROREG_OK = 0,
+  ROREG_ERR_ARG = -1,        /* bad argument                                     */
+  ROREG_ERR_CUDA = -2,       /* CUDA runtime error (see roreg_last_error)        */
+  ROREG_ERR_NOMEM = -3,      /* workspace allocation failed                      */
+  ROREG_ERR_UNSUPPORTED = -4 /* size outside the compiled limits                 */
+} roreg_status;
+
+typedef struct roreg_ctx roreg_ctx;
+
+int roreg_version(void);
+/* perm60x60: utils/group_related/60_60.npy as int32 (P[a][b] = idx(R_b R_a));  nei60x13:
+ * Nei_Index_in_SO3_ordered_13.npy as int32;  rot60x3x3: Rotation.npy float64.  HOST pointers. */
+int roreg_ctx_create(int device, const int32_t* perm60x60_host, const int32_t* nei60x13_host,
+                     const double* rot60x3x3_host, roreg_ctx** out);
+int roreg_ctx_destroy(roreg_ctx* ctx);
+const char* roreg_last_error(roreg_ctx* ctx);
+/* number of kernel launches issued through this context since creation (bench.py gpu_launches) */
+int64_t roreg_launch_count(roreg_ctx* ctx);
+
+/* ---- a13  test/matcher.py:69-72 (normalise=1) / network/rot_coh_match.py:346-347 (normalise=0)
+ * out[i,:] = mean_g eqv[sample[i],:,g]  (then x/(||x||+1e-5)).  sample may be NULL (identity).      */
+int roreg_inv_pool(roreg_ctx* ctx, const float* eqv, const int32_t* sample, int n_out, int normalise,
+                   float* out, void* stream);
+
+/* ---- a15  utils/knn_search.py:138-162  modified_knn_matcher.__call__(target, source):
+ * for every SOURCE row the k nearest TARGET rows under d = sqrt(sum (a-b)^2 + 1e-7) (difference form,
+ * float32), ascending, ties -> lower index.  target [n,f], source [m,f] row-major, f <= 32, k <= 16.  */
+int roreg_knn(roreg_ctx* ctx, const float* target, int n, const float* source, int m, int f, int k,
+              float* dist, int32_t* idx, void* stream);
+
+/* ---- a13  test/matcher.py:94-106: 1-NN both ways on [n0,32] / [n1,32] invariant features + the mutual
+ * check; matches come out in increasing row of f0 as (row in f0, row in f1).  n_matches: device int32[1].
+ * nn01 [n0] / nn10 [n1] optional outputs (may be NULL).  mode 0 = float32 difference form (reference
+ * arithmetic), mode 1 = tensor-core Gram form (3xTF32).                                               */
+int roreg_mutual_match(roreg_ctx* ctx, const float* f0, int n0, const float* f1, int n1, int mode,
+                       int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream);
+
+/* ---- a4 / a5  equivariant correlation on K (X row, Y row) pairs.
+ * variant 1: test/estimator.py:85-89 Batch_Des2R_torch  cor[a] = sum_{f,g} X[f,P[a,g]] Y[f,g]
+ * variant 2: network/rot_coh_match.py:158-163 R-indicator  cor[h] = sum_{f,g} X[f,P[g,h]] Y[f,g]
+ * X,Y: descriptor arrays [*,32,60]; idxX/idxY: int32 row indices [K] (NULL = 0..K-1).
+ * cor_out [K,60] float32 and argmax_out [K] int32 (first maximal index) are each optional.           */
+int roreg_group_corr(roreg_ctx* ctx, const float* X, const int32_t* idxX, const float* Y,
+                     const int32_t* idxY, int K, int variant, float* cor_out, int32_t* argmax_out,
+                     void* stream);
+
+/* ---- a17  test/estimator.py:349-366 + utils/r_eval.py:90-106:
+ * R = quat2mat(q)(float32 products) @ float32(Rgroup[pre_idx]),  t = key0 - key1 @ R^T  -> [K,3,4] f64 */
+int roreg_hypotheses_from_quat(roreg_ctx* ctx, const float* quat, const int32_t* pre_idx,
+                               const double* keys0_m, const double* keys1_m, int K, double* trans,
+                               void* stream);
+
+/* ---- a18  test/estimator.py:377-382,426-436  one-shot RANSAC: overlap[h] = sum_i s_i [|k0_i - T_h k1_i|^2
+ * < ird^2] / K for h = 0..H-1 with T_h = trans[order[h]] (order NULL = identity); best = first maximum
+ * under strict '>' starting from 0 (best_id = -1 if every overlap is 0).  scores: float32 (scores_f64=0)
+ * or float64 (=1).  overlaps [H] optional.  best_id int32[1], best_overlap float64[1] on the device.   */
+int roreg_ransac_oneshot(roreg_ctx* ctx, const double* k0, const double* k1, const void* scores,
+                         int scores_f64, int K, const double* trans, const int32_t* order, int H,
+                         double ird, double* overlaps, int32_t* best_id, double* best_overlap,
+                         void* stream);
+
+/* ---- a19  test/estimator.py:28-72 refiner.Refine_trans applied at radius ird*2 then ird
+ * (:438-439): weighted Kabsch on the inliers, R = U V^T without reflection fix.  T_in: [3,4] device
+ * pointer, or, if T_index != NULL, trans[order[*T_index]] as in roreg_ransac_oneshot.  T_out [4,4];
+ * inlier_mask [K] uint8 optional = inliers of T_out's predecessor at radius ird (the set the last
+ * Kabsch used).                                                                                      */
+int roreg_refine(roreg_ctx* ctx, const double* k0, const double* k1, const void* scores, int scores_f64,
+                 int K, const double* T_in, const int32_t* order, const int32_t* T_index, double ird,
+                 double* T_out, uint8_t* inlier_mask, void* stream);
+
+/* ---- a19  one refiner.Refine_trans call (test/estimator.py:60-72) at the given radius; T_in [3,4].
+ * inlier_mask [K] optional = the inliers of T_in at `radius`.                                           */
+int roreg_refine_once(roreg_ctx* ctx, const double* k0, const double* k1, const void* scores, int scores_f64,
+                      int K, const double* T_in, double radius, double* T_out, uint8_t* inlier_mask,
+                      void* stream);
+
+/* ---- a20  test/estimator.py:139-147 Threepps2Tran on device, proper-rotation branch (see DESIGN.md
+ * "rank-2 Kabsch"): triplets [H,3] int32 index the K_sel selected matches.  -> trans [H,3,4]          */
+int roreg_kabsch3(roreg_ctx* ctx, const double* k0_sel, const double* k1_sel, const int32_t* triplets,
+                  int H, double* trans, void* stream);
+
+/* ---- batched engine: B independent pairs per call (the throughput path bench.py times) ------------
+ * Clouds live in one arena: desc [n_clouds][n][32][60] float32, keys [n_clouds][n][3] float64.
+ * pair_cloud [B][2] int32 = (cloud id0, cloud id1).  sample [B][2][keynum] int32 or NULL (identity,
+ * keynum = n).  Pipeline = mutual matcher -> Des2R -> (yohoc | yohoo-with-given-hypotheses) -> refine. */
+typedef struct {
+  int32_t n_clouds, n, keynum, B;
+  const float* desc;
+  const double* keys;
+  const int32_t* pair_cloud;
+  const int32_t* sample;
+  int32_t nn_mode;            /* roreg_mutual_match mode                                            */
+  int32_t estimator;          /* 0 = yohoc (coarse-rotation-guided), 1 = yohoo (hypotheses given)   */
+  int32_t max_iter;           /* RANSAC iterations (hypotheses scored)                              */
+  double ird;                 /* inlier radius, cfg.ransac_ird                                      */
+  uint64_t seed;              /* device RNG seed (estimator 0 with triplets == NULL)                */
+  const int32_t* triplets;    /* [B][max_iter][3] host-drawn triplets (parity mode) or NULL         */
+  const double* hyp_host_svd; /* [B][max_iter][3][4] hypotheses computed by the caller or NULL      */
+  /* outputs */
+  int32_t* matches;           /* [B][keynum][2] original keypoint indices (id0, id1)                */
+  int32_t* n_matches;         /* [B]                                                                */
+  int32_t* dr_index;          /* [B][keynum]                                                        */
+  double* poses;              /* [B][4][4]                                                          */
+  int32_t* recall;            /* [B] index (yohoo: 0-based, yohoc: 1-based) of the winning hypothesis */
+  double* best_overlap;       /* [B]                                                                */
+} roreg_batch;
+
+int roreg_register_batch(roreg_ctx* ctx, const roreg_batch* batch, void* stream);
+
+/* Per-stage device timing of the last roreg_register_batch call (measurement hook for bench.py; events are
+ * recorded on the call's stream).  Stages: 0 inv_pool, 1 nn (both directions), 2 mutual compaction,
+ * 3 group correlation (Des2R), 4 hypothesis generation, 5 scoring + selection, 6 refine.
+ * roreg_get_stage_ms synchronises on the last event and writes ROREG_N_STAGES floats (milliseconds). */
+#define ROREG_N_STAGES 7
+int roreg_set_timing(roreg_ctx* ctx, int enable);
+int roreg_get_stage_ms(roreg_ctx* ctx, float* ms_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

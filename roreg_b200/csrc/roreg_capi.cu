@@ -1,0 +1,306 @@
+// roreg_capi.cu - extern "C" entry points of libroreg_b200.so (see include/roreg_b200.h).
+#include "common.cuh"
+#include "kernels_match.cuh"
+#include "kernels_corr.cuh"
+#include "kernels_ransac.cuh"
+#include "kernels_nn_tc.cuh"
+
+using namespace roreg;
+
+extern "C" {
+
+int roreg_version(void) { return 100; }
+
+int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const double* rot, roreg_ctx** out) {
+  if (!perm || !nei || !rot || !out) return ROREG_ERR_ARG;
+  roreg_ctx* c = new roreg_ctx();
+  memset(c, 0, sizeof(*c));
+  c->device = device;
+  *out = c;
+  RR_CUDA(c, cudaSetDevice(device));
+  cudaDeviceProp prop;
+  RR_CUDA(c, cudaGetDeviceProperties(&prop, device));
+  c->sm_count = prop.multiProcessorCount;
+  uint8_t p8[3600], pT8[3600];
+  float r32[540];
+  for (int a = 0; a < 60; ++a)
+    for (int g = 0; g < 60; ++g) {
+      const int v = perm[a * 60 + g];
+      if (v < 0 || v >= 60) { snprintf(c->err, sizeof(c->err), "perm table entry out of range"); return ROREG_ERR_ARG; }
+      p8[a * 60 + g] = (uint8_t)v;
+      pT8[g * 60 + a] = (uint8_t)v;       // pT8[h][g] = P[g][h]
+    }
+  for (int i = 0; i < 540; ++i) r32[i] = (float)rot[i];
+  RR_CUDA(c, cudaMalloc(&c->d_perm8, 3600));
+  RR_CUDA(c, cudaMalloc(&c->d_permT8, 3600));
+  RR_CUDA(c, cudaMalloc(&c->d_nei, 60 * 13 * sizeof(int32_t)));
+  RR_CUDA(c, cudaMalloc(&c->d_rot32, 540 * sizeof(float)));
+  RR_CUDA(c, cudaMalloc(&c->d_rot64, 540 * sizeof(double)));
+  RR_CUDA(c, cudaMemcpy(c->d_perm8, p8, 3600, cudaMemcpyHostToDevice));
+  RR_CUDA(c, cudaMemcpy(c->d_permT8, pT8, 3600, cudaMemcpyHostToDevice));
+  RR_CUDA(c, cudaMemcpy(c->d_nei, nei, 60 * 13 * sizeof(int32_t), cudaMemcpyHostToDevice));
+  RR_CUDA(c, cudaMemcpy(c->d_rot32, r32, sizeof(r32), cudaMemcpyHostToDevice));
+  RR_CUDA(c, cudaMemcpy(c->d_rot64, rot, 540 * sizeof(double), cudaMemcpyHostToDevice));
+  return ROREG_OK;
+}
+
+int roreg_ctx_destroy(roreg_ctx* c) {
+  if (!c) return ROREG_ERR_ARG;
+  cudaSetDevice(c->device);
+  cudaDeviceSynchronize();
+  if (c->ev[0]) for (int i = 0; i <= ROREG_N_STAGES; ++i) cudaEventDestroy(c->ev[i]);
+  cudaFree(c->d_perm8); cudaFree(c->d_permT8); cudaFree(c->d_nei); cudaFree(c->d_rot32); cudaFree(c->d_rot64);
+  if (c->ws) cudaFree(c->ws);
+  delete c;
+  return ROREG_OK;
+}
+
+int roreg_set_timing(roreg_ctx* c, int enable) {
+  if (!c) return ROREG_ERR_ARG;
+  if (enable && !c->ev[0])
+    for (int i = 0; i <= ROREG_N_STAGES; ++i) RR_CUDA(c, cudaEventCreate(&c->ev[i]));
+  c->timing = enable; c->ev_valid = 0;
+  return ROREG_OK;
+}
+
+int roreg_get_stage_ms(roreg_ctx* c, float* ms) {
+  RR_ARG(c, ms != nullptr);
+  if (!c->timing || !c->ev_valid) { snprintf(c->err, sizeof(c->err), "no timed batch call recorded"); return ROREG_ERR_ARG; }
+  RR_CUDA(c, cudaEventSynchronize(c->ev[ROREG_N_STAGES]));
+  for (int i = 0; i < ROREG_N_STAGES; ++i) RR_CUDA(c, cudaEventElapsedTime(&ms[i], c->ev[i], c->ev[i + 1]));
+  return ROREG_OK;
+}
+
+const char* roreg_last_error(roreg_ctx* c) { return c ? c->err : "null context"; }
+int64_t roreg_launch_count(roreg_ctx* c) { return c ? c->launches : -1; }
+
+// ------------------------------------------------------------------------------------------------
+int roreg_inv_pool(roreg_ctx* c, const float* eqv, const int32_t* sample, int n_out, int normalise,
+                   float* out, void* stream) {
+  RR_ARG(c, eqv && out && n_out >= 0);
+  if (n_out == 0) return ROREG_OK;
+  PoolArgs a{eqv, nullptr, sample, 0, n_out, n_out, normalise, out};
+  inv_pool_kernel<<<(n_out + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+static int launch_nn(roreg_ctx* c, int mode, const float* src, const float* tgt, long long src_ps, long long tgt_ps,
+                     int n_src, int n_tgt, int32_t* out_idx, float* out_dist, long long out_ps, int B, cudaStream_t st) {
+  if (n_src == 0) return ROREG_OK;
+  NNArgs a{src, tgt, src_ps, tgt_ps, n_src, n_tgt, out_idx, out_dist, out_ps};
+  if (mode == 1) {
+    int rc = nn_tc_launch(c, a, B, st);
+    if (rc != ROREG_OK) return rc;
+  } else {
+    nn_diff_kernel<<<dim3((n_src + 63) / 64, B), 256, 0, st>>>(a);
+  }
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_knn(roreg_ctx* c, const float* target, int n, const float* source, int m, int f, int k,
+              float* dist, int32_t* idx, void* stream) {
+  RR_ARG(c, target && source && idx && dist);
+  RR_ARG(c, n >= 1 && m >= 0 && f >= 1 && f <= 32 && k >= 1 && k <= 16 && k <= n);
+  if (m == 0) return ROREG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (f == 32 && k == 1) return launch_nn(c, 0, source, target, 0, 0, m, n, idx, dist, 0, 1, st);
+  knn_small_kernel<16><<<(m + 127) / 128, 128, 128 * f * sizeof(float), st>>>(target, n, source, m, f, k, dist, idx);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, int n1, int mode,
+                       int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream) {
+  RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode == 0 || mode == 1));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * n0) + rr_align(sizeof(int32_t) * n1) + 4096);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  int32_t* w01 = nn01 ? nn01 : ar.take<int32_t>(n0);
+  int32_t* w10 = nn10 ? nn10 : ar.take<int32_t>(n1);
+  if ((rc = launch_nn(c, mode, f0, f1, 0, 0, n0, n1, w01, nullptr, 0, 1, st))) return rc;   // KNN(feats1, feats0): rows of cloud0 search cloud1
+  if ((rc = launch_nn(c, mode, f1, f0, 0, 0, n1, n0, w10, nullptr, 0, 1, st))) return rc;
+  CompactArgs ca{w01, w10, n0, n1, 0, nullptr, 0, matches, n0 < n1 ? n0 : n1, n_matches};
+  mutual_compact_kernel<<<1, 1024, 0, st>>>(ca);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_group_corr(roreg_ctx* c, const float* X, const int32_t* idxX, const float* Y, const int32_t* idxY,
+                     int K, int variant, float* cor_out, int32_t* argmax_out, void* stream) {
+  RR_ARG(c, X && Y && K >= 0 && (variant == 1 || variant == 2) && (cor_out || argmax_out));
+  if (K == 0) return ROREG_OK;
+  CorrArgs a{};
+  a.X = X; a.Y = Y; a.idxX = idxX; a.idxY = idxY; a.idx_stride = 1; a.pair_cloud = nullptr; a.n = 0;
+  a.n_matches = nullptr; a.K = K; a.B = 1; a.tab = (variant == 1) ? c->d_perm8 : c->d_permT8;
+  a.cor_out = cor_out; a.argmax_out = argmax_out;
+  const int grid = K < c->sm_count * 8 ? K : c->sm_count * 8;
+  group_corr_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_hypotheses_from_quat(roreg_ctx* c, const float* quat, const int32_t* pre_idx, const double* k0,
+                               const double* k1, int K, double* trans, void* stream) {
+  RR_ARG(c, quat && pre_idx && k0 && k1 && trans && K >= 0);
+  if (K == 0) return ROREG_OK;
+  hyp_from_quat_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(quat, pre_idx, k0, k1, K, c->d_rot32, trans);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+static MatchView single_view(const double* k0, const double* k1, const void* scores, int scores_f64, int K) {
+  MatchView v{};
+  v.keys0 = k0; v.keys1 = k1; v.pair_cloud = nullptr; v.n = 0; v.matches = nullptr; v.cap = K;
+  v.n_matches = nullptr; v.K = K; v.scores = scores; v.scores_f64 = scores_f64; v.scores_pair_stride = 0;
+  return v;
+}
+
+static int score_and_select(roreg_ctx* c, const MatchView& mv, int cap, const double* hyps, long long hyp_ps,
+                            const int32_t* order, const int32_t* n_hyp, int H, double ird, double* partial,
+                            double* overlaps, int32_t* best_id, double* best_overlap, int B, cudaStream_t st) {
+  const int tiles = (cap + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
+  ScoreArgs sa{mv, hyps, hyp_ps, order, n_hyp, H, ird * ird, partial, tiles};
+  ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
+  RR_LAUNCH_CHECK(c);
+  SelectArgs se{partial, tiles, H, mv.n_matches, mv.K, overlaps, best_id, best_overlap};
+  ransac_select_kernel<<<B, 256, 0, st>>>(se);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_ransac_oneshot(roreg_ctx* c, const double* k0, const double* k1, const void* scores, int scores_f64,
+                         int K, const double* trans, const int32_t* order, int H, double ird, double* overlaps,
+                         int32_t* best_id, double* best_overlap, void* stream) {
+  RR_ARG(c, k0 && k1 && trans && best_id && best_overlap && K >= 1 && H >= 1 && ird > 0);
+  const int tiles = (K + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
+  int rc = rr_ws_reserve(c, rr_align(sizeof(double) * (size_t)tiles * H) + 4096);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  double* partial = ar.take<double>((size_t)tiles * H);
+  MatchView mv = single_view(k0, k1, scores, scores_f64, K);
+  return score_and_select(c, mv, K, trans, 0, order, nullptr, H, ird, partial, overlaps, best_id, best_overlap, 1,
+                          (cudaStream_t)stream);
+}
+
+int roreg_refine(roreg_ctx* c, const double* k0, const double* k1, const void* scores, int scores_f64, int K,
+                 const double* T_in, const int32_t* order, const int32_t* T_index, double ird, double* T_out,
+                 uint8_t* inlier_mask, void* stream) {
+  RR_ARG(c, k0 && k1 && T_in && T_out && K >= 1 && ird > 0);
+  RefineArgs a{};
+  a.mv = single_view(k0, k1, scores, scores_f64, K);
+  if (T_index) { a.T_in = nullptr; a.hyps = T_in; a.hyp_pair_stride = 0; a.order = order; a.best_id = T_index; }
+  else { a.T_in = T_in; a.T_pair_stride = 0; }
+  a.rad0 = ird * 2.0; a.rad1 = ird; a.rounds = 2; a.T_out = T_out; a.inlier_mask = inlier_mask; a.mask_stride = K;
+  refine_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_refine_once(roreg_ctx* c, const double* k0, const double* k1, const void* scores, int scores_f64, int K,
+                      const double* T_in, double radius, double* T_out, uint8_t* inlier_mask, void* stream) {
+  RR_ARG(c, k0 && k1 && T_in && T_out && K >= 1 && radius > 0);
+  RefineArgs a{};
+  a.mv = single_view(k0, k1, scores, scores_f64, K);
+  a.T_in = T_in; a.T_pair_stride = 0;
+  a.rad0 = radius; a.rad1 = radius; a.rounds = 1; a.T_out = T_out; a.inlier_mask = inlier_mask; a.mask_stride = K;
+  refine_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_kabsch3(roreg_ctx* c, const double* k0s, const double* k1s, const int32_t* triplets, int H,
+                  double* trans, void* stream) {
+  RR_ARG(c, k0s && k1s && triplets && trans && H >= 0);
+  if (H == 0) return ROREG_OK;
+  kabsch3_kernel<<<(H + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k0s, k1s, triplets, H, trans);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched engine
+// ------------------------------------------------------------------------------------------------
+int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
+  RR_ARG(c, b && b->desc && b->keys && b->pair_cloud && b->matches && b->n_matches && b->dr_index && b->poses &&
+                b->recall && b->best_overlap);
+  RR_ARG(c, b->B >= 1 && b->n >= 1 && b->keynum >= 1 && b->keynum <= b->n && b->max_iter >= 1 && b->ird > 0);
+  RR_ARG(c, b->sample || b->keynum == b->n);
+  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd));
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = b->B, S = b->keynum, H = b->max_iter;
+  const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
+  size_t need = rr_align(sizeof(float) * (size_t)B * 2 * S * RR_F) + 2 * rr_align(sizeof(int32_t) * (size_t)B * S) +
+                rr_align(sizeof(double) * (size_t)B * H * 12) + rr_align(sizeof(double) * (size_t)B * tiles * H) +
+                rr_align(sizeof(int32_t) * (size_t)B * S) + 4 * rr_align(sizeof(int32_t) * (size_t)B) + 8192;
+  int rc = rr_ws_reserve(c, need);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  float* inv = ar.take<float>((size_t)B * 2 * S * RR_F);
+  int32_t* nn01 = ar.take<int32_t>((size_t)B * S);
+  int32_t* nn10 = ar.take<int32_t>((size_t)B * S);
+  double* hyps = ar.take<double>((size_t)B * H * 12);
+  double* partial = ar.take<double>((size_t)B * tiles * H);
+  int32_t* scratch = ar.take<int32_t>((size_t)B * S);
+  int32_t* n_hyp = ar.take<int32_t>(B);
+
+#define RR_MARK(i) do { if (c->timing) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); } while (0)
+  RR_MARK(0);
+  // 1. invariant pooling + normalisation of both sides of every pair  (test/matcher.py:69-72)
+  PoolArgs pa{b->desc, b->pair_cloud, b->sample, b->n, S, B * 2 * S, 1, inv};
+  inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
+  RR_LAUNCH_CHECK(c);
+  RR_MARK(1);
+  // 2. 1-NN both ways  (test/matcher.py:94-97)
+  const long long ps = 2LL * S * RR_F;
+  if ((rc = launch_nn(c, b->nn_mode, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;
+  if ((rc = launch_nn(c, b->nn_mode, inv + (size_t)S * RR_F, inv, ps, ps, S, S, nn10, nullptr, S, B, st))) return rc;
+  RR_MARK(2);
+  // 3. mutual check, ordered compaction  (test/matcher.py:98-107)
+  CompactArgs ca{nn01, nn10, S, S, S, b->sample, S, b->matches, S, b->n_matches};
+  mutual_compact_kernel<<<B, 1024, 0, st>>>(ca);
+  RR_LAUNCH_CHECK(c);
+  RR_MARK(3);
+  // 4. coarse rotation of every match  (test/estimator.py:105-111: X = cloud id1, Y = cloud id0)
+  CorrArgs co{};
+  co.X = b->desc; co.Y = b->desc; co.idxX = b->matches + 1; co.idxY = b->matches; co.idx_stride = 2;
+  co.pair_cloud = b->pair_cloud; co.n = b->n; co.n_matches = b->n_matches; co.K = S; co.B = B;
+  co.tab = c->d_perm8; co.cor_out = nullptr; co.argmax_out = b->dr_index;
+  {
+    const long long total = (long long)B * S;
+    const int grid = (int)(total < (long long)c->sm_count * 8 ? total : (long long)c->sm_count * 8);
+    group_corr_kernel<<<grid, 128, 0, st>>>(co);
+    RR_LAUNCH_CHECK(c);
+  }
+  RR_MARK(4);
+  // 5. hypotheses
+  MatchView mv{};
+  mv.keys0 = b->keys; mv.keys1 = b->keys; mv.pair_cloud = b->pair_cloud; mv.n = b->n; mv.matches = b->matches;
+  mv.cap = S; mv.n_matches = b->n_matches; mv.K = S; mv.scores = nullptr; mv.scores_f64 = 0; mv.scores_pair_stride = 0;
+  const double* hyp_src = hyps;
+  const int32_t* n_hyp_src = n_hyp;
+  if (b->hyp_host_svd) { hyp_src = b->hyp_host_svd; n_hyp_src = nullptr; }
+  else {
+    CoarseArgs cg{mv, b->dr_index, S, b->triplets, H, b->seed, hyps, n_hyp, scratch};
+    coarse_hyp_kernel<<<B, 256, 0, st>>>(cg);
+    RR_LAUNCH_CHECK(c);
+  }
+  RR_MARK(5);
+  // 6. score every hypothesis on all matches, keep the first best  (test/estimator.py:149-154,232-238 / :426-436)
+  if ((rc = score_and_select(c, mv, S, hyp_src, (long long)H * 12, nullptr, n_hyp_src, H, b->ird, partial, nullptr,
+                             b->recall, b->best_overlap, B, st))) return rc;
+  RR_MARK(6);
+  // 7. refine twice  (test/estimator.py:240-241 / :438-439)
+  RefineArgs ra{};
+  ra.mv = mv; ra.T_in = nullptr; ra.hyps = hyp_src; ra.hyp_pair_stride = (long long)H * 12; ra.order = nullptr;
+  ra.best_id = b->recall; ra.rad0 = b->ird * 2.0; ra.rad1 = b->ird; ra.rounds = 2; ra.T_out = b->poses; ra.inlier_mask = nullptr; ra.mask_stride = S;
+  refine_kernel<<<B, 512, 0, st>>>(ra);
+  RR_LAUNCH_CHECK(c);
+  RR_MARK(7);
+  if (c->timing) c->ev_valid = 1;
+  return ROREG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,93 @@
+"""Drop-in parity at the plugin boundary: the mirrors of test/{matcher,estimator}.py are run through
+their reference signatures against a cache directory and the files they write are compared with the
+golden fixtures recorded from the UNMODIFIED reference (tests/golden/make_golden.py)."""
+import os
+import types
+import numpy as np
+import pytest
+from conftest import load_golden
+from roreg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _cfg(cache, **kw):
+    c = types.SimpleNamespace(output_cache_fn=cache, model_fn="", SO3_related_files=None, backbone="FCGF",
+                              bs_GF=1250, bs_ET=1000, RD=False, RM=False, match_n=0.5, ransac_ird=0.1,
+                              keynum=5000, max_iter=1000)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.mark.parametrize("name", ["s256", "s700"])
+def test_plugins_reproduce_reference_files(name, tmp_path):
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden(name)
+    ds = synth.SynthDataset(seeds, n=n, name=f"synth/{name}", max_res_deg=2.0)
+    cache = str(tmp_path / "cache")
+    ds.write_cache(cache)
+    cfg = _cfg(cache)
+    base = f"{cache}/{ds.name}/match_{keynum}"
+    # registries and signatures are the reference's (test/__init__.py:6-22)
+    assert set(rt.name2matcher) == {"matmul", "yoho_mat"} and set(rt.name2estimator) == {"yohoc", "yohoo"}
+    # ---- matcher: same global-RNG consumption as the reference run that produced the fixture
+    np.random.seed(1234)
+    rt.name2matcher["matmul"](cfg).run(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        m = np.load(f"{base}/{id0}-{id1}.npy"); s = np.load(f"{base}/scores/{id0}-{id1}.npy")
+        assert m.dtype == np.int64 and np.array_equal(m, z[f"match_{id0}-{id1}"])
+        assert s.dtype == np.float64 and np.array_equal(s, z[f"scores_{id0}-{id1}"])
+    # ---- coarse rotation index
+    rt.extractor_dr_index(cfg).Rindex(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        d = np.load(f"{base}/DR_index/{id0}-{id1}.npy")
+        assert d.dtype == np.int64 and np.array_equal(d, z[f"dr_index_{id0}-{id1}"])
+    # ---- one-shot RANSAC on the reference's own Trans_pre (the ET network is outside this build)
+    os.makedirs(f"{base}/Trans_pre", exist_ok=True)
+    for (id0, id1) in ds.pair_ids:
+        np.save(f"{base}/Trans_pre/{id0}-{id1}.npy", z[f"trans_pre_{id0}-{id1}"])
+    np.random.seed(4321)
+    rt.yohoo_ransac(cfg).ransac(ds, keynum, max_iter)
+    for (id0, id1) in ds.pair_ids:
+        r = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoo_recall_{id0}-{id1}"])
+        assert np.abs(r["trans"] - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-9      # stated tolerance on poses: 1e-4
+    got = open(f"{base}/yohoo/{max_iter}iters/pre.log", "rb").read()
+    ref = bytes(z["pre_log_yohoo"])
+    assert len(got.splitlines()) == len(ref.splitlines())
+    for a, b in zip(got.decode().split(), ref.decode().split()):
+        assert abs(float(a) - float(b)) < 1e-9
+    # ---- yohoc, parity mode (host RNG + host LAPACK for the rank-2 Kabsch, device scoring/refine)
+    os.makedirs(f"{base}/yohoc/{max_iter}iters", exist_ok=True)
+    yc = rt.yohoc_ransac(cfg)
+    for pi, pair in enumerate(ds.pair_ids):
+        np.random.seed(777 + pi)
+        yc.ransac_once(ds, keynum, max_iter, pair)
+        id0, id1 = pair
+        r = np.load(f"{base}/yohoc/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoc_recall_{id0}-{id1}"])
+        assert np.abs(r["trans"] - z[f"yohoc_trans_{id0}-{id1}"]).max() < 1e-9
+
+
+def test_yohoc_run_device_mode(tmp_path):
+    """yohoc.run end to end (Rindex + ransac + pre.log) with device-side draws: poses agree with ground truth."""
+    import roreg_b200.test as rt
+    ds = synth.SynthDataset([61, 62], n=500, name="synth/dev")
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    cfg = _cfg(cache, yohoc_mode="device")
+    np.random.seed(9)
+    rt.mutual(cfg).run(ds, 500)
+    rt.yohoc(cfg).run(ds, 500, 400)
+    for pi, (id0, id1) in enumerate(ds.pair_ids):
+        r = np.load(f"{cache}/{ds.name}/match_500/yohoc/400iters/{id0}-{id1}.npz")
+        assert np.abs(r["trans"][:3] - ds.pairs[pi]["gt"]).max() < 5e-3
+    assert os.path.exists(f"{cache}/{ds.name}/match_500/yohoc/400iters/pre.log")
+
+
+def test_unbuilt_plugins_fail_loudly():
+    import roreg_b200.test as rt
+    with pytest.raises(NotImplementedError):
+        rt.yoho_mat(_cfg("/tmp"))
+    with pytest.raises(NotImplementedError):
+        rt.yoho_des(_cfg("/tmp")).run(None)

@@ -1,0 +1,306 @@
+"""GPU parity tests: every C-ABI entry point against the oracle on seeded inputs (sizes the oracle
+finishes in seconds), bit-exact for indices / masks outside the stated near-tie band, and to the
+tolerance written next to each float comparison."""
+import numpy as np
+import pytest
+import torch
+from oracle import roreg_oracle as O
+from roreg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TIE_EPS = 2e-6      # relative top-2 gap (float64 adjudicator) below which a float32 argmin may legitimately differ
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return synth.make_pair(101, n=1200, with_fcgf=True)
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+# ---------------------------------------------------------------------------------------- a13
+@pytest.mark.parametrize("normalise", [True, False])
+def test_inv_pool(ctx, pair, normalise):
+    eqv = ctx.dev(pair["feats0"])
+    got = _np(ctx.inv_pool(eqv, None, normalise))
+    ref = O.inv_pool(pair["feats0"], normalise)
+    assert np.abs(got - ref).max() < 2e-7           # float32 sum of 60 terms in a different order
+    rng = np.random.default_rng(0)
+    s = rng.permutation(1200)[:700].astype(np.int32)
+    got = _np(ctx.inv_pool(eqv, ctx.dev(s), normalise))
+    assert np.abs(got - ref[s]).max() < 2e-7
+
+
+def test_inv_pool_is_group_invariant(ctx, pair, tables):
+    """the mean over G is unchanged by a group permutation."""
+    x = pair["feats0"][:256]
+    a = ctx.inv_pool(ctx.dev(x)); b = ctx.inv_pool(ctx.dev(np.ascontiguousarray(x[:, :, tables.perm[17]])))
+    assert (a - b).abs().max().item() < 2e-7
+
+
+# ---------------------------------------------------------------------------------------- a15
+def _check_nn(idx, dist, target, source):
+    d_ref, i_ref = O.knn(target, source, 1)
+    i64, best, second = O.knn_f64(target, source)
+    bad = idx != i_ref[:, 0]
+    # any disagreement must sit inside the near-tie band of the float64 adjudicator
+    assert np.all((second[bad] - best[bad]) <= TIE_EPS * np.maximum(best[bad], 1e-12)), int(bad.sum())
+    assert bad.mean() < 0.01
+    if dist is not None:
+        assert np.abs(dist[~bad] - d_ref[~bad, 0]).max() < 1e-6     # stated tolerance on descriptor distances: 1e-4
+    return int(bad.sum())
+
+
+def test_knn_k1_f32(ctx, pair):
+    f0 = O.inv_pool(pair["feats0"]); f1 = O.inv_pool(pair["feats1"])
+    d, i = ctx.knn(ctx.dev(f1), ctx.dev(f0), 1)
+    _check_nn(_np(i)[:, 0], _np(d)[:, 0], f1, f0)
+    # ragged: source and target sizes differ and are not multiples of the tile
+    d, i = ctx.knn(ctx.dev(f1[:777]), ctx.dev(f0[:131]), 1)
+    _check_nn(_np(i)[:, 0], _np(d)[:, 0], f1[:777], f0[:131])
+
+
+def test_knn_duplicates_pick_first_index(ctx):
+    """torch.min(dim) returns the first minimal index: exact duplicates in the target must resolve to the lower row."""
+    rng = np.random.default_rng(3)
+    t = rng.standard_normal((300, 32)).astype(np.float32)
+    t[200] = t[17]; t[250] = t[17]
+    s = t[[17, 200, 250, 5]].copy()
+    _, i = ctx.knn(ctx.dev(t), ctx.dev(s), 1)
+    assert _np(i)[:, 0].tolist() == [17, 17, 17, 5]
+
+
+def test_knn_k5_xyz(ctx, pair):
+    kf = pair["keys0"].astype(np.float32)
+    d, i = ctx.knn(ctx.dev(kf), ctx.dev(kf), 5)
+    d_ref, i_ref = O.knn(kf, kf, 5)
+    agree = (_np(i) == i_ref).mean()
+    assert agree > 0.999
+    assert np.abs(_np(d) - d_ref).max() < 1e-6
+    assert (_np(i)[:, 0] == np.arange(kf.shape[0])).all()       # self is the nearest (distance sqrt(1e-7))
+
+
+def test_mutual_match_ordered_and_equal_to_oracle(ctx, pair):
+    f0 = O.inv_pool(pair["feats0"]); f1 = O.inv_pool(pair["feats1"])
+    m, cnt, nn01, nn10 = ctx.mutual_match(ctx.dev(f0), ctx.dev(f1), 0)
+    k = int(cnt.item()); m = _np(m)[:k]
+    ref, r01, r10 = O.mutual_matches(f0, f1)
+    nbad = _check_nn(_np(nn01), None, f1, f0) + _check_nn(_np(nn10), None, f0, f1)
+    if nbad == 0:
+        assert np.array_equal(m, ref)
+    assert (np.diff(m[:, 0]) > 0).all()                        # rows come out in increasing index of cloud 0
+    assert (_np(nn10)[m[:, 1]] == m[:, 0]).all() and (_np(nn01)[m[:, 0]] == m[:, 1]).all()
+
+
+# ---------------------------------------------------------------------------------------- a4 / a5
+@pytest.mark.parametrize("variant", [1, 2])
+def test_group_corr(ctx, pair, tables, variant):
+    rng = np.random.default_rng(4)
+    K = 500
+    ix = rng.integers(0, 1200, K).astype(np.int32); iy = rng.integers(0, 1200, K).astype(np.int32)
+    X = pair["feats1"]; Y = pair["feats0"]
+    cor, am = ctx.group_corr(ctx.dev(X), ctx.dev(Y), ctx.dev(ix), ctx.dev(iy), variant)
+    f = O.group_corr_v1 if variant == 1 else O.group_corr_v2
+    ref64 = f(X[ix], Y[iy], tables.perm, np.float64)
+    assert np.abs(_np(cor) - ref64).max() < 1e-5            # |cor| <= 60; stated tolerance 1e-4
+    top2 = np.sort(ref64, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 1e-5
+    assert (_np(am)[clear] == np.argmax(ref64, axis=1)[clear]).all()
+    ref32 = f(X[ix], Y[iy], tables.perm)
+    assert (_np(am) == np.argmax(ref32, axis=1)).mean() > 0.995
+
+
+def test_des2r_known_answers(ctx, tables):
+    """Des2R(X, X[:,:,P[a]]) = a ; Des2R(X[:,:,P[a]], X) = inv[a]."""
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((64, 32, 60)).astype(np.float32)
+    for a in (0, 1, 7, 33, 59):
+        Xa = np.ascontiguousarray(X[:, :, tables.perm[a]])
+        _, am = ctx.group_corr(ctx.dev(X), ctx.dev(Xa), variant=1, want_cor=False)
+        assert (_np(am) == a).all()
+        _, am = ctx.group_corr(ctx.dev(Xa), ctx.dev(X), variant=1, want_cor=False)
+        assert (_np(am) == tables.inv[a]).all()
+
+
+# ---------------------------------------------------------------------------------------- a17
+def test_hypotheses_from_quat(ctx, pair, tables):
+    rng = np.random.default_rng(6)
+    K = 400
+    q = rng.standard_normal((K, 4)).astype(np.float32); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    idx = rng.integers(0, 60, K).astype(np.int32)
+    k0 = pair["keys0"][:K]; k1 = pair["keys1"][:K]
+    got = _np(ctx.hypotheses_from_quat(ctx.dev(q), ctx.dev(idx), ctx.dev(k0, torch.float64), ctx.dev(k1, torch.float64)))
+    ref = O.hypotheses_from_quat(q, idx, k0, k1, tables.rot)
+    assert np.abs(got[:, :, :3] - ref[:, :, :3]).max() < 1e-15   # rotation part: exact float32 products, float64 sums of exact products
+    assert np.abs(got - ref).max() < 1e-14
+
+
+# ---------------------------------------------------------------------------------------- a18 / a19
+def _matched(pair):
+    m = pair["corr0"] >= 0
+    i0 = np.where(m)[0]; i1 = pair["corr0"][m]
+    rng = np.random.default_rng(7)
+    # add wrong correspondences so that the inlier test has something to reject
+    w0 = rng.integers(0, 1200, 300); w1 = rng.integers(0, 1200, 300)
+    i0 = np.concatenate([i0, w0]); i1 = np.concatenate([i1, w1])
+    p = rng.permutation(i0.shape[0])
+    return pair["keys0"][i0[p]], pair["keys1"][i1[p]]
+
+
+def _hyps(pair, H, rng):
+    Hs = np.concatenate([np.linalg.qr(rng.standard_normal((H, 3, 3)))[0], rng.standard_normal((H, 3, 1))], 2)
+    for j in range(0, H, 7):        # a family of near-correct hypotheses with different inlier counts
+        Hs[j] = pair["gt"]; Hs[j][:, 3] += rng.standard_normal(3) * 0.04
+    return np.ascontiguousarray(Hs)
+
+
+@pytest.mark.parametrize("scores_kind", ["ones_f64", "f32"])
+def test_ransac_oneshot_and_refine(ctx, pair, scores_kind):
+    rng = np.random.default_rng(8)
+    k0, k1 = _matched(pair)
+    K = k0.shape[0]; H = 333
+    Hs = _hyps(pair, H, rng)
+    order = rng.permutation(H)[:250].astype(np.int32)
+    sc = np.ones(K) if scores_kind == "ones_f64" else rng.random(K).astype(np.float32)
+    scd = ctx.dev(sc, torch.float64 if sc.dtype == np.float64 else torch.float32)
+    d0 = ctx.dev(k0, torch.float64); d1 = ctx.dev(k1, torch.float64); dH = ctx.dev(Hs, torch.float64)
+    best, bov, ov = ctx.ransac_oneshot(d0, d1, scd, dH, ctx.dev(order), 0.1, want_overlaps=True)
+    rb, rov, rovs = O.oneshot_ransac(k0, k1, sc.astype(np.float64), Hs[order], 0.1)
+    if scores_kind == "ones_f64":
+        assert np.array_equal(_np(ov), rovs)                   # integer inlier counts / K: exact
+    else:
+        assert np.abs(_np(ov) - rovs).max() < 1e-12
+    assert int(best.item()) == rb and abs(float(bov.item()) - rov) < 1e-12
+    # refine: two rounds from the winning hypothesis, inlier mask of the last round bit-exact
+    T, mask = ctx.refine(d0, d1, scd, dH, 0.1, order=ctx.dev(order), T_index=best, want_mask=True)
+    T1 = O.refine_once(k0, k1, Hs[order][rb], sc, 0.2)
+    Tr = O.refine_once(k0, k1, T1, sc, 0.1)
+    tol = 1e-9 if scores_kind == "ones_f64" else 2e-6          # float32 weights are normalised in float32 by the reference
+    assert np.abs(_np(T) - Tr).max() < tol
+    assert np.array_equal(_np(mask).astype(bool), O.inlier_mask(k0, k1, T1, 0.1))
+    # single round entry (refiner.Refine_trans)
+    T1g, m1 = ctx.refine_once(d0, d1, scd, ctx.dev(Hs[order][rb], torch.float64), 0.2, want_mask=True)
+    assert np.abs(_np(T1g) - T1).max() < tol
+    assert np.array_equal(_np(m1).astype(bool), O.inlier_mask(k0, k1, Hs[order][rb], 0.2))
+
+
+def test_ransac_planted_pose_known_answer(ctx, pair):
+    """a planted SE(3) among random hypotheses comes back at its position; refining exact
+    correspondences returns the planted pose."""
+    pr = synth.make_pair(3, n=900, sigma_xyz=0.0)
+    m = pr["corr0"] >= 0
+    k0 = pr["keys0"][m]; k1 = pr["keys1"][pr["corr0"][m]]
+    rng = np.random.default_rng(9)
+    Hs = np.concatenate([np.linalg.qr(rng.standard_normal((100, 3, 3)))[0], rng.standard_normal((100, 3, 1))], 2)
+    Hs[41] = pr["gt"]
+    d0 = ctx.dev(k0, torch.float64); d1 = ctx.dev(k1, torch.float64); dH = ctx.dev(np.ascontiguousarray(Hs), torch.float64)
+    best, bov, _ = ctx.ransac_oneshot(d0, d1, None, dH, None, 0.1)
+    assert int(best.item()) == 41 and float(bov.item()) == 1.0
+    T, _ = ctx.refine(d0, d1, None, dH, 0.1, T_index=best)
+    assert np.abs(_np(T)[:3] - pr["gt"]).max() < 1e-9
+
+
+def test_ransac_no_positive_overlap_returns_minus_one(ctx, pair):
+    k0, k1 = _matched(pair)
+    far = np.zeros((5, 3, 4)); far[:, :, :3] = np.eye(3); far[:, :, 3] = 1e3
+    best, bov, _ = ctx.ransac_oneshot(ctx.dev(k0, torch.float64), ctx.dev(k1, torch.float64), None, ctx.dev(far, torch.float64), None, 0.1)
+    assert int(best.item()) == -1 and float(bov.item()) == 0.0
+
+
+# ---------------------------------------------------------------------------------------- a20
+def test_kabsch3_proper_branch(ctx, pair):
+    k0, k1 = _matched(pair)
+    rng = np.random.default_rng(10)
+    trip = rng.integers(0, 600, (500, 3)).astype(np.int32)
+    got = _np(ctx.kabsch3(ctx.dev(k0, torch.float64), ctx.dev(k1, torch.float64), ctx.dev(trip)))
+    nproper = 0
+    for h in range(500):
+        ref = O.threepps2tran(k0[trip[h]], k1[trip[h]])
+        assert abs(np.linalg.det(got[h, :, :3]) - 1) < 1e-9
+        if len(set(trip[h].tolist())) == 3 and np.linalg.det(ref[:, :3]) > 0:
+            nproper += 1
+            assert np.abs(got[h] - ref).max() < 1e-8
+    assert nproper > 100
+
+
+# ---------------------------------------------------------------------------------------- batched engine
+def _oracle_pipeline(pr, tables, hyp=None, trip=None, ird=0.1):
+    pps, sc = O.mutual_run(pr["feats0"], pr["feats1"])
+    dr = O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm)
+    k0 = pr["keys0"][pps[:, 0]]; k1 = pr["keys1"][pps[:, 1]]
+    return pps, sc, dr, k0, k1
+
+
+def test_register_batch_parity_mode(ctx, tables):
+    """B = 3 pairs through the fused engine with host-LAPACK 3-point hypotheses: every stage equals the
+    oracle (= the reference's mutual -> Rindex -> yohoc path with the same draws)."""
+    seeds = [31, 32, 33]; n = 700; H = 150
+    prs = [synth.make_pair(s, n=n) for s in seeds]
+    desc = ctx.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+    keys = ctx.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+    pc = ctx.dev(np.array([[2 * i, 2 * i + 1] for i in range(3)], np.int32))
+    hyps = np.zeros((3, H, 3, 4)); stages = []
+    for i, pr in enumerate(prs):
+        pps, sc, dr, k0, k1 = _oracle_pipeline(pr, tables)
+        np.random.seed(50 + i)
+        draws, _, _ = O.yohoc_draws(dr, H)
+        hyps[i] = np.stack([O.threepps2tran(k0[d[1]], k1[d[1]]) for d in draws])
+        stages.append((pps, sc, dr, k0, k1))
+    out = ctx.register_batch(desc, keys, pc, max_iter=H, ird=0.1, hyps=ctx.dev(hyps, torch.float64))
+    torch.cuda.synchronize()
+    for i, (pps, sc, dr, k0, k1) in enumerate(stages):
+        k = int(out["n_matches"][i])
+        assert k == pps.shape[0]
+        assert np.array_equal(_np(out["matches"][i, :k]), pps)
+        assert np.array_equal(_np(out["dr_index"][i, :k]), dr)
+        best, bov, _ = O.oneshot_ransac(k0, k1, sc, hyps[i], 0.1)
+        assert int(out["recall"][i]) == best and abs(float(out["best_overlap"][i]) - bov) < 1e-12
+        T = O.refine(k0, k1, hyps[i][best], sc, 0.1)
+        assert np.abs(_np(out["poses"][i]) - T).max() < 1e-9
+        assert np.abs(T[:3] - prs[i]["gt"]).max() < 5e-3
+
+
+def test_register_batch_device_draws(ctx, tables):
+    """Device RNG + proper-rotation Kabsch: not the reference's random stream, so the check is the
+    domain property - the pose agrees with ground truth and with the oracle's refinement of the winning
+    hypothesis's inlier set."""
+    seeds = [41, 42]; n = 900
+    prs = [synth.make_pair(s, n=n) for s in seeds]
+    desc = ctx.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+    keys = ctx.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+    pc = ctx.dev(np.array([[0, 1], [2, 3]], np.int32))
+    out = ctx.register_batch(desc, keys, pc, max_iter=500, ird=0.1, seed=1234)
+    out2 = ctx.register_batch(desc, keys, pc, max_iter=500, ird=0.1, seed=1234)
+    torch.cuda.synchronize()
+    assert torch.equal(out["poses"], out2["poses"])            # deterministic for a given seed
+    for i, pr in enumerate(prs):
+        assert int(out["recall"][i]) >= 0
+        assert np.abs(_np(out["poses"][i])[:3] - pr["gt"]).max() < 5e-3
+
+
+def test_register_batch_with_sampling(ctx, tables):
+    """keynum < n with explicit sample index arrays (test/matcher.py:85-88): matches are reported in
+    ORIGINAL keypoint indices."""
+    pr = synth.make_pair(77, n=800)
+    rng = np.random.default_rng(11)
+    s0 = rng.permutation(800)[:500]; s1 = rng.permutation(800)[:500]
+    desc = ctx.dev(np.stack([pr["feats0"], pr["feats1"]]))
+    keys = ctx.dev(np.stack([pr["keys0"], pr["keys1"]]), torch.float64)
+    samp = ctx.dev(np.stack([s0, s1])[None].astype(np.int32))
+    out = ctx.register_batch(desc, keys, ctx.dev(np.array([[0, 1]], np.int32)), keynum=500, sample=samp, max_iter=300, seed=5)
+    torch.cuda.synchronize()
+    pps, _ = O.mutual_run(pr["feats0"], pr["feats1"], s0, s1)
+    k = int(out["n_matches"][0])
+    assert k == pps.shape[0] and np.array_equal(_np(out["matches"][0, :k]), pps)
+    assert np.array_equal(_np(out["dr_index"][0, :k]), O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm))

@@ -1,0 +1,52 @@
+"""Host build of roreg_b200/csrc/math3.cuh (the exact source the RANSAC / refine kernels compile)
+against NumPy/LAPACK: polar factor U V^T, proper 3-point Kabsch, quaternion x anchor product."""
+import ctypes
+import os
+import subprocess
+import numpy as np
+from oracle import roreg_oracle as O
+
+REPO = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+SRC = os.path.join(REPO, "roreg_b200", "csrc", "math3_host.cpp")
+SO = os.path.join(REPO, "roreg_b200", "csrc", "libmath3_host.so")
+dp = ctypes.POINTER(ctypes.c_double); fp = ctypes.POINTER(ctypes.c_float)
+
+
+def _lib():
+    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(SRC):
+        subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", SO, SRC])
+    return ctypes.CDLL(SO)
+
+
+def test_polar_factor_matches_lapack():
+    L = _lib(); rng = np.random.default_rng(0)
+    for i in range(500):
+        H = rng.standard_normal((3, 3)) * 10 ** rng.uniform(-3, 3)
+        U, S, VT = np.linalg.svd(H)
+        R = np.zeros((3, 3)); L.rr_host_polar_uvt(H.ctypes.data_as(dp), R.ctypes.data_as(dp))
+        if S[2] / S[0] > 1e-8:
+            assert np.abs(R - U @ VT).max() < 1e-7 / (S[2] / S[0]) * 1e-6 + 1e-12
+
+
+def test_three_point_transform_is_proper_branch_of_reference():
+    L = _lib(); rng = np.random.default_rng(1)
+    for i in range(500):
+        k1 = rng.random((3, 3)) * 3
+        Q = np.linalg.qr(rng.standard_normal((3, 3)))[0]
+        if np.linalg.det(Q) < 0: Q[:, 0] *= -1
+        k0 = np.ascontiguousarray(k1 @ Q.T + rng.standard_normal(3) + rng.standard_normal((3, 3)) * 0.01)
+        T = np.zeros((3, 4)); L.rr_host_three_point_transform(k0.ctypes.data_as(dp), k1.ctypes.data_as(dp), T.ctypes.data_as(dp))
+        Tr = O.threepps2tran(k0, k1)
+        assert abs(np.linalg.det(T[:, :3]) - 1) < 1e-9
+        if np.linalg.det(Tr[:, :3]) > 0:
+            assert np.abs(T - Tr).max() < 1e-9
+        assert np.abs(k1 @ T[:, :3].T + T[:, 3] - (k1 @ Tr[:, :3].T + Tr[:, 3])).max() < 1e-8
+
+
+def test_quat_times_anchor_bit_exact(tables):
+    L = _lib(); rng = np.random.default_rng(2)
+    for i in range(300):
+        q = rng.standard_normal(4).astype(np.float32); q /= np.linalg.norm(q)
+        Rg = np.ascontiguousarray(tables.rot[int(rng.integers(60))].astype(np.float32))
+        R = np.zeros((3, 3)); L.rr_host_quat_times_anchor(q.ctypes.data_as(fp), Rg.ctypes.data_as(fp), R.ctypes.data_as(dp))
+        assert np.array_equal(R, O.matrix_from_quaternion(q) @ Rg)
