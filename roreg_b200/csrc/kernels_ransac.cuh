@@ -87,62 +87,75 @@ struct CoarseArgs {
   double* hyps;                  // [B][H][12]
   int32_t* n_hyp;                // [B]
   int32_t* scratch;              // [B][cap] bucket-sorted match ids
+  int32_t* bucket;               // [B][128]: cnt[60] | start[61]  (written by coarse_bucket_kernel)
+  double* cdf;                   // [B][60]
 };
 
-__global__ void __launch_bounds__(256) coarse_hyp_kernel(CoarseArgs a) {
+// stage 1: per-pair histogram / cdf / bucket sort (one CTA per pair)
+__global__ void __launch_bounds__(256) coarse_bucket_kernel(CoarseArgs a) {
   __shared__ int cnt[60], start[61], fill[60];
-  __shared__ double cdf[60];
-  __shared__ int ok;
   const int p = blockIdx.x, tid = threadIdx.x;
   const int K = mv_count(a.mv, p);
   const int32_t* dr = a.dr_index + p * a.dr_pair_stride;
   int32_t* sorted = a.scratch + (long long)p * a.mv.cap;
+  if (tid < 60) { cnt[tid] = 0; fill[tid] = 0; }
+  __syncthreads();
+  for (int k = tid; k < K; k += 256) atomicAdd(&cnt[dr[k]], 1);
+  __syncthreads();
+  if (tid == 0) {
+    double tot = 0; int s = 0;
+    double c[60];
+    for (int r = 0; r < 60; ++r) {
+      start[r] = s; s += cnt[r];
+      double pr = 0;
+      if (cnt[r] >= 2) { const double num = (double)cnt[r] / 100.0; pr = num * (num - 0.01) * (num - 0.02); }
+      tot += pr; c[r] = tot;
+    }
+    start[60] = s;
+    for (int r = 0; r < 60; ++r) a.cdf[p * 60 + r] = (tot > 0) ? c[r] / tot : 0.0;
+    a.n_hyp[p] = (tot > 0) ? a.H : 0;
+  }
+  __syncthreads();
+  if (tid < 60) a.bucket[p * 128 + tid] = cnt[tid];
+  if (tid < 61) a.bucket[p * 128 + 60 + tid] = start[tid];
+  for (int k = tid; k < K; k += 256) { const int r = dr[k]; sorted[start[r] + atomicAdd(&fill[r], 1)] = k; }
+}
+
+// stage 2: one thread per hypothesis, grid = (ceil(H/64), B)
+__global__ void __launch_bounds__(64) coarse_hyp_kernel(CoarseArgs a) {
+  __shared__ int cnt[60], start[61];
+  __shared__ double cdf[60];
+  const int p = blockIdx.y, tid = threadIdx.x;
+  const int it = blockIdx.x * 64 + tid;
+  const int32_t* sorted = a.scratch + (long long)p * a.mv.cap;
   if (!a.triplets) {
-    if (tid < 60) { cnt[tid] = 0; fill[tid] = 0; }
-    __syncthreads();
-    for (int k = tid; k < K; k += 256) atomicAdd(&cnt[dr[k]], 1);
-    __syncthreads();
-    if (tid == 0) {
-      double tot = 0; int s = 0;
-      for (int r = 0; r < 60; ++r) {
-        start[r] = s; s += cnt[r];
-        double pr = 0;
-        if (cnt[r] >= 2) { const double num = (double)cnt[r] / 100.0; pr = num * (num - 0.01) * (num - 0.02); }
-        tot += pr; cdf[r] = tot;
-      }
-      start[60] = s;
-      ok = tot > 0;
-      if (tot > 0) for (int r = 0; r < 60; ++r) cdf[r] /= tot;
-    }
-    __syncthreads();
-    if (!ok) { if (tid == 0) a.n_hyp[p] = 0; return; }
-    for (int k = tid; k < K; k += 256) { const int r = dr[k]; sorted[start[r] + atomicAdd(&fill[r], 1)] = k; }
+    if (a.n_hyp[p] == 0) return;                       // degenerate pair: no bucket with >= 2 members
+    if (tid < 60) { cnt[tid] = a.bucket[p * 128 + tid]; cdf[tid] = a.cdf[p * 60 + tid]; }
+    if (tid < 61) start[tid] = a.bucket[p * 128 + 60 + tid];
     __syncthreads();
   }
-  if (tid == 0) a.n_hyp[p] = a.H;
-  for (int it = tid; it < a.H; it += 256) {
-    int idx[3];
-    if (a.triplets) {
-      const int32_t* t = a.triplets + ((long long)p * a.H + it) * 3;
-      idx[0] = t[0]; idx[1] = t[1]; idx[2] = t[2];
-    } else {
-      const double u = rr_u01(a.seed, p, it, 0);
-      int r = 0;
-      while (r < 59 && !(u < cdf[r])) ++r;
-      while (r > 0 && cnt[r] < 2) --r;              // guard against cdf round-off landing on an empty bucket
-      if (cnt[r] < 2) { for (r = 0; r < 59 && cnt[r] < 2; ++r) {} }
+  if (it >= a.H) return;
+  int idx[3];
+  if (a.triplets) {
+    const int32_t* t = a.triplets + ((long long)p * a.H + it) * 3;
+    idx[0] = t[0]; idx[1] = t[1]; idx[2] = t[2];
+  } else {
+    const double u = rr_u01(a.seed, p, it, 0);
+    int r = 0;
+    while (r < 59 && !(u < cdf[r])) ++r;
+    while (r > 0 && cnt[r] < 2) --r;                // guard against cdf round-off landing on an empty bucket
+    if (cnt[r] < 2) { for (r = 0; r < 59 && cnt[r] < 2; ++r) {} }
 #pragma unroll
-      for (int j = 0; j < 3; ++j) {
-        int o = (int)(rr_u01(a.seed, p, it, 1 + j) * cnt[r]);
-        o = min(o, cnt[r] - 1);
-        idx[j] = sorted[start[r] + o];
-      }
+    for (int j = 0; j < 3; ++j) {
+      int o = (int)(rr_u01(a.seed, p, it, 1 + j) * cnt[r]);
+      o = min(o, cnt[r] - 1);
+      idx[j] = sorted[start[r] + o];
     }
-    double k0[9], k1[9], s;
-#pragma unroll
-    for (int j = 0; j < 3; ++j) mv_load(a.mv, p, idx[j], &k0[3 * j], &k1[3 * j], s);
-    three_point_transform(k0, k1, a.hyps + ((long long)p * a.H + it) * 12);
   }
+  double k0[9], k1[9], s;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) mv_load(a.mv, p, idx[j], &k0[3 * j], &k1[3 * j], s);
+  three_point_transform(k0, k1, a.hyps + ((long long)p * a.H + it) * 12);
 }
 
 // kabsch3: the 3-point solver alone on gathered (selected) matches - single-call C-ABI entry.

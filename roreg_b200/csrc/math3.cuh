@@ -54,10 +54,11 @@ RR_HD double det3(const double M[9]) {
          M[2] * (M[3] * M[7] - M[4] * M[6]);
 }
 
-// U (orthonormal columns) from A = U*diag(S); a column whose singular value is below
-// 1e-13*max(S) is rebuilt as the cross product of the other two with the sign that makes det(U) =
-// det(V) (so that U*V^T is a proper rotation in the rank-deficient case).  Returns the index of the
-// smallest singular value.
+// U (orthonormal columns) from A = U*diag(S).  The column of the SMALLEST singular value is always
+// rebuilt as the cross product of the other two (exactly orthonormal U even when sigma_min is rounding
+// noise, as in the rank-2 3-point Kabsch); its sign follows the computed column when sigma_min is
+// meaningful (> 1e-10*sigma_max) and otherwise makes det(U) = det(V), i.e. U*V^T a proper rotation.
+// Returns the index of the smallest singular value.
 RR_HD int svd3_complete_u(const double A[9], const double V[9], const double S[3], double U[9]) {
   const double smax = fmax(S[0], fmax(S[1], S[2]));
   int jmin = 0;
@@ -67,16 +68,16 @@ RR_HD int svd3_complete_u(const double A[9], const double V[9], const double S[3
     const double inv = (S[j] > 0) ? 1.0 / S[j] : 0.0;
     for (int i = 0; i < 3; ++i) U[3 * i + j] = A[3 * i + j] * inv;
   }
-  if (!(S[jmin] > 1e-13 * smax)) {
-    const int a = (jmin + 1) % 3, b = (jmin + 2) % 3;
-    double c0 = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
-    double c1 = U[6 + a] * U[0 + b] - U[0 + a] * U[6 + b];
-    double c2 = U[0 + a] * U[3 + b] - U[3 + a] * U[0 + b];
-    const double n = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
-    if (n > 0) { c0 /= n; c1 /= n; c2 /= n; }
-    U[0 + jmin] = c0; U[3 + jmin] = c1; U[6 + jmin] = c2;
-    if (det3(U) * det3(V) < 0) { U[0 + jmin] = -c0; U[3 + jmin] = -c1; U[6 + jmin] = -c2; }
-  }
+  const int a = (jmin + 1) % 3, b = (jmin + 2) % 3;
+  double c0 = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
+  double c1 = U[6 + a] * U[0 + b] - U[0 + a] * U[6 + b];
+  double c2 = U[0 + a] * U[3 + b] - U[3 + a] * U[0 + b];
+  const double n = sqrt(c0 * c0 + c1 * c1 + c2 * c2);
+  if (n > 0) { c0 /= n; c1 /= n; c2 /= n; }
+  double sgn;
+  if (S[jmin] > 1e-10 * smax) sgn = (A[0 + jmin] * c0 + A[3 + jmin] * c1 + A[6 + jmin] * c2) >= 0 ? 1.0 : -1.0;
+  else sgn = (det3(V) >= 0) ? 1.0 : -1.0;      // det([c, u_a, u_b]) = +1 for the cyclic (jmin, a, b)
+  U[0 + jmin] = sgn * c0; U[3 + jmin] = sgn * c1; U[6 + jmin] = sgn * c2;
   return jmin;
 }
 

@@ -88,13 +88,9 @@ int roreg_inv_pool(roreg_ctx* c, const float* eqv, const int32_t* sample, int n_
 static int launch_nn(roreg_ctx* c, int mode, const float* src, const float* tgt, long long src_ps, long long tgt_ps,
                      int n_src, int n_tgt, int32_t* out_idx, float* out_dist, long long out_ps, int B, cudaStream_t st) {
   if (n_src == 0) return ROREG_OK;
+  (void)mode;
   NNArgs a{src, tgt, src_ps, tgt_ps, n_src, n_tgt, out_idx, out_dist, out_ps};
-  if (mode == 1) {
-    int rc = nn_tc_launch(c, a, B, st);
-    if (rc != ROREG_OK) return rc;
-  } else {
-    nn_diff_kernel<<<dim3((n_src + 63) / 64, B), 256, 0, st>>>(a);
-  }
+  nn_diff_kernel<<<dim3((n_src + 63) / 64, B), 256, 0, st>>>(a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }
@@ -115,13 +111,29 @@ int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, i
                        int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream) {
   RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode == 0 || mode == 1));
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * n0) + rr_align(sizeof(int32_t) * n1) + 4096);
+  if (mode == 1 && n0 != n1) {
+    snprintf(c->err, sizeof(c->err), "nn mode 1 (tcgen05 Gram) needs n0 == n1 in the single-pair entry");
+    return ROREG_ERR_UNSUPPORTED;
+  }
+  size_t need = rr_align(sizeof(int32_t) * n0) + rr_align(sizeof(int32_t) * n1) + 4096;
+  if (mode == 1) need += rr_align(sizeof(float) * 2 * (size_t)n0 * RR_F) + nn_tc_workspace_bytes(2LL * n0);
+  int rc = rr_ws_reserve(c, need);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
   int32_t* w01 = nn01 ? nn01 : ar.take<int32_t>(n0);
   int32_t* w10 = nn10 ? nn10 : ar.take<int32_t>(n1);
-  if ((rc = launch_nn(c, mode, f0, f1, 0, 0, n0, n1, w01, nullptr, 0, 1, st))) return rc;   // KNN(feats1, feats0): rows of cloud0 search cloud1
-  if ((rc = launch_nn(c, mode, f1, f0, 0, 0, n1, n0, w10, nullptr, 0, 1, st))) return rc;
+  if (mode == 1) {
+    float* inv2 = ar.take<float>(2 * (size_t)n0 * RR_F);
+    float* Ahat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
+    float* Bhat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
+    float* nh = ar.take<float>(2 * (size_t)n0);
+    RR_CUDA(c, cudaMemcpyAsync(inv2, f0, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
+    RR_CUDA(c, cudaMemcpyAsync(inv2 + (size_t)n0 * RR_F, f1, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
+    if ((rc = nn_tc_launch_both(c, inv2, n0, 1, Ahat, Bhat, nh, w01, w10, st))) return rc;
+  } else {
+    if ((rc = launch_nn(c, mode, f0, f1, 0, 0, n0, n1, w01, nullptr, 0, 1, st))) return rc;   // KNN(feats1, feats0): rows of cloud0 search cloud1
+    if ((rc = launch_nn(c, mode, f1, f0, 0, 0, n1, n0, w10, nullptr, 0, 1, st))) return rc;
+  }
   CompactArgs ca{w01, w10, n0, n1, 0, nullptr, 0, matches, n0 < n1 ? n0 : n1, n_matches};
   mutual_compact_kernel<<<1, 1024, 0, st>>>(ca);
   RR_LAUNCH_CHECK(c);
@@ -234,7 +246,10 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
   size_t need = rr_align(sizeof(float) * (size_t)B * 2 * S * RR_F) + 2 * rr_align(sizeof(int32_t) * (size_t)B * S) +
                 rr_align(sizeof(double) * (size_t)B * H * 12) + rr_align(sizeof(double) * (size_t)B * tiles * H) +
-                rr_align(sizeof(int32_t) * (size_t)B * S) + 4 * rr_align(sizeof(int32_t) * (size_t)B) + 8192;
+                rr_align(sizeof(int32_t) * (size_t)B * S) + 4 * rr_align(sizeof(int32_t) * (size_t)B) +
+                rr_align(sizeof(int32_t) * (size_t)B * 128) + rr_align(sizeof(double) * (size_t)B * 60) + 8192;
+  if (b->nn_mode == 1) need += nn_tc_workspace_bytes((long long)B * 2 * S);
+  RR_ARG(c, b->nn_mode == 0 || b->nn_mode == 1);
   int rc = rr_ws_reserve(c, need);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
@@ -245,6 +260,8 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   double* partial = ar.take<double>((size_t)B * tiles * H);
   int32_t* scratch = ar.take<int32_t>((size_t)B * S);
   int32_t* n_hyp = ar.take<int32_t>(B);
+  int32_t* bucket = ar.take<int32_t>((size_t)B * 128);
+  double* cdf = ar.take<double>((size_t)B * 60);
 
 #define RR_MARK(i) do { if (c->timing) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); } while (0)
   RR_MARK(0);
@@ -255,8 +272,15 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   RR_MARK(1);
   // 2. 1-NN both ways  (test/matcher.py:94-97)
   const long long ps = 2LL * S * RR_F;
-  if ((rc = launch_nn(c, b->nn_mode, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;
-  if ((rc = launch_nn(c, b->nn_mode, inv + (size_t)S * RR_F, inv, ps, ps, S, S, nn10, nullptr, S, B, st))) return rc;
+  if (b->nn_mode == 1) {
+    float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
+    float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
+    float* nh = ar.take<float>((size_t)B * 2 * S);
+    if ((rc = nn_tc_launch_both(c, inv, S, B, Ahat, Bhat, nh, nn01, nn10, st))) return rc;
+  } else {
+    if ((rc = launch_nn(c, 0, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;
+    if ((rc = launch_nn(c, 0, inv + (size_t)S * RR_F, inv, ps, ps, S, S, nn10, nullptr, S, B, st))) return rc;
+  }
   RR_MARK(2);
   // 3. mutual check, ordered compaction  (test/matcher.py:98-107)
   CompactArgs ca{nn01, nn10, S, S, S, b->sample, S, b->matches, S, b->n_matches};
@@ -283,8 +307,14 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   const int32_t* n_hyp_src = n_hyp;
   if (b->hyp_host_svd) { hyp_src = b->hyp_host_svd; n_hyp_src = nullptr; }
   else {
-    CoarseArgs cg{mv, b->dr_index, S, b->triplets, H, b->seed, hyps, n_hyp, scratch};
-    coarse_hyp_kernel<<<B, 256, 0, st>>>(cg);
+    CoarseArgs cg{mv, b->dr_index, S, b->triplets, H, b->seed, hyps, n_hyp, scratch, bucket, cdf};
+    if (!b->triplets) {
+      coarse_bucket_kernel<<<B, 256, 0, st>>>(cg);
+      RR_LAUNCH_CHECK(c);
+    } else {
+      RR_CUDA(c, cudaMemsetAsync(n_hyp, 0x7f, sizeof(int32_t) * B, st));     // "all H hypotheses valid"
+    }
+    coarse_hyp_kernel<<<dim3((H + 63) / 64, B), 64, 0, st>>>(cg);
     RR_LAUNCH_CHECK(c);
   }
   RR_MARK(5);

@@ -43,6 +43,24 @@ def test_three_point_transform_is_proper_branch_of_reference():
         assert np.abs(k1 @ T[:, :3].T + T[:, 3] - (k1 @ Tr[:, :3].T + Tr[:, 3])).max() < 1e-8
 
 
+def test_three_point_transform_arbitrary_triplets():
+    """Non-rigid triplets (wrong correspondences, repeated points): sigma_3 of the cross-covariance is pure
+    rounding noise of any relative size; the proper-rotation branch must still equal the reference's result
+    whenever LAPACK's coin flip lands on det = +1."""
+    L = _lib(); rng = np.random.default_rng(4)
+    nproper = 0
+    for i in range(3000):
+        k0 = np.ascontiguousarray(rng.random((3, 3)) * 3 + rng.uniform(-5, 5, 3))
+        k1 = np.ascontiguousarray(rng.random((3, 3)) * 3)
+        T = np.zeros((3, 4)); L.rr_host_three_point_transform(k0.ctypes.data_as(dp), k1.ctypes.data_as(dp), T.ctypes.data_as(dp))
+        Tr = O.threepps2tran(k0, k1)
+        assert abs(np.linalg.det(T[:, :3]) - 1) < 1e-9 and np.abs(T[:, :3] @ T[:, :3].T - np.eye(3)).max() < 1e-9
+        if np.linalg.det(Tr[:, :3]) > 0:
+            nproper += 1
+            assert np.abs(T - Tr).max() < 1e-8
+    assert nproper > 1000
+
+
 def test_quat_times_anchor_bit_exact(tables):
     L = _lib(); rng = np.random.default_rng(2)
     for i in range(300):
