@@ -26,7 +26,7 @@ constexpr int TC_STAGES = 3;
 constexpr int TC_BOX_BYTES = TC_BM * TC_KC * 4;                  // 16 KB per [128 x 32 f32] box
 constexpr int TC_TILE_BYTES = TC_BOX_BYTES * TC_NCHUNK;          // 48 KB per operand tile
 constexpr int TC_SMEM_BYTES = TC_TILE_BYTES * (1 + TC_STAGES) + 2 * TC_BN * 4 + 1024 /*align slack*/ + 256 /*barriers*/;
-constexpr uint32_t TC_SPIN_LIMIT = 200u * 1000u * 1000u;
+constexpr long long TC_WAIT_CYCLES = 3000000000LL;     // ~1.5-2 s of SM clocks: a lost arrive becomes a trap, never a hung GPU
 
 // ---- prep: split the pooled features into the extended-K operands ------------------------------------
 __global__ void __launch_bounds__(256) nn_tc_prep_kernel(const float* __restrict__ inv, int rows,
@@ -59,10 +59,11 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
-  for (uint32_t spin = 0; !done; ++spin) {
+  const long long t0 = clock64();
+  while (!done) {
     asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
                  : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-    if (spin > TC_SPIN_LIMIT) __trap();          // never hang the GPU: a lost arrive becomes a launch failure
+    if (!done && clock64() - t0 > TC_WAIT_CYCLES) __trap();     // never hang the GPU: a lost arrive becomes a launch failure
   }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
