@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--n", type=int, default=5000, help="keypoints per cloud")
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "1")), help="0 = float32 difference form (reference arithmetic), 1 = tcgen05 3xTF32 Gram")
+    ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "0")), help="0 = FP32 CUDA-core Gram, 1 = tcgen05 3xTF32 Gram")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="bounded CPU-baseline sample (seconds of host work)")
     return ap.parse_args()
@@ -182,6 +183,7 @@ def main():
     from roreg_b200 import ops
     torch.cuda.set_device(local)
     ctx = ops.Context(local)
+    ctx.set_corr_mode(args.corr_mode)
     B, n, H = args.pairs_per_step, args.n, args.max_iter
     prs, desc_h, keys_h, pc_h = make_inputs(B, n, rank)
     desc_pin = torch.from_numpy(desc_h).pin_memory(); keys_pin = torch.from_numpy(keys_h).pin_memory()
@@ -315,7 +317,7 @@ def main():
                 "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
                         "steps": e2e_steps},
                 "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
-                "nn_mode": args.nn_mode}
+                "nn_mode": args.nn_mode, "corr_mode": args.corr_mode}
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

@@ -60,7 +60,7 @@ int roreg_knn(roreg_ctx* ctx, const float* target, int n, const float* source, i
 /* ---- a13  test/matcher.py:94-106: 1-NN both ways on [n0,32] / [n1,32] invariant features + the mutual
  * check; matches come out in increasing row of f0 as (row in f0, row in f1).  n_matches: device int32[1].
  * nn01 [n0] / nn10 [n1] optional outputs (may be NULL).  mode 0 = float32 difference form (reference
- * arithmetic), mode 1 = tensor-core Gram form (3xTF32).                                               */
+ * arithmetic), mode 1 / 2 = tensor-core Gram form (tcgen05, 3xTF32; 2 = two row blocks per CTA).                                               */
 int roreg_mutual_match(roreg_ctx* ctx, const float* f0, int n0, const float* f1, int n1, int mode,
                        int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream);
 
@@ -72,6 +72,10 @@ int roreg_mutual_match(roreg_ctx* ctx, const float* f0, int n0, const float* f1,
 int roreg_group_corr(roreg_ctx* ctx, const float* X, const int32_t* idxX, const float* Y,
                      const int32_t* idxY, int K, int variant, float* cor_out, int32_t* argmax_out,
                      void* stream);
+
+/* Arithmetic of the 60x60 Gram inside roreg_group_corr / roreg_register_batch: 0 = float32 FMA on CUDA cores
+ * (default), 1 = tcgen05 tensor cores with the 3xTF32 split (float32-class products, different summation order). */
+int roreg_set_corr_mode(roreg_ctx* ctx, int mode);
 
 /* ---- a17  test/estimator.py:349-366 + utils/r_eval.py:90-106:
  * R = quat2mat(q)(float32 products) @ float32(Rgroup[pre_idx]),  t = key0 - key1 @ R^T  -> [K,3,4] f64 */

@@ -35,6 +35,7 @@ SIGNATURES = {
     "roreg_knn": (_i, [_p, _p, _i, _p, _i, _i, _i, _p, _p, _p]),
     "roreg_mutual_match": (_i, [_p, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p]),
     "roreg_group_corr": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p]),
+    "roreg_set_corr_mode": (_i, [_p, _i]),
     "roreg_hypotheses_from_quat": (_i, [_p, _p, _p, _p, _p, _i, _p, _p]),
     "roreg_ransac_oneshot": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _i, _d, _p, _p, _p, _p]),
     "roreg_refine": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _p]),

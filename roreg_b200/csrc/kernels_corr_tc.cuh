@@ -1,0 +1,264 @@
+// kernels_corr_tc.cuh - equivariant correlation (Des2R / R-indicator) with the 60x60 Gram on tcgen05.
+//
+// Per match  G[h][g] = sum_f X[f][h] * Y[f][g]  is a dense [60x32]x[32x60] contraction.  Two matches are
+// stacked per MMA (M = N = 128: rows = (match, h), columns = (match, g); the two off-diagonal 64x64
+// blocks are unused - the tensor pipe has the head-room, the kernel is HBM-bound on the 2 x 7680 B it
+// must gather per match).  Operands are MN-major: a descriptor row [32 f][60 h] lands in shared memory
+// exactly as it lies in HBM (TMA box [32 f] x [32 h], SWIZZLE_128B; columns 60..63 are zero-filled by
+// the tensor map's bound), so there is no transposition anywhere.
+// Accuracy: 3xTF32.  A "convert" warp group splits the landed tile in place, hi = tf32(x), lo = x - hi,
+// and the issuer runs (hi,hi) + (lo,hi) + (hi,lo) into one TMEM accumulator: float32-class products.
+// Epilogue: each thread owns one Gram row in TMEM, writes it transposed to shared memory and thread a
+// sums the generalised diagonal  cor[a] = sum_g G[tab[a][g]][g]  (tab = P: variant 1, P^T: variant 2).
+//
+//   warp 0      TMA producer     8 boxes (2 matches x {X,Y} x 2 h-halves) per stage
+//   warp 1      MMA issuer       3 x 4 tcgen05.mma kind::tf32 (M=N=128, K=8), commit -> mbarrier
+//   warps 2-5   convert          hi/lo split in shared memory, fence.proxy.async, arrive
+//   warps 6-9   epilogue         tcgen05.ld -> smem transpose -> diagonal sums -> argmax
+#pragma once
+#include "kernels_nn_tc.cuh"
+#include "kernels_corr.cuh"
+
+namespace roreg {
+
+constexpr int CT_STAGES = 2;
+constexpr int CT_BOX_BYTES = 32 * 32 * 4;                 // [32 f][32 h] f32
+constexpr int CT_OPER_BYTES = 4 * CT_BOX_BYTES;           // 2 matches x 2 h-halves = 16 KB (one MMA operand, M or N = 128)
+constexpr int CT_STAGE_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Yhi | Xlo | Ylo = 64 KB
+constexpr int CT_GS_BYTES = 2 * 64 * 64 * 4;              // transposed Gram of both matches
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;
+constexpr int CT_THREADS = 320;
+// kind::tf32, A and B MN-major (bits 15, 16), D = f32, M = 128, N = 128
+constexpr uint32_t CT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+
+// MN-major SWIZZLE_128B: 32-element (128 B) MN blocks at LBO, 8-row K groups at SBO = 1024 B
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(CT_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+struct CorrTcArgs {
+  const int32_t* idxX; const int32_t* idxY; int idx_stride;
+  const int32_t* pair_cloud; int n;
+  const int32_t* n_matches; int K, B;
+  const uint8_t* tab;
+  float* cor_out; int32_t* argmax_out;
+};
+
+__global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __grid_constant__ CUtensorMap mapX,
+                                                                      const __grid_constant__ CUtensorMap mapY, CorrTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  float* Gs = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);                 // [2][64 g][64 h]
+  uint8_t* tabs = smem + CT_STAGES * CT_STAGE_BYTES + CT_GS_BYTES;                        // 3600 B
+  float* red_v = reinterpret_cast<float*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_v + 2);   // [2] each
+  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tabs + 3600 + 16) + 7) & ~uintptr_t(7));
+  // barriers: 0..1 raw_full, 2..3 conv_done, 4..5 mma_done, 6..7 acc_free
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+
+  for (int e = threadIdx.x; e < 3600; e += CT_THREADS) tabs[e] = a.tab[e];
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < CT_STAGES; ++s) {
+      mbar_init(BAR(0 + s), 1); mbar_init(BAR(2 + s), 128); mbar_init(BAR(4 + s), 1); mbar_init(BAR(6 + s), 128);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int items_per_pair = (a.K + 1) / 2;
+  const long long n_items = (long long)a.B * items_per_pair;
+  // every role walks the same item sequence and skips the same items (device-side match counts)
+  auto item_count = [&](long long item, int& p, int& k0) -> int {
+    p = (int)(item / items_per_pair); k0 = (int)(item % items_per_pair) * 2;
+    const int cnt = a.n_matches ? a.n_matches[p] : a.K;
+    return cnt - k0;                                   // <= 0: nothing, 1: one match, >= 2: two matches
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int p, k0; const int avail = item_count(item, p, k0);
+        if (avail <= 0) continue;
+        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(BAR(4 + st), ph ^ 1);                // MMAs that read this stage have retired
+        uint8_t* sb = smem + st * CT_STAGE_BYTES;
+        mbar_expect_tx(BAR(0 + st), 2 * CT_OPER_BYTES);
+        for (int m = 0; m < 2; ++m) {
+          const int k = k0 + ((m < avail) ? m : 0);    // odd tail: the second slot re-reads the first match
+          const long long w = (long long)p * a.K + k;
+          long long rx = a.idxX ? a.idxX[w * a.idx_stride] : k;
+          long long ry = a.idxY ? a.idxY[w * a.idx_stride] : k;
+          if (a.pair_cloud) { rx += (long long)a.pair_cloud[2 * p + 1] * a.n; ry += (long long)a.pair_cloud[2 * p] * a.n; }
+          for (int hh = 0; hh < 2; ++hh) {
+            tma_load_2d(smem_u32(sb + (m * 2 + hh) * CT_BOX_BYTES), &mapX, hh * 32, (int)(rx * 32), BAR(0 + st));
+            tma_load_2d(smem_u32(sb + CT_OPER_BYTES + (m * 2 + hh) * CT_BOX_BYTES), &mapY, hh * 32, (int)(ry * 32), BAR(0 + st));
+          }
+        }
+        ++it;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        int p, k0; if (item_count(item, p, k0) <= 0) continue;
+        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+        mbar_wait(BAR(2 + st), ph);                    // hi/lo split done and visible to the async proxy
+        mbar_wait(BAR(6 + st), ph ^ 1);                // accumulator drained
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sb = smem_u32(smem + st * CT_STAGE_BYTES);
+        const uint32_t xhi = sb, yhi = sb + CT_OPER_BYTES, xlo = sb + 2 * CT_OPER_BYTES, ylo = sb + 3 * CT_OPER_BYTES;
+        const uint32_t d_tmem = tmem_base + st * 128;
+        const uint32_t aop[3] = {xhi, xlo, xhi}, bop[3] = {yhi, yhi, ylo};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_tf32(d_tmem, umma_desc_mn_sw128(aop[c] + kk * 1024), umma_desc_mn_sw128(bop[c] + kk * 1024), CT_IDESC, (c | kk) ? 1u : 0u);
+        umma_commit(BAR(4 + st));
+        ++it;
+      }
+    }
+  } else if (warp < 6) {
+    // ===================== convert: in-place hi, separate lo =====================
+    const int ct = threadIdx.x - 64;                   // 0..127
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int p, k0; if (item_count(item, p, k0) <= 0) continue;
+      const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(BAR(0 + st), ph);
+      float4* hi = reinterpret_cast<float4*>(smem + st * CT_STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + st * CT_STAGE_BYTES + 2 * CT_OPER_BYTES);
+#pragma unroll 4
+      for (int i = 0; i < (2 * CT_OPER_BYTES / 16) / 128; ++i) {      // 16 float4 per thread
+        const int e = ct + i * 128;
+        const float4 x = hi[e];
+        float4 h, l;
+        uint32_t t;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = x.x - h.x;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = x.y - h.y;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = x.z - h.z;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = x.w - h.w;
+        hi[e] = h; lo[e] = l;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
+      mbar_arrive(BAR(2 + st));
+      ++it;
+    }
+  } else {
+    // ===================== epilogue =====================
+    const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
+    const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
+    float* G = Gs + m * 64 * 64;
+    uint32_t it = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      int p, k0; const int avail = item_count(item, p, k0);
+      if (avail <= 0) continue;
+      const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(BAR(4 + st), ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + st * 128 + m * 64;
+      uint32_t r[64];
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t* rr = r + half * 32;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                     "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                     : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),
+                       "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15]),
+                       "=r"(rr[16]), "=r"(rr[17]), "=r"(rr[18]), "=r"(rr[19]), "=r"(rr[20]), "=r"(rr[21]), "=r"(rr[22]), "=r"(rr[23]),
+                       "=r"(rr[24]), "=r"(rr[25]), "=r"(rr[26]), "=r"(rr[27]), "=r"(rr[28]), "=r"(rr[29]), "=r"(rr[30]), "=r"(rr[31])
+                     : "r"(taddr + half * 32) : "memory");
+      }
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(BAR(6 + st));                        // accumulator free as soon as it sits in registers
+      // transposed store: Gs[m][g][h]; a warp writes 32 consecutive h -> conflict-free
+#pragma unroll
+      for (int g = 0; g < 60; ++g) G[g * 64 + h] = __uint_as_float(r[g]);
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");
+      float c = -INFINITY;
+      if (h < RR_G) {
+        c = 0.f;
+        const uint8_t* t = tabs + h * 60;
+#pragma unroll 10
+        for (int g = 0; g < RR_G; ++g) c += G[g * 64 + t[g]];
+      }
+      const bool valid = m < avail;
+      const long long w = (long long)p * a.K + k0 + m;
+      if (valid && h < RR_G && a.cor_out) a.cor_out[w * RR_G + h] = c;
+      float v = c; int ix = (h < RR_G) ? h : 0x7fffffff;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float vo = __shfl_xor_sync(0xffffffffu, v, o);
+        const int io = __shfl_xor_sync(0xffffffffu, ix, o);
+        if (vo > v || (vo == v && io < ix)) { v = vo; ix = io; }
+      }
+      if ((q & 1) == 1 && lane == 0) { red_v[m] = v; red_i[m] = ix; }       // upper half-row warp (h 32..63) publishes
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");
+      if ((q & 1) == 0 && lane == 0 && valid && a.argmax_out) {
+        int best = ix;                                                      // lower warp holds the smaller indices
+        if (red_v[m] > v) best = red_i[m];
+        a.argmax_out[w] = best;
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");             // Gs / red reusable
+      ++it;
+    }
+  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+// tensor map over a descriptor array viewed as [rows*32][60] float32, box [32 f][32 h], SWIZZLE_128B
+static inline int corr_tc_make_map(roreg_ctx* c, CUtensorMap* m, const float* base, long long rows) {
+  CUtensorMap tmp;
+  (void)tmp;
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !p || qres != cudaDriverEntryPointSuccess) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled entry point unavailable"); return ROREG_ERR_CUDA; }
+    fn = (PFN_encodeTiled)p;
+  }
+  const cuuint64_t dims[2] = {(cuuint64_t)RR_G, (cuuint64_t)rows * RR_F};
+  const cuuint64_t strides[1] = {(cuuint64_t)RR_G * sizeof(float)};
+  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(desc) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
+  return ROREG_OK;
+}
+
+static inline int group_corr_tc_launch(roreg_ctx* c, const float* X, long long rowsX, const float* Y, long long rowsY,
+                                       const CorrTcArgs& a, cudaStream_t st) {
+  CUtensorMap mX, mY;
+  int rc;
+  if ((rc = corr_tc_make_map(c, &mX, X, rowsX))) return rc;
+  if ((rc = corr_tc_make_map(c, &mY, Y, rowsY))) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    attr_set = true;
+  }
+  const long long items = (long long)a.B * ((a.K + 1) / 2);
+  const int grid = (int)(items < c->sm_count ? items : c->sm_count);
+  group_corr_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(mX, mY, a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+}  // namespace roreg

@@ -277,6 +277,223 @@ static inline int nn_tc_launch_both(roreg_ctx* c, const float* inv, int S, int B
   return ROREG_OK;
 }
 
+
+// =====================================================================================================
+// v2 (nn mode 2).  ncu on v1 (profiles/r01_run3_*): tensor pipe 36 % active, L2 12 %, one epilogue warp per
+// SMSP serialised on  tcgen05.ld -> wait -> 32 columns of math  => the EPILOGUE, not the MMA, paces the tile.
+// v2 keeps the tile shape and changes what v1 was slow at:
+//   * 8 epilogue warps (two per TMEM lane quadrant, each owning 64 of the 128 columns); both 32-column
+//     tcgen05.ld of a tile are issued back to back and waited once; the accumulator is released as soon as
+//     it sits in registers, before the min/argmin math;
+//   * the min is taken first (FADD+FMNMX per element), the index is only searched when the chunk improves
+//     the running minimum (rare after the first tiles);
+//   * one operand array H[rows][64] = [hi | lo]: the three products (hi,hi),(lo,hi),(hi,lo) address chunks
+//     of the same tiles, so an operand tile is 2 TMA boxes (32 KB) instead of 3, and 4 stages fit.
+// =====================================================================================================
+constexpr int T2_STAGES = 4;
+constexpr int T2_TILE_BYTES = 2 * TC_BOX_BYTES;                                  // [hi | lo] = 32 KB
+constexpr int T2_SMEM_BYTES = T2_TILE_BYTES * (1 + T2_STAGES) + 2 * TC_BN * 4 + 128 * 8 + 1024 + 256;
+constexpr int T2_THREADS = 64 + 256;
+
+__global__ void __launch_bounds__(256) nn_tc2_prep_kernel(const float* __restrict__ inv, int rows,
+                                                          float* __restrict__ H, float* __restrict__ nrm_half) {
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const float x = inv[(long long)r * 32 + lane];
+  uint32_t hb;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+  const float hi = __uint_as_float(hb);
+  H[(long long)r * 64 + lane] = hi;
+  H[(long long)r * 64 + 32 + lane] = x - hi;
+  const float ss = warp_sum(x * x);
+  if (lane == 0) nrm_half[r] = 0.5f * ss;
+}
+
+#define RR_TMEM_LD32(rr, addr)                                                                                              \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                    \
+               "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];" \
+               : "=r"(rr[0]), "=r"(rr[1]), "=r"(rr[2]), "=r"(rr[3]), "=r"(rr[4]), "=r"(rr[5]), "=r"(rr[6]), "=r"(rr[7]),     \
+                 "=r"(rr[8]), "=r"(rr[9]), "=r"(rr[10]), "=r"(rr[11]), "=r"(rr[12]), "=r"(rr[13]), "=r"(rr[14]), "=r"(rr[15]), \
+                 "=r"(rr[16]), "=r"(rr[17]), "=r"(rr[18]), "=r"(rr[19]), "=r"(rr[20]), "=r"(rr[21]), "=r"(rr[22]), "=r"(rr[23]), \
+                 "=r"(rr[24]), "=r"(rr[25]), "=r"(rr[26]), "=r"(rr[27]), "=r"(rr[28]), "=r"(rr[29]), "=r"(rr[30]), "=r"(rr[31])  \
+               : "r"(addr) : "memory")
+
+__global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_constant__ CUtensorMap mapH, NNTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                   // 32 KB
+  uint8_t* sB = smem + T2_TILE_BYTES;                   // T2_STAGES x 32 KB
+  float* sNb = reinterpret_cast<float*>(smem + T2_TILE_BYTES * (1 + T2_STAGES));   // [2][128]
+  float* mrg_v = sNb + 2 * TC_BN; int* mrg_j = reinterpret_cast<int*>(mrg_v + 128);  // [128] each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mrg_j + 128);
+  // barriers: 0 a_full, 1 a_empty, 2..5 b_full, 6..9 b_empty, 10..11 tmem_full, 12..13 tmem_empty
+  __shared__ uint32_t tmem_base_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(6 + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(10 + s), 1); mbar_init(BAR(12 + s), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int nrb = (a.S + TC_BM - 1) / TC_BM;
+  const int nct = (a.S + TC_BN - 1) / TC_BN;
+  const int n_items = a.B * 2 * nrb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it_b = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = item % nrb, d = (item / nrb) & 1, p = item / (2 * nrb);
+        const int a_row0 = (p * 2 + d) * a.S + rb * TC_BM;
+        const int b_row_base = (p * 2 + (1 - d)) * a.S;
+        mbar_wait(BAR(1), a_phase ^ 1);
+        mbar_expect_tx(BAR(0), T2_TILE_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(smem_u32(sA + c * TC_BOX_BYTES), &mapH, c * TC_KC, a_row0, BAR(0));
+        a_phase ^= 1;
+        for (int ct = 0; ct < nct; ++ct, ++it_b) {
+          const int st = it_b % T2_STAGES; const uint32_t ph = (it_b / T2_STAGES) & 1;
+          mbar_wait(BAR(6 + st), ph ^ 1);
+          mbar_expect_tx(BAR(2 + st), T2_TILE_BYTES);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(smem_u32(sB + st * T2_TILE_BYTES + c * TC_BOX_BYTES), &mapH, c * TC_KC, b_row_base + ct * TC_BN, BAR(2 + st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it_b = 0, it_t = 0, a_phase = 0;
+      const uint32_t ahi = smem_u32(sA), alo = ahi + TC_BOX_BYTES;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(BAR(0), a_phase); a_phase ^= 1;
+        for (int ct = 0; ct < nct; ++ct, ++it_b, ++it_t) {
+          const int st = it_b % T2_STAGES; const uint32_t ph = (it_b / T2_STAGES) & 1;
+          const int par = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+          mbar_wait(BAR(2 + st), ph);
+          mbar_wait(BAR(12 + par), tph ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t bhi = smem_u32(sB + st * T2_TILE_BYTES), blo = bhi + TC_BOX_BYTES;
+          const uint32_t d_tmem = tmem_base + par * TC_BN;
+          const uint32_t aop[3] = {ahi, alo, ahi}, bop[3] = {bhi, bhi, blo};
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int kk = 0; kk < TC_KC / 8; ++kk)
+              umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+          umma_commit(BAR(6 + st));
+          umma_commit(BAR(10 + par));
+        }
+        umma_commit(BAR(1));
+      }
+    }
+  } else {
+    // ===================== epilogue: 8 warps, warp -> (lane quadrant q, column half hf) =====================
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;                     // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127
+    const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 64;                    // 0..255
+    uint32_t it_t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rb = item % nrb, d = (item / nrb) & 1, p = item / (2 * nrb);
+      const int b_row_base = (p * 2 + (1 - d)) * a.S;
+      float best_v = INFINITY; int best_j = 0x7fffffff;
+      for (int ct = 0; ct < nct; ++ct, ++it_t) {
+        const int par = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+        if (et < TC_BN) {
+          const int j = ct * TC_BN + et;
+          sNb[par * TC_BN + et] = (j < a.S) ? a.nrm_half[b_row_base + j] : INFINITY;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(BAR(10 + par), tph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + par * TC_BN + hf * 64;
+        uint32_t r0[32], r1[32];
+        RR_TMEM_LD32(r0, taddr);
+        RR_TMEM_LD32(r1, taddr + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(BAR(12 + par));                     // accumulator free: the MMA of tile t+2 may start
+        const float4* nb4 = reinterpret_cast<const float4*>(sNb + par * TC_BN + hf * 64);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* rg = half ? r1 : r0;
+          float m = INFINITY;
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 nb = nb4[half * 8 + j4];
+            m = fminf(m, fminf(fminf(nb.x - __uint_as_float(rg[4 * j4]), nb.y - __uint_as_float(rg[4 * j4 + 1])),
+                               fminf(nb.z - __uint_as_float(rg[4 * j4 + 2]), nb.w - __uint_as_float(rg[4 * j4 + 3]))));
+          }
+          if (m < best_v) {                             // rare: find the first column attaining the new minimum
+            const float* nbs = sNb + par * TC_BN + hf * 64 + half * 32;
+            int jj = 31;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) if (nbs[j] - __uint_as_float(rg[j]) == m) jj = j;
+            best_v = m; best_j = ct * TC_BN + hf * 64 + half * 32 + jj;
+          }
+        }
+      }
+      // merge the two column halves of each row (lexicographic (value, index); half 1 has the larger indices)
+      if (hf == 1) { mrg_v[row_in_tile] = best_v; mrg_j[row_in_tile] = best_j; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hf == 0) {
+        if (mrg_v[row_in_tile] < best_v) { best_v = mrg_v[row_in_tile]; best_j = mrg_j[row_in_tile]; }
+        const int row = rb * TC_BM + row_in_tile;
+        if (row < a.S) (d == 0 ? a.nn01 : a.nn10)[(long long)p * a.S + row] = best_j;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+static inline int nn_tc2_launch_both(roreg_ctx* c, const float* inv, int S, int B, float* H, float* nrm_half,
+                                     int32_t* nn01, int32_t* nn10, cudaStream_t st) {
+  const long long rows = (long long)B * 2 * S;
+  nn_tc2_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(inv, (int)rows, H, nrm_half);
+  RR_LAUNCH_CHECK(c);
+  CUtensorMap mH;
+  {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+      void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || !p || qres != cudaDriverEntryPointSuccess) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled entry point unavailable"); return ROREG_ERR_CUDA; }
+      fn = (PFN_encodeTiled)p;
+    }
+    const cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {64 * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&mH, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)H, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(H) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(c, cudaFuncSetAttribute(nn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nrb = (S + TC_BM - 1) / TC_BM;
+  const int items = B * 2 * nrb;
+  const int grid = items < c->sm_count ? items : c->sm_count;
+  NNTcArgs a{nrm_half, S, B, nn01, nn10};
+  nn_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mH, a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
 static inline size_t nn_tc_workspace_bytes(long long rows) {
   return 2 * rr_align(sizeof(float) * rows * TC_KEXT) + rr_align(sizeof(float) * rows) + 1024;
 }

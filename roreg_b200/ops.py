@@ -50,6 +50,9 @@ class Context:
 
     STAGES = ("inv_pool", "nn", "compact", "group_corr", "hypotheses", "score_select", "refine")
 
+    def set_corr_mode(self, mode):
+        _lib.check(self.h, self.lib.roreg_set_corr_mode(self.h, int(mode)), "roreg_set_corr_mode")
+
     def set_timing(self, on=True):
         _lib.check(self.h, self.lib.roreg_set_timing(self.h, int(on)), "roreg_set_timing")
 

@@ -321,13 +321,14 @@ def _check_nn_tc(idx, target, source):
     return int(bad.sum())
 
 
-@pytest.mark.parametrize("n", [1200, 128, 131, 700])
-def test_mutual_match_tensor_core_mode(ctx, n):
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("n", [1200, 128, 131, 700, 300])
+def test_mutual_match_tensor_core_mode(ctx, n, mode):
     """nn mode 1: tcgen05 (kind::tf32, 3xTF32 split) Gram + TMEM-side running argmin; indices must equal the
     float64 adjudicator outside the stated near-tie band, for full tiles, one tile, ragged tiles."""
     pr = synth.make_pair(200 + n, n=n)
     f0 = O.inv_pool(pr["feats0"]); f1 = O.inv_pool(pr["feats1"])
-    m, cnt, nn01, nn10 = ctx.mutual_match(ctx.dev(f0), ctx.dev(f1), 1)
+    m, cnt, nn01, nn10 = ctx.mutual_match(ctx.dev(f0), ctx.dev(f1), mode)
     torch.cuda.synchronize()
     nbad = _check_nn_tc(_np(nn01), f1, f0) + _check_nn_tc(_np(nn10), f0, f1)
     k = int(cnt.item()); m = _np(m)[:k]
@@ -340,7 +341,8 @@ def test_mutual_match_tensor_core_mode(ctx, n):
             assert np.array_equal(m, ref)
 
 
-def test_register_batch_tensor_core_nn(ctx, tables):
+@pytest.mark.parametrize("mode", [1, 2])
+def test_register_batch_tensor_core_nn(ctx, tables, mode):
     seeds = [91, 92, 93]; n = 900
     prs = [synth.make_pair(s, n=n) for s in seeds]
     desc = ctx.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
@@ -348,10 +350,66 @@ def test_register_batch_tensor_core_nn(ctx, tables):
     pc = ctx.dev(np.array([[0, 1], [2, 3], [4, 5]], np.int32))
     o0 = ctx.register_batch(desc, keys, pc, max_iter=300, seed=3, nn_mode=0)
     o0 = {k: v.clone() for k, v in o0.items()}
-    o1 = ctx.register_batch(desc, keys, pc, max_iter=300, seed=3, nn_mode=1)
+    o1 = ctx.register_batch(desc, keys, pc, max_iter=300, seed=3, nn_mode=mode)
     torch.cuda.synchronize()
     for i, pr in enumerate(prs):
         assert np.abs(_np(o1["poses"][i])[:3] - pr["gt"]).max() < 5e-3
         k0 = int(o0["n_matches"][i]); k1 = int(o1["n_matches"][i])
         a = {tuple(r) for r in _np(o0["matches"][i, :k0]).tolist()}; b = {tuple(r) for r in _np(o1["matches"][i, :k1]).tolist()}
         assert len(a ^ b) <= 4          # the two NN arithmetics may differ on a handful of near ties only
+
+
+# ---------------------------------------------------------------------------------------- corr mode 1 (tcgen05)
+@pytest.fixture(scope="module")
+def ctx_tc():
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    c.set_corr_mode(1)
+    yield c
+    c.close()
+
+
+@pytest.mark.parametrize("variant,K", [(1, 500), (2, 501), (1, 1), (1, 2), (2, 3)])
+def test_group_corr_tensor_core_mode(ctx_tc, pair, tables, variant, K):
+    """tcgen05 Gram (MN-major operands straight from HBM, 3xTF32 split in shared memory): values to 1e-5 of the
+    float64 restatement, argmax equal wherever the float64 top-2 gap is clear; odd / tiny K exercise the tail slot."""
+    rng = np.random.default_rng(40 + K)
+    ix = rng.integers(0, 1200, K).astype(np.int32); iy = rng.integers(0, 1200, K).astype(np.int32)
+    X = pair["feats1"]; Y = pair["feats0"]
+    cor, am = ctx_tc.group_corr(ctx_tc.dev(X), ctx_tc.dev(Y), ctx_tc.dev(ix), ctx_tc.dev(iy), variant)
+    torch.cuda.synchronize()
+    f = O.group_corr_v1 if variant == 1 else O.group_corr_v2
+    ref64 = f(X[ix], Y[iy], tables.perm, np.float64)
+    assert np.abs(_np(cor) - ref64).max() < 2e-5
+    top2 = np.sort(ref64, axis=1)[:, -2:]
+    clear = (top2[:, 1] - top2[:, 0]) > 5e-5
+    assert (_np(am)[clear] == np.argmax(ref64, axis=1)[clear]).all()
+
+
+def test_des2r_known_answers_tensor_core_mode(ctx_tc, tables):
+    rng = np.random.default_rng(5)
+    X = rng.standard_normal((65, 32, 60)).astype(np.float32)
+    for a in (0, 7, 33, 59):
+        Xa = np.ascontiguousarray(X[:, :, tables.perm[a]])
+        _, am = ctx_tc.group_corr(ctx_tc.dev(X), ctx_tc.dev(Xa), variant=1, want_cor=False)
+        assert (_np(am) == a).all()
+        _, am = ctx_tc.group_corr(ctx_tc.dev(Xa), ctx_tc.dev(X), variant=1, want_cor=False)
+        assert (_np(am) == tables.inv[a]).all()
+
+
+def test_register_batch_tensor_core_corr(ctx, ctx_tc, tables):
+    seeds = [95, 96]; n = 800
+    prs = [synth.make_pair(s, n=n) for s in seeds]
+    for c in (ctx, ctx_tc):
+        desc = c.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+        keys = c.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+        pc = c.dev(np.array([[0, 1], [2, 3]], np.int32))
+        o = c.register_batch(desc, keys, pc, max_iter=300, seed=3, nn_mode=0)
+        torch.cuda.synchronize()
+        if c is ctx:
+            ref = {k: v.clone() for k, v in o.items()}
+    for i, pr in enumerate(prs):
+        k = int(ref["n_matches"][i])
+        assert int(o["n_matches"][i]) == k and torch.equal(o["matches"][i, :k], ref["matches"][i, :k])
+        assert (o["dr_index"][i, :k] == ref["dr_index"][i, :k]).float().mean().item() > 0.995
+        assert np.abs(_np(o["poses"][i])[:3] - pr["gt"]).max() < 5e-3
