@@ -3,11 +3,14 @@
 // Per match  G[h][g] = sum_f X[f][h] * Y[f][g]  is a dense [60x32]x[32x60] contraction.  Two matches are
 // stacked per MMA (M = N = 128: rows = (match, h), columns = (match, g); the two off-diagonal 64x64
 // blocks are unused - the tensor pipe has the head-room, the kernel is HBM-bound on the 2 x 7680 B it
-// must gather per match).  Operands are MN-major: a descriptor row [32 f][60 h] lands in shared memory
-// exactly as it lies in HBM (TMA box [32 f] x [32 h], SWIZZLE_128B; columns 60..63 are zero-filled by
-// the tensor map's bound), so there is no transposition anywhere.
-// Accuracy: 3xTF32.  A "convert" warp group splits the landed tile in place, hi = tf32(x), lo = x - hi,
-// and the issuer runs (hi,hi) + (lo,hi) + (hi,lo) into one TMEM accumulator: float32-class products.
+// must gather per match).  A descriptor row [32 f][60 h] lands in shared memory exactly as it lies in
+// HBM (TMA box [32 f] x [64 h], no swizzle; columns 60..63 are zero-filled by the tensor map's bound).
+// Accuracy: 3xTF32.  A "convert" warp group reads the landed tile, splits hi = tf32(x), lo = x - hi and
+// writes both TRANSPOSED into the K-major SWIZZLE_128B operand layout the NN kernel already uses
+// ([128 rows = (match,h)] x [32 f]), and the issuer runs (hi,hi) + (lo,hi) + (hi,lo) into one TMEM
+// accumulator: float32-class products.  (A first version fed the MN-major tiles to the MMA directly; it
+// ran but produced zeros on the B200 - run 4 - so the transposition moved into the convert stage, which
+// touches every element anyway.)
 // Epilogue: each thread owns one Gram row in TMEM, writes it transposed to shared memory and thread a
 // sums the generalised diagonal  cor[a] = sum_g G[tab[a][g]][g]  (tab = P: variant 1, P^T: variant 2).
 //
@@ -21,20 +24,14 @@
 
 namespace roreg {
 
-constexpr int CT_STAGES = 2;
-constexpr int CT_BOX_BYTES = 32 * 32 * 4;                 // [32 f][32 h] f32
-constexpr int CT_OPER_BYTES = 4 * CT_BOX_BYTES;           // 2 matches x 2 h-halves = 16 KB (one MMA operand, M or N = 128)
-constexpr int CT_STAGE_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Yhi | Xlo | Ylo = 64 KB
+constexpr int CT_STAGES = 2;                              // raw landing buffers (TMA double-buffered)
+constexpr int CT_RAW_BOX = 32 * 64 * 4;                   // [32 f][64 h] f32 = 8 KB (one descriptor row, h padded to 64)
+constexpr int CT_RAW_BYTES = 4 * CT_RAW_BOX;              // X0 | X1 | Y0 | Y1 = 32 KB per stage
+constexpr int CT_OPER_BYTES = 128 * 32 * 4;               // one K-major operand: 128 rows x 32 f = 16 KB
+constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB (single-buffered)
 constexpr int CT_GS_BYTES = 2 * 64 * 64 * 4;              // transposed Gram of both matches
-constexpr int CT_SMEM_BYTES = CT_STAGES * CT_STAGE_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;
 constexpr int CT_THREADS = 320;
-// kind::tf32, A and B MN-major (bits 15, 16), D = f32, M = 128, N = 128
-constexpr uint32_t CT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-
-// MN-major SWIZZLE_128B: 32-element (128 B) MN blocks at LBO, 8-row K groups at SBO = 1024 B
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(CT_BOX_BYTES >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
-}
 
 struct CorrTcArgs {
   const int32_t* idxX; const int32_t* idxY; int idx_stride;
@@ -48,11 +45,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap mapY, CorrTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  float* Gs = reinterpret_cast<float*>(smem + CT_STAGES * CT_STAGE_BYTES);                 // [2][64 g][64 h]
-  uint8_t* tabs = smem + CT_STAGES * CT_STAGE_BYTES + CT_GS_BYTES;                        // 3600 B
+  uint8_t* tiles = smem + CT_STAGES * CT_RAW_BYTES;                                        // Xhi | Xlo | Yhi | Ylo
+  float* Gs = reinterpret_cast<float*>(tiles + CT_TILES_BYTES);                            // [2][64 g][64 h]
+  uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + CT_GS_BYTES;                            // 3600 B
   float* red_v = reinterpret_cast<float*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_v + 2);   // [2] each
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tabs + 3600 + 16) + 7) & ~uintptr_t(7));
-  // barriers: 0..1 raw_full, 2..3 conv_done, 4..5 mma_done, 6..7 acc_free
+  // barriers: 0..1 raw_full[s], 2..3 raw_free[s], 4 conv_done, 5 tiles_free, 6..7 mma_done[acc], 8..9 acc_free[acc]
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -60,9 +58,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 
   for (int e = threadIdx.x; e < 3600; e += CT_THREADS) tabs[e] = a.tab[e];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CT_STAGES; ++s) {
-      mbar_init(BAR(0 + s), 1); mbar_init(BAR(2 + s), 128); mbar_init(BAR(4 + s), 1); mbar_init(BAR(6 + s), 128);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(BAR(0 + s), 1); mbar_init(BAR(2 + s), 128); mbar_init(BAR(6 + s), 1); mbar_init(BAR(8 + s), 128);
     }
+    mbar_init(BAR(4), 128); mbar_init(BAR(5), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -91,19 +90,17 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         int p, k0; const int avail = item_count(item, p, k0);
         if (avail <= 0) continue;
         const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(4 + st), ph ^ 1);                // MMAs that read this stage have retired
-        uint8_t* sb = smem + st * CT_STAGE_BYTES;
-        mbar_expect_tx(BAR(0 + st), 2 * CT_OPER_BYTES);
+        mbar_wait(BAR(2 + st), ph ^ 1);                // convert warps have consumed this raw buffer
+        uint8_t* sb = smem + st * CT_RAW_BYTES;
+        mbar_expect_tx(BAR(0 + st), CT_RAW_BYTES);
         for (int m = 0; m < 2; ++m) {
           const int k = k0 + ((m < avail) ? m : 0);    // odd tail: the second slot re-reads the first match
           const long long w = (long long)p * a.K + k;
           long long rx = a.idxX ? a.idxX[w * a.idx_stride] : k;
           long long ry = a.idxY ? a.idxY[w * a.idx_stride] : k;
           if (a.pair_cloud) { rx += (long long)a.pair_cloud[2 * p + 1] * a.n; ry += (long long)a.pair_cloud[2 * p] * a.n; }
-          for (int hh = 0; hh < 2; ++hh) {
-            tma_load_2d(smem_u32(sb + (m * 2 + hh) * CT_BOX_BYTES), &mapX, hh * 32, (int)(rx * 32), BAR(0 + st));
-            tma_load_2d(smem_u32(sb + CT_OPER_BYTES + (m * 2 + hh) * CT_BOX_BYTES), &mapY, hh * 32, (int)(ry * 32), BAR(0 + st));
-          }
+          tma_load_2d(smem_u32(sb + m * CT_RAW_BOX), &mapX, 0, (int)(rx * 32), BAR(0 + st));
+          tma_load_2d(smem_u32(sb + (2 + m) * CT_RAW_BOX), &mapY, 0, (int)(ry * 32), BAR(0 + st));
         }
         ++it;
       }
@@ -114,47 +111,57 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       uint32_t it = 0;
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         int p, k0; if (item_count(item, p, k0) <= 0) continue;
-        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(2 + st), ph);                    // hi/lo split done and visible to the async proxy
-        mbar_wait(BAR(6 + st), ph ^ 1);                // accumulator drained
+        const int acc = it & 1; const uint32_t aph = (it >> 1) & 1;
+        mbar_wait(BAR(4), it & 1);                     // operand tiles written and visible to the async proxy
+        mbar_wait(BAR(8 + acc), aph ^ 1);              // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t sb = smem_u32(smem + st * CT_STAGE_BYTES);
-        const uint32_t xhi = sb, yhi = sb + CT_OPER_BYTES, xlo = sb + 2 * CT_OPER_BYTES, ylo = sb + 3 * CT_OPER_BYTES;
-        const uint32_t d_tmem = tmem_base + st * 128;
+        const uint32_t tb = smem_u32(tiles);
+        const uint32_t xhi = tb, xlo = tb + CT_OPER_BYTES, yhi = tb + 2 * CT_OPER_BYTES, ylo = tb + 3 * CT_OPER_BYTES;
+        const uint32_t d_tmem = tmem_base + acc * 128;
         const uint32_t aop[3] = {xhi, xlo, xhi}, bop[3] = {yhi, yhi, ylo};
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
-            umma_tf32(d_tmem, umma_desc_mn_sw128(aop[c] + kk * 1024), umma_desc_mn_sw128(bop[c] + kk * 1024), CT_IDESC, (c | kk) ? 1u : 0u);
-        umma_commit(BAR(4 + st));
+            umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+        umma_commit(BAR(5));                           // operand tiles reusable by the convert warps
+        umma_commit(BAR(6 + acc));                     // accumulator ready for the epilogue
         ++it;
       }
     }
   } else if (warp < 6) {
-    // ===================== convert: in-place hi, separate lo =====================
-    const int ct = threadIdx.x - 64;                   // 0..127
+    // ===================== convert: split hi/lo and transpose into K-major SW128 operand tiles ============
+    // raw[f][h] (h contiguous, pitch 64) -> tile row r = (match, h), 128 B of f per row, 16-B chunk c = f/4
+    // stored at chunk position c ^ (r % 8)  (the 128-byte swizzle TMA / UMMA use).
+    const int ct = threadIdx.x - 64;                   // 0..127 == operand row (match = ct/64, h = ct%64)
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; if (item_count(item, p, k0) <= 0) continue;
       const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(BAR(0 + st), ph);
-      float4* hi = reinterpret_cast<float4*>(smem + st * CT_STAGE_BYTES);
-      float4* lo = reinterpret_cast<float4*>(smem + st * CT_STAGE_BYTES + 2 * CT_OPER_BYTES);
-#pragma unroll 4
-      for (int i = 0; i < (2 * CT_OPER_BYTES / 16) / 128; ++i) {      // 16 float4 per thread
-        const int e = ct + i * 128;
-        const float4 x = hi[e];
-        float4 h, l;
-        uint32_t t;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.x)); h.x = __uint_as_float(t); l.x = x.x - h.x;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.y)); h.y = __uint_as_float(t); l.y = x.y - h.y;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.z)); h.z = __uint_as_float(t); l.z = x.z - h.z;
-        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x.w)); h.w = __uint_as_float(t); l.w = x.w - h.w;
-        hi[e] = h; lo[e] = l;
+      mbar_wait(BAR(0 + st), ph);                      // raw tile landed
+      mbar_wait(BAR(5), (it & 1) ^ 1);                 // MMAs of the previous item no longer read the operand tiles
+      const float* raw = reinterpret_cast<const float*>(smem + st * CT_RAW_BYTES);
+      const int m = ct >> 6, h = ct & 63;
+#pragma unroll
+      for (int op = 0; op < 2; ++op) {                 // 0: X, 1: Y
+        const float* src = raw + (op * 2 + m) * (CT_RAW_BOX / 4) + h;
+        uint8_t* thi = tiles + (op * 2) * CT_OPER_BYTES + ct * 128;
+        uint8_t* tlo = thi + CT_OPER_BYTES;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          float4 hv, lv; float x; uint32_t t;
+          x = src[(4 * c + 0) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.x = __uint_as_float(t); lv.x = x - hv.x;
+          x = src[(4 * c + 1) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.y = __uint_as_float(t); lv.y = x - hv.y;
+          x = src[(4 * c + 2) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.z = __uint_as_float(t); lv.z = x - hv.z;
+          x = src[(4 * c + 3) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.w = __uint_as_float(t); lv.w = x - hv.w;
+          const int pos = (c ^ (ct & 7)) * 16;
+          *reinterpret_cast<float4*>(thi + pos) = hv;
+          *reinterpret_cast<float4*>(tlo + pos) = lv;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
-      mbar_arrive(BAR(2 + st));
+      mbar_arrive(BAR(4));                             // conv_done
+      mbar_arrive(BAR(2 + st));                        // raw buffer free for the next TMA
       ++it;
     }
   } else {
@@ -167,10 +174,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; const int avail = item_count(item, p, k0);
       if (avail <= 0) continue;
-      const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(BAR(4 + st), ph);
+      const int acc = it & 1; const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(BAR(6 + acc), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + st * 128 + m * 64;
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + m * 64;
       uint32_t r[64];
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
@@ -185,7 +192,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(BAR(6 + st));                        // accumulator free as soon as it sits in registers
+      mbar_arrive(BAR(8 + acc));                       // accumulator free as soon as it sits in registers
       // transposed store: Gs[m][g][h]; a warp writes 32 consecutive h -> conflict-free
 #pragma unroll
       for (int g = 0; g < 60; ++g) G[g * 64 + h] = __uint_as_float(r[g]);
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
 }
 
-// tensor map over a descriptor array viewed as [rows*32][60] float32, box [32 f][32 h], SWIZZLE_128B
+// tensor map over a descriptor array viewed as [rows*32][60] float32, box [32 f][64 h] (h 60..63 zero-filled), no swizzle
 static inline int corr_tc_make_map(roreg_ctx* c, CUtensorMap* m, const float* base, long long rows) {
   CUtensorMap tmp;
   (void)tmp;
@@ -235,10 +242,10 @@ static inline int corr_tc_make_map(roreg_ctx* c, CUtensorMap* m, const float* ba
   }
   const cuuint64_t dims[2] = {(cuuint64_t)RR_G, (cuuint64_t)rows * RR_F};
   const cuuint64_t strides[1] = {(cuuint64_t)RR_G * sizeof(float)};
-  const cuuint32_t box[2] = {32, 32};
+  const cuuint32_t box[2] = {64, 32};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(desc) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
   return ROREG_OK;
 }
