@@ -40,11 +40,11 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--pairs-per-step", type=int, default=8)
+    ap.add_argument("--pairs-per-step", type=int, default=32)
     ap.add_argument("--n", type=int, default=5000, help="keypoints per cloud")
     ap.add_argument("--max-iter", type=int, default=1000)
-    ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "1")), help="0 = float32 difference form (reference arithmetic), 1 = tcgen05 3xTF32 Gram")
-    ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "0")), help="0 = FP32 CUDA-core Gram, 1 = tcgen05 3xTF32 Gram")
+    ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "2")), help="0 = float32 difference form (reference arithmetic), 1 = tcgen05 3xTF32 Gram")
+    ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "1")), help="0 = FP32 CUDA-core Gram, 1 = tcgen05 3xTF32 Gram")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="bounded CPU-baseline sample (seconds of host work)")
     return ap.parse_args()
