@@ -112,6 +112,29 @@ int roreg_refine_once(roreg_ctx* ctx, const double* k0, const double* k1, const 
 int roreg_kabsch3(roreg_ctx* ctx, const double* k0_sel, const double* k1_sel, const int32_t* triplets,
                   int H, double* trans, void* stream);
 
+/* ---- a1-a3 / a22  group-convolution networks (GF: network/group_feat.py:26-45, ET: network/eqv_trans.py:119-138,
+ * RD: network/rot_detect.py:43-55).  Activations are channel-last rows [(item*60+g)][C] split into tf32 hi/lo
+ * parts; a group convolution is im2col over the 13 group neighbours (data_process, group_feat.py:20-24) followed
+ * by the tcgen05 GEMM with a fused bias / residual / eval-BN / ReLU epilogue.                                      */
+/* descriptors [*,32,60] -> rows [(item*60+g)][n_src*32]; src_host / rows_host / permute_host are HOST arrays of
+ * n_src device pointers / flags; flagged sources are read through P[pre_idx[item]] (eqv_trans.py:126-128).      */
+int roreg_pack_descriptors(roreg_ctx* ctx, int n_src, const float* const* src_host, const int32_t* const* rows_host,
+                           const int32_t* permute_host, const int32_t* pre_idx, int n_items, const float* bn_scale,
+                           const float* bn_shift, int relu, float* out_hi, float* out_lo, void* stream);
+/* out[(item*n_gout+j)][k*C+c] = act[(item*60 + N[gset[j]][k])][c]; gset NULL = all 60 group elements.            */
+int roreg_gconv_im2col(roreg_ctx* ctx, const float* act_hi, const float* act_lo, int n_items, int C,
+                       const int32_t* gset, int n_gout, float* out_hi, float* out_lo, void* stream);
+/* out[r][o] = sum_c A[r][c] W[o][c]; v = out + bias (+ residual[r*res_ld+o]); raw_out = v; act = relu?(v*bn_scale
+ * + bn_shift) split hi/lo.  Kdim % 32 == 0; W has w_rows >= ceil(O/NT)*NT rows; npass 1 (TF32) or 3 (3xTF32).    */
+int roreg_gemm(roreg_ctx* ctx, const float* A_hi, const float* A_lo, int R, int Kdim, const float* W_hi,
+               const float* W_lo, int w_rows, int O, int NT, int npass, const float* bias, const float* residual,
+               int res_ld, float* raw_out, int raw_ld, float* act_hi, float* act_lo, int act_ld,
+               const float* bn_scale, const float* bn_shift, int relu, void* stream);
+int roreg_gf_finalize(roreg_ctx* ctx, const float* conv_out, const float* x, int n, float* eqv_out, void* stream);
+int roreg_rd_finalize(roreg_ctx* ctx, const float* raw, int n, float* feat_out, void* stream);
+int roreg_row_std60(roreg_ctx* ctx, const float* cor, int n, float* out, void* stream);
+int roreg_quat_normalize(roreg_ctx* ctx, const float* q_in, int ld, int K, float* q_out, void* stream);
+
 /* ---- batched engine: B independent pairs per call (the throughput path bench.py times) ------------
  * Clouds live in one arena: desc [n_clouds][n][32][60] float32, keys [n_clouds][n][3] float64.
  * pair_cloud [B][2] int32 = (cloud id0, cloud id1).  sample [B][2][keynum] int32 or NULL (identity,

@@ -41,6 +41,13 @@ SIGNATURES = {
     "roreg_refine": (_i, [_p, _p, _p, _p, _i, _i, _p, _p, _p, _d, _p, _p, _p]),
     "roreg_refine_once": (_i, [_p, _p, _p, _p, _i, _i, _p, _d, _p, _p, _p]),
     "roreg_kabsch3": (_i, [_p, _p, _p, _p, _i, _p, _p]),
+    "roreg_pack_descriptors": (_i, [_p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
+    "roreg_gconv_im2col": (_i, [_p, _p, _p, _i, _i, _p, _i, _p, _p, _p]),
+    "roreg_gemm": (_i, [_p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p, _i, _p]),
+    "roreg_gf_finalize": (_i, [_p, _p, _p, _i, _p, _p]),
+    "roreg_rd_finalize": (_i, [_p, _p, _i, _p, _p]),
+    "roreg_row_std60": (_i, [_p, _p, _i, _p, _p]),
+    "roreg_quat_normalize": (_i, [_p, _p, _i, _i, _p, _p]),
     "roreg_register_batch": (_i, [_p, C.POINTER(RoregBatch), _p]),
     "roreg_set_timing": (_i, [_p, _i]),
     "roreg_get_stage_ms": (_i, [_p, C.POINTER(C.c_float)]),

@@ -5,6 +5,8 @@
 #include "kernels_ransac.cuh"
 #include "kernels_nn_tc.cuh"
 #include "kernels_corr_tc.cuh"
+#include "kernels_gemm_tc.cuh"
+#include "kernels_gconv.cuh"
 
 using namespace roreg;
 
@@ -240,6 +242,85 @@ int roreg_kabsch3(roreg_ctx* c, const double* k0s, const double* k1s, const int3
   RR_ARG(c, k0s && k1s && triplets && trans && H >= 0);
   if (H == 0) return ROREG_OK;
   kabsch3_kernel<<<(H + 127) / 128, 128, 0, (cudaStream_t)stream>>>(k0s, k1s, triplets, H, trans);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// group-convolution networks (GF / ET / RD): pack, im2col, GEMM, tails
+// ------------------------------------------------------------------------------------------------
+int roreg_pack_descriptors(roreg_ctx* c, int n_src, const float* const* src_host, const int32_t* const* rows_host,
+                           const int32_t* permute_host, const int32_t* pre_idx, int n_items, const float* bn_scale,
+                           const float* bn_shift, int relu, float* out_hi, float* out_lo, void* stream) {
+  RR_ARG(c, n_src >= 1 && n_src <= 4 && src_host && out_hi && n_items >= 0);
+  if (n_items == 0) return ROREG_OK;
+  PackArgs a{};
+  for (int s = 0; s < n_src; ++s) {
+    RR_ARG(c, src_host[s] != nullptr);
+    a.src[s] = src_host[s]; a.rows[s] = rows_host ? rows_host[s] : nullptr; a.permute[s] = permute_host ? permute_host[s] : 0;
+  }
+  a.n_src = n_src; a.pre_idx = pre_idx; a.perm = c->d_perm8; a.n_items = n_items;
+  a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.relu = relu; a.out_hi = out_hi; a.out_lo = out_lo;
+  pack_desc_kernel<<<dim3(n_items, n_src), 256, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_gconv_im2col(roreg_ctx* c, const float* act_hi, const float* act_lo, int n_items, int C, const int32_t* gset,
+                       int n_gout, float* out_hi, float* out_lo, void* stream) {
+  RR_ARG(c, act_hi && out_hi && n_items >= 0 && C >= 4 && (C % 4) == 0 && n_gout >= 1 && n_gout <= 60);
+  RR_ARG(c, (out_lo == nullptr) || (act_lo != nullptr));
+  if (n_items == 0) return ROREG_OK;
+  const long long total = (long long)n_items * n_gout * 13 * (C / 4);
+  long long blocks = (total + 255) / 256;
+  if (blocks > (long long)c->sm_count * 32) blocks = (long long)c->sm_count * 32;
+  gconv_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(act_hi, act_lo, n_items, C, c->d_nei, gset, n_gout, out_hi, out_lo);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_gemm(roreg_ctx* c, const float* A_hi, const float* A_lo, int R, int Kdim, const float* W_hi, const float* W_lo,
+               int w_rows, int O, int NT, int npass, const float* bias, const float* residual, int res_ld, float* raw_out,
+               int raw_ld, float* act_hi, float* act_lo, int act_ld, const float* bn_scale, const float* bn_shift, int relu,
+               void* stream) {
+  RR_ARG(c, A_hi && W_hi && R >= 0 && O >= 1 && NT >= 16 && w_rows >= NT && (raw_out || act_hi));
+  GemmArgs a{};
+  a.R = R; a.Kdim = Kdim; a.O = O; a.NT = NT; a.n_ntiles = (O + NT - 1) / NT; a.npass = npass;
+  RR_ARG(c, (long long)a.n_ntiles * NT <= w_rows);
+  a.bias = bias; a.residual = residual; a.res_ld = res_ld; a.raw_out = raw_out; a.raw_ld = raw_ld;
+  a.act_hi = act_hi; a.act_lo = act_lo; a.act_ld = act_ld; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.relu = relu;
+  RR_ARG(c, (bn_scale == nullptr) == (bn_shift == nullptr));
+  return gemm_tc_launch(c, A_hi, A_lo, W_hi, W_lo, w_rows, a, (cudaStream_t)stream);
+}
+
+int roreg_gf_finalize(roreg_ctx* c, const float* conv_out, const float* x, int n, float* eqv_out, void* stream) {
+  RR_ARG(c, conv_out && x && eqv_out && n >= 0);
+  if (n == 0) return ROREG_OK;
+  gf_finalize_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(conv_out, x, n, eqv_out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_rd_finalize(roreg_ctx* c, const float* raw, int n, float* feat_out, void* stream) {
+  RR_ARG(c, raw && feat_out && n >= 0);
+  if (n == 0) return ROREG_OK;
+  rd_finalize_kernel<<<n, 256, 0, (cudaStream_t)stream>>>(raw, n, feat_out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_row_std60(roreg_ctx* c, const float* cor, int n, float* out, void* stream) {
+  RR_ARG(c, cor && out && n >= 0);
+  if (n == 0) return ROREG_OK;
+  row_std60_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(cor, n, out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_quat_normalize(roreg_ctx* c, const float* q_in, int ld, int K, float* q_out, void* stream) {
+  RR_ARG(c, q_in && q_out && ld >= 4 && K >= 0);
+  if (K == 0) return ROREG_OK;
+  quat_normalize_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q_in, ld, K, q_out);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

@@ -219,22 +219,54 @@ class yohoc:
 
 # yohoo
 class extractor_localtrans():
-    """test/estimator.py:275-367.  The ET network (SURVEY.md section 8(f) rank 1) is not in this build;
-    Rt_pre therefore fails loudly.  Given quaternions, the pose arithmetic of :349-366 is on the device
-    (hypotheses_from_quat)."""
+    """test/estimator.py:275-367: ET network -> residual quaternion per match -> R = quat2mat(q) @ Rgroup[pre_idx],
+    t = key0 - key1 @ R.T -> Trans_pre/{id0}-{id1}.npy float64 [K,3,4].  Network and pose arithmetic on the device."""
 
     def __init__(self, cfg):
         self.cfg = cfg
         self.ctx = context(cfg)
+        self.best_model_fn = f'{self.cfg.model_fn}/ET/model_best.pth'
+        self.test_batch_size = self.cfg.bs_ET
+        self.npass = int(getattr(cfg, "net_passes", 3))
+        self.net = None
+
+    def _load_model(self):
+        from .extractor import load_state_dict
+        from .. import nets
+        # strict=False in the reference (:289): the checkpoint also carries an unused PartI_net.* copy
+        self.net = nets.ETNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass, chunk=int(self.test_batch_size))
 
     def hypotheses(self, quat, pre_idx, Keys0_m, Keys1_m):
         ctx = self.ctx
-        tr = ctx.hypotheses_from_quat(ctx.dev(quat, torch.float32), ctx.dev(pre_idx.astype(np.int32)),
+        tr = ctx.hypotheses_from_quat(ctx.dev(quat, torch.float32), ctx.dev(np.asarray(pre_idx).astype(np.int32)),
                                       ctx.dev(Keys0_m, torch.float64), ctx.dev(Keys1_m, torch.float64))
         return tr.cpu().numpy()
 
     def Rt_pre(self, dataset, keynum):
-        raise NotImplementedError("extractor_localtrans.Rt_pre: ET group-conv kernels are not part of this build")
+        self._load_model()
+        ctx = self.ctx
+        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
+        DRindex_dir = f'{match_dir}/DR_index'
+        Save_dir = f'{match_dir}/Trans_pre'
+        make_non_exists_dir(Save_dir)
+        datasetname = feature_dataset_name(dataset)
+        FCGF_dir = f'{self.cfg.output_cache_fn}/{datasetname}/{self.cfg.backbone}_Input_Group_feature'
+        YOMO_dir = f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature'
+        print(f'Extracting the local transformation on each correspondence of {dataset.name}')
+        cache = CloudCache(ctx)
+        for pair in tqdm(dataset.pair_ids):
+            id0, id1 = pair
+            pps = np.load(f'{match_dir}/{id0}-{id1}.npy')
+            Index_pre = np.load(f'{DRindex_dir}/{id0}-{id1}.npy')
+            i0 = ctx.dev(pps[:, 0].astype(np.int32)); i1 = ctx.dev(pps[:, 1].astype(np.int32))
+            pre = ctx.dev(Index_pre.astype(np.int32))
+            # batch_create (:293-306): side 0 of the network = cloud id1 ("exchanged")
+            quat = self.net.forward(cache.get(f'{FCGF_dir}/{id1}.npy'), i1, cache.get(f'{FCGF_dir}/{id0}.npy'), i0,
+                                    cache.get(f'{YOMO_dir}/{id1}.npy'), i1, cache.get(f'{YOMO_dir}/{id0}.npy'), i0, pre)
+            Keys0 = dataset.get_kps(id0)[pps[:, 0], :]
+            Keys1 = dataset.get_kps(id1)[pps[:, 1], :]
+            Trans = ctx.hypotheses_from_quat(quat, pre, ctx.dev(Keys0, torch.float64), ctx.dev(Keys1, torch.float64))
+            np.save(f'{Save_dir}/{id0}-{id1}.npy', Trans.cpu().numpy())
 
 
 class yohoo_ransac:

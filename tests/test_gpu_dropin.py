@@ -89,5 +89,3 @@ def test_unbuilt_plugins_fail_loudly():
     import roreg_b200.test as rt
     with pytest.raises(NotImplementedError):
         rt.yoho_mat(_cfg("/tmp"))
-    with pytest.raises(NotImplementedError):
-        rt.yoho_des(_cfg("/tmp")).run(None)

@@ -1,0 +1,143 @@
+"""Group-convolution networks (tcgen05 GEMM + pack / im2col / tails) against the oracle on seeded random
+weights, and against files the UNMODIFIED reference wrote (tests/golden/s256.npz: gf_eqv_*, det_score_*, trans_pre_*)."""
+import os
+import types
+import numpy as np
+import pytest
+import torch
+from conftest import load_golden
+from oracle import roreg_oracle as O
+from roreg_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    yield c
+    c.close()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+@pytest.mark.parametrize("npass,tol", [(3, 2e-5), (1, 3e-3)])
+@pytest.mark.parametrize("R,K,Odim", [(300, 416, 256), (129, 64, 4), (1000, 3328, 512), (60, 6656, 256)])
+def test_gemm_tc_against_float64(ctx, npass, tol, R, K, Odim):
+    from roreg_b200 import nets
+    rng = np.random.default_rng(R + K)
+    A = rng.standard_normal((R, K)).astype(np.float32); W = (rng.standard_normal((Odim, K)) / np.sqrt(K)).astype(np.float32)
+    b = rng.standard_normal(Odim).astype(np.float32); res = rng.standard_normal((R, Odim)).astype(np.float32)
+    sc = (1 + 0.1 * rng.standard_normal(Odim)).astype(np.float32); sh = (0.1 * rng.standard_normal(Odim)).astype(np.float32)
+    g = nets.GroupNets(ctx, npass)
+    L = nets.Layer(ctx, W.reshape(Odim, K, 1, 1), b)
+    hi, lo = nets.tf32_split(A)
+    raw, (ahi, alo) = g.gemm((ctx.dev(hi), ctx.dev(lo)), R, L, residual=ctx.dev(res), res_ld=Odim, want_raw=True, bn=(sc, sh), relu=True)
+    torch.cuda.synchronize()
+    ref = A.astype(np.float64) @ W.astype(np.float64).T + b + res
+    assert np.abs(_np(raw) - ref).max() < tol * max(1.0, np.abs(ref).max())
+    act = np.maximum(ref * sc + sh, 0)
+    assert np.abs(_np(ahi) + _np(alo) - act).max() < tol * max(1.0, np.abs(act).max())
+    assert (np.abs(_np(alo)) <= np.abs(_np(ahi)) * 2.0 ** -10 + 1e-30).all()          # hi carries 11 significant bits
+
+
+def test_gf_net_against_oracle_and_reference(ctx, tables):
+    from roreg_b200 import nets
+    z, n, keynum, max_iter, seeds = load_golden("s256")
+    ds = synth.SynthDataset(seeds[:1], n=n, name="synth/s256", max_res_deg=2.0)
+    sd = O.random_state_dict("GF", 101)
+    net = nets.GFNet(ctx, sd, npass=3, chunk=100)
+    for cid in ds.pc_ids:
+        x = ds.get_feats(cid, "fcgf")
+        got = _np(net.forward(ctx.dev(x[:140])))
+        ref, _ = O.gf_forward(x[:140], sd, tables.nei)
+        assert np.abs(got - ref).max() < 2e-5                        # float32-class (3xTF32) vs the NumPy oracle
+        assert np.abs(got[:40] - z[f"gf_eqv_{cid}"]).max() < 2e-5    # vs the file the reference's yoho_des.run wrote
+    # equivariance known answer (SURVEY 8c ii): permuting the input group axis by P[a] permutes the output
+    x = ds.get_feats("0", "fcgf")[:64]
+    a = 23
+    ya = _np(net.forward(ctx.dev(np.ascontiguousarray(x[:, :, tables.perm[a]]))))
+    y = _np(net.forward(ctx.dev(x)))
+    assert np.abs(ya - y[:, :, tables.perm[a]]).max() < 2e-5
+
+
+def test_gf_net_single_pass_tf32(ctx, tables):
+    from roreg_b200 import nets
+    sd = O.random_state_dict("GF", 7)
+    x = synth.make_pair(5, n=64, with_fcgf=True)["fcgf0"]
+    got = _np(nets.GFNet(ctx, sd, npass=1).forward(ctx.dev(x)))
+    ref, _ = O.gf_forward(x, sd, tables.nei)
+    assert np.abs(got - ref).max() < 5e-3            # one TF32 pass: the reference's own cuDNN arithmetic class, not parity-grade
+
+
+def test_et_net_against_oracle(ctx, tables):
+    from roreg_b200 import nets
+    pr = synth.make_pair(33, n=500, with_fcgf=True, max_res_deg=2.0)
+    pps, _ = O.mutual_run(pr["feats0"], pr["feats1"])
+    dr = O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm)
+    sd = O.random_state_dict("ET", 102)
+    net = nets.ETNet(ctx, sd, npass=3, chunk=128)
+    i0 = ctx.dev(pps[:, 0].astype(np.int32)); i1 = ctx.dev(pps[:, 1].astype(np.int32))
+    q = _np(net.forward(ctx.dev(pr["fcgf1"]), i1, ctx.dev(pr["fcgf0"]), i0, ctx.dev(pr["feats1"]), i1, ctx.dev(pr["feats0"]), i0,
+                        ctx.dev(dr.astype(np.int32))))
+    ref = O.et_forward(pr["fcgf1"][pps[:, 1]], pr["fcgf0"][pps[:, 0]], pr["feats1"][pps[:, 1]], pr["feats0"][pps[:, 0]], dr, sd,
+                       tables.nei, tables.perm)
+    assert np.abs(q - ref).max() < 2e-5
+    assert np.abs(np.linalg.norm(q, axis=1) - 1).max() < 1e-6
+
+
+def test_rd_net_against_oracle(ctx, tables):
+    from roreg_b200 import nets
+    sd = O.random_state_dict("RD", 103)
+    x = synth.make_pair(44, n=300)["feats0"]
+    s = _np(nets.RDNet(ctx, sd, npass=3, chunk=128).forward(ctx.dev(x)))
+    ref = O.rd_forward(x, sd, tables.nei, tables.perm)
+    assert np.abs(s - ref).max() < 2e-5 * max(1.0, np.abs(ref).max())
+
+
+def _write_ckpt(path, sd):
+    os.makedirs(os.path.dirname(path), exist_ok=True)
+    full = {}
+    for k, v in sd.items():
+        full[k] = torch.from_numpy(v)
+    torch.save({"best_para": 0, "network_state_dict": full}, path)
+
+
+def test_net_plugins_reproduce_reference_files(tmp_path):
+    """yoho_des.run / yoho_det.run / extractor_localtrans.Rt_pre through the reference signatures, against the
+    files the reference wrote with the same (seeded random) checkpoints."""
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden("s256")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/s256", max_res_deg=2.0)
+    model_fn = str(tmp_path / "ckpt")
+    for kind, seed in (("GF", 101), ("ET", 102), ("RD", 103)):
+        _write_ckpt(f"{model_fn}/{kind}/model_best.pth", O.random_state_dict(kind, seed))
+    # per-cloud stages on clouds 0, 1 (what the fixture recorded)
+    cache_pc = str(tmp_path / "cache_pc")
+    ds.write_cache(cache_pc, yoho=False)
+    cfg = types.SimpleNamespace(output_cache_fn=cache_pc, model_fn=model_fn, SO3_related_files=None, backbone="FCGF", bs_GF=1250,
+                                bs_ET=1000, RD=False, RM=False, match_n=0.5, ransac_ird=0.1)
+    ds_pc = synth.SynthDataset(seeds[:1], n=n, name="synth/s256", max_res_deg=2.0)
+    rt.yoho_des(cfg).run(ds_pc)
+    rt.yoho_det(cfg).run(ds_pc)
+    for cid in ds_pc.pc_ids:
+        eqv = np.load(f"{cache_pc}/synth/s256/YOHO_Output_Group_feature/{cid}.npy")
+        assert eqv.dtype == np.float32 and eqv.shape == (n, 32, 60)
+        assert np.abs(eqv[:40] - z[f"gf_eqv_{cid}"]).max() < 2e-5
+        det = np.load(f"{cache_pc}/synth/s256/det_score/{cid}.npy")
+        assert np.mean(np.abs(det - z[f"det_score_{cid}"]) * n <= 1.0) > 0.97       # rank statistic: near ties may swap neighbours
+    # ET stage on the reference's own matches / DR_index
+    cache = str(tmp_path / "cache")
+    ds.write_cache(cache)
+    cfg.output_cache_fn = cache
+    base = f"{cache}/synth/s256/match_{keynum}"
+    os.makedirs(f"{base}/DR_index", exist_ok=True)
+    for (id0, id1) in ds.pair_ids:
+        np.save(f"{base}/{id0}-{id1}.npy", z[f"match_{id0}-{id1}"]); np.save(f"{base}/DR_index/{id0}-{id1}.npy", z[f"dr_index_{id0}-{id1}"])
+    rt.extractor_localtrans(cfg).Rt_pre(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        tr = np.load(f"{base}/Trans_pre/{id0}-{id1}.npy")
+        assert tr.dtype == np.float64 and np.abs(tr - z[f"trans_pre_{id0}-{id1}"]).max() < 5e-5
