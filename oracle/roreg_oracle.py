@@ -458,3 +458,126 @@ def random_state_dict(kind, seed):
     else:
         raise KeyError(kind)
     return sd
+
+
+# ----------------------------------------------------------------------------------------
+# a6-a11  rotation-coherence matcher Match_ot  (network/rot_coh_match.py), inference only
+# ----------------------------------------------------------------------------------------
+def _conv1x1(x, sd, p):
+    """nn.Conv2d(cin, cout, 1) on [C, P] (P = flattened positions)."""
+    W = sd[p + ".weight"].reshape(sd[p + ".weight"].shape[0], -1)
+    return (W @ x + sd[p + ".bias"][:, None]).astype(F32)
+
+
+def _instnorm(x):
+    """nn.InstanceNorm2d(affine=False, eps=1e-5) on [C, P]: per-channel statistics over ALL positions (biased var)."""
+    m = x.mean(axis=1, keepdims=True, dtype=np.float64); v = x.var(axis=1, keepdims=True, dtype=np.float64)
+    return ((x - m) / np.sqrt(v + 1e-5)).astype(F32)
+
+
+def mlp_2layer(x, sd, p):
+    """mlp_2layer / Contextnorm forward (rot_coh_match.py:14-32, :63-81) on [Cin, P]."""
+    h = _conv1x1(x, sd, p + ".net.0")
+    h = np.maximum(_instnorm(h), 0)
+    out = _conv1x1(h, sd, p + ".net.3")
+    if p + ".res.weight" in sd:
+        out = out + _conv1x1(x, sd, p + ".res")
+    return out.astype(F32)
+
+
+def knn_index_desc(score, k):
+    """Knn_index_extract(axis=2) rot_coh_match.py:34-45: first k columns of a descending argsort per row."""
+    return np.argsort(-score, axis=1, kind="stable")[:, :k]
+
+
+def multi_head_attention(q, kf, vf, sd, p):
+    """MultiHeadedAttention.forward + attention (rot_coh_match.py:84-119): q [32,m], kf / vf [32,m,k];
+    4 heads, channel c = d*4 + h (view(b, dim, heads, -1))."""
+    m, k = kf.shape[1], kf.shape[2]
+    Q = _conv1x1(q, sd, p + ".proj.0").reshape(8, 4, m)
+    K = _conv1x1(kf.reshape(32, m * k), sd, p + ".proj.1").reshape(8, 4, m, k)
+    V = _conv1x1(vf.reshape(32, m * k), sd, p + ".proj.2").reshape(8, 4, m, k)
+    sc = np.einsum("fhm,fhmk->hmk", Q, K) / np.float32(8 ** .5)
+    sc = sc - sc.max(axis=-1, keepdims=True)
+    pr = np.exp(sc); pr = pr / pr.sum(axis=-1, keepdims=True)
+    x = np.einsum("hmk,dhmk->dhm", pr.astype(F32), V).reshape(32, m)
+    return _conv1x1(x.astype(F32), sd, p + ".merge")
+
+
+def cross_attention_block(src, tgt, src_eqv, tgt_eqv, featinv, k, s2t, sd, p, perm):
+    """Cross_attention_block.forward rot_coh_match.py:132-165.  src/tgt/featinv [32,m]/[32,n]; *_eqv [m,32,60]."""
+    score = (src.T @ tgt).astype(F32)                      # score_mat
+    knn = knn_index_desc(score, k); nn = knn_index_desc(score, 1)[:, 0]
+    knn_fea = tgt[:, knn]                                  # [32,m,k]
+    feat = multi_head_attention(src, knn_fea, knn_fea, sd, p + ".cross_attn")
+    feat = mlp_2layer(np.concatenate([featinv, src, feat], 0), sd, p + ".merge")
+    t_nn = tgt_eqv[nn]                                     # eqv descriptor of each point's 1-NN
+    if s2t:
+        rind = group_corr_v2(src_eqv, t_nn, perm)          # sum_{f,g} S[f,P[g,h]] T_nn[f,g]
+    else:
+        rind = group_corr_v2(t_nn, src_eqv, perm)          # sum_{f,g} T_nn[f,P[g,h]] S[f,g]
+    return feat, rind.T.astype(F32)                        # [32,m], [60,m]
+
+
+def self_attention_block(feat, coor, rind, featinv, k, sd, p):
+    """Self_attention_block.forward rot_coh_match.py:187-210.  feat/featinv [32,m], coor [3,m], rind [60,m]."""
+    m = feat.shape[1]
+    score = (feat.T @ feat).astype(F32)
+    knn = knn_index_desc(score, k)
+    knn_fea = feat[:, knn]                                 # [32,m,k]
+    knn_coor = coor[:, knn] - coor[:, :, None]             # [3,m,k]
+    pe = mlp_2layer(knn_coor.reshape(3, m * k).astype(F32), sd, p + ".pos_en").reshape(32, m, k)
+    r2 = np.concatenate([rind, np.repeat(rind.max(axis=1, keepdims=True), m, 1)], 0)      # [120,m]
+    conf = mlp_2layer(r2.astype(F32), sd, p + ".ambiguity")                                # [32,m]
+    pe = pe / np.linalg.norm(pe, axis=0, keepdims=True)
+    kf = knn_fea / np.linalg.norm(knn_fea, axis=0, keepdims=True)
+    conf = conf / np.linalg.norm(conf, axis=0, keepdims=True)
+    val_in = np.concatenate([pe, kf, np.repeat(conf[:, :, None], k, 2)], 0).reshape(96, m * k).astype(F32)
+    value = mlp_2layer(val_in, sd, p + ".val_en").reshape(32, m, k)
+    out = multi_head_attention(feat, kf.astype(F32), value, sd, p + ".self_attn")
+    return mlp_2layer(np.concatenate([featinv, feat, out], 0), sd, p + ".merge")
+
+
+def log_sinkhorn(scores, alpha, iters=100):
+    """sinkhorn_ot.log_optimal_transport rot_coh_match.py:284-313 (float32, scipy-free logsumexp)."""
+    m, n = scores.shape
+    Z = np.full((m + 1, n + 1), alpha, F32); Z[:m, :n] = scores
+    norm = F32(-np.log(F32(m + n)))
+    log_mu = np.concatenate([np.full(m, norm, F32), [F32(np.log(F32(n))) + norm]]).astype(F32)
+    log_nu = np.concatenate([np.full(n, norm, F32), [F32(np.log(F32(m))) + norm]]).astype(F32)
+
+    def lse(a, axis):
+        mx = a.max(axis=axis, keepdims=True)
+        return (mx + np.log(np.exp(a - mx).sum(axis=axis, keepdims=True, dtype=F32))).squeeze(axis).astype(F32)
+    u = np.zeros(m + 1, F32); v = np.zeros(n + 1, F32)
+    for _ in range(iters):
+        u = log_mu - lse(Z + v[None, :], 1)
+        v = log_nu - lse(Z + u[:, None], 0)
+    return (Z + u[:, None] + v[None, :] - norm).astype(F32)
+
+
+def match_ot_forward(feats0, feats1, keys0, keys1, sd, perm, iters=100):
+    """Match_ot.forward rot_coh_match.py:339-390 for one pair.  feats0/keys0 = the batch's 'source' side
+    (test/matcher.py:192-197 feeds cloud id1 there).  Returns matches0 [m] (-1 = none), matching_scores0 [m],
+    matches1 [n], matching_scores1 [n], and the OT matrix."""
+    src_eqv = feats0.astype(F32); tgt_eqv = feats1.astype(F32)             # [m,32,60]
+    sc = (keys0.astype(F32).T / F32(0.025)); tc = (keys1.astype(F32).T / F32(0.025))
+    s_inv = src_eqv.mean(axis=-1).T.astype(F32); t_inv = tgt_eqv.mean(axis=-1).T.astype(F32)   # [32,m]
+    src, tgt = s_inv, t_inv
+    for li, k in enumerate((16, 8)):
+        p = f"Graph.merge_blocks.{li}"
+        s2t, r_s = cross_attention_block(src, tgt, src_eqv, tgt_eqv, s_inv, k, True, sd, p + ".cross_graph_s2t", perm)
+        eh_s = self_attention_block(s2t, sc, r_s, s_inv, k, sd, p + ".self_graph_s")
+        t2s, r_t = cross_attention_block(tgt, src, tgt_eqv, src_eqv, t_inv, k, False, sd, p + ".cross_graph_t2s", perm)
+        eh_t = self_attention_block(t2s, tc, r_t, t_inv, k, sd, p + ".self_graph_t")
+        src, tgt = eh_s, eh_t
+    s_fin = mlp_2layer(np.concatenate([s_inv, src], 0), sd, "final_mlp")
+    t_fin = mlp_2layer(np.concatenate([t_inv, tgt], 0), sd, "final_mlp")
+    score = (s_fin.T @ t_fin).astype(F32)
+    Z = log_sinkhorn(score, F32(sd["ot_layer.bin_score"]), iters)
+    inner = Z[:-1, :-1]
+    i0 = inner.argmax(1); i1 = inner.argmax(0)
+    m0 = np.arange(inner.shape[0]) == i1[i0]; m1 = np.arange(inner.shape[1]) == i0[i1]
+    ms0 = np.where(m0, np.exp(inner.max(1)), 0).astype(F32)
+    ms1 = np.where(m1, ms0[i1], 0).astype(F32)
+    return np.where(m0, i0, -1), ms0, np.where(m1 & m0[i1], i1, -1), ms1, Z

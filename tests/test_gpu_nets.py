@@ -24,7 +24,7 @@ def _np(t):
     return t.cpu().numpy()
 
 
-@pytest.mark.parametrize("npass,tol", [(3, 2e-5), (1, 3e-3)])
+@pytest.mark.parametrize("npass,tol", [(3, 5e-5), (1, 3e-3)])   # 3xTF32: float32-class products; the tensor core's accumulator truncation grows with K
 @pytest.mark.parametrize("R,K,Odim", [(300, 416, 256), (129, 64, 4), (1000, 3328, 512), (60, 6656, 256)])
 def test_gemm_tc_against_float64(ctx, npass, tol, R, K, Odim):
     from roreg_b200 import nets
@@ -54,14 +54,14 @@ def test_gf_net_against_oracle_and_reference(ctx, tables):
         x = ds.get_feats(cid, "fcgf")
         got = _np(net.forward(ctx.dev(x[:140])))
         ref, _ = O.gf_forward(x[:140], sd, tables.nei)
-        assert np.abs(got - ref).max() < 2e-5                        # float32-class (3xTF32) vs the NumPy oracle
-        assert np.abs(got[:40] - z[f"gf_eqv_{cid}"]).max() < 2e-5    # vs the file the reference's yoho_des.run wrote
+        assert np.abs(got - ref).max() < 1e-4                        # stated tolerance on descriptors: 1e-4 (measured 4e-5)
+        assert np.abs(got[:40] - z[f"gf_eqv_{cid}"]).max() < 1e-4    # vs the file the reference's yoho_des.run wrote
     # equivariance known answer (SURVEY 8c ii): permuting the input group axis by P[a] permutes the output
     x = ds.get_feats("0", "fcgf")[:64]
     a = 23
     ya = _np(net.forward(ctx.dev(np.ascontiguousarray(x[:, :, tables.perm[a]]))))
     y = _np(net.forward(ctx.dev(x)))
-    assert np.abs(ya - y[:, :, tables.perm[a]]).max() < 2e-5
+    assert np.abs(ya - y[:, :, tables.perm[a]]).max() < 1e-4
 
 
 def test_gf_net_single_pass_tf32(ctx, tables):
@@ -126,7 +126,7 @@ def test_net_plugins_reproduce_reference_files(tmp_path):
     for cid in ds_pc.pc_ids:
         eqv = np.load(f"{cache_pc}/synth/s256/YOHO_Output_Group_feature/{cid}.npy")
         assert eqv.dtype == np.float32 and eqv.shape == (n, 32, 60)
-        assert np.abs(eqv[:40] - z[f"gf_eqv_{cid}"]).max() < 2e-5
+        assert np.abs(eqv[:40] - z[f"gf_eqv_{cid}"]).max() < 1e-4
         det = np.load(f"{cache_pc}/synth/s256/det_score/{cid}.npy")
         assert np.mean(np.abs(det - z[f"det_score_{cid}"]) * n <= 1.0) > 0.97       # rank statistic: near ties may swap neighbours
     # ET stage on the reference's own matches / DR_index
@@ -134,10 +134,18 @@ def test_net_plugins_reproduce_reference_files(tmp_path):
     ds.write_cache(cache)
     cfg.output_cache_fn = cache
     base = f"{cache}/synth/s256/match_{keynum}"
-    os.makedirs(f"{base}/DR_index", exist_ok=True)
+    os.makedirs(f"{base}/DR_index", exist_ok=True); os.makedirs(f"{base}/scores", exist_ok=True)
     for (id0, id1) in ds.pair_ids:
         np.save(f"{base}/{id0}-{id1}.npy", z[f"match_{id0}-{id1}"]); np.save(f"{base}/DR_index/{id0}-{id1}.npy", z[f"dr_index_{id0}-{id1}"])
+        np.save(f"{base}/scores/{id0}-{id1}.npy", z[f"scores_{id0}-{id1}"])
     rt.extractor_localtrans(cfg).Rt_pre(ds, keynum)
     for (id0, id1) in ds.pair_ids:
         tr = np.load(f"{base}/Trans_pre/{id0}-{id1}.npy")
-        assert tr.dtype == np.float64 and np.abs(tr - z[f"trans_pre_{id0}-{id1}"]).max() < 5e-5
+        assert tr.dtype == np.float64 and np.abs(tr - z[f"trans_pre_{id0}-{id1}"]).max() < 1e-4
+    # the complete yohoo estimator (Rindex -> Rt_pre -> one-shot RANSAC -> refine) against the reference's final poses
+    np.random.seed(4321)
+    rt.yohoo(cfg).run(ds, keynum, max_iter)
+    for (id0, id1) in ds.pair_ids:
+        r = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoo_recall_{id0}-{id1}"])
+        assert np.abs(r["trans"] - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-4
