@@ -1,0 +1,264 @@
+// kernels_matchot.cuh - small kernels of the rotation-coherence matcher Match_ot
+// (network/rot_coh_match.py:8-390).  The dense 1x1 layers and the [m,n] score matrices run on the tcgen05
+// GEMM (kernels_gemm_tc.cuh) and the R-indicator on the group-correlation kernels (variant 2); what is
+// here is the glue the reference expresses with argsort / advanced indexing / softmax / InstanceNorm /
+// logsumexp:  top-k of a score row, row gathers, the 4-head neighbourhood attention, per-channel instance
+// statistics, operand preparation (concat + normalise + tf32 split) and the log-domain Sinkhorn passes.
+// Activations are channel-last rows [positions][C] float32.
+#pragma once
+#include "common.cuh"
+
+namespace roreg {
+
+// ---- top-k of each row of S [m][n] (descending value, ties -> lower column), k <= 16 ---------------------------
+// Knn_index_extract (rot_coh_match.py:34-45) sorts the whole row; only the first k columns are ever used.
+__global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict__ S, int n, int ld, int k, int32_t* __restrict__ idx) {
+  extern __shared__ float row[];                 // [n]
+  __shared__ float rv[8]; __shared__ int ri[8];
+  const int r = blockIdx.x, tid = threadIdx.x;
+  const float* src = S + (long long)r * ld;
+  for (int j = tid; j < n; j += 256) row[j] = src[j];
+  __syncthreads();
+  for (int t = 0; t < k; ++t) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int j = tid; j < n; j += 256) { const float v = row[j]; if (v > bv) { bv = v; bi = j; } }   // increasing j: first max per thread
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float vo = __shfl_xor_sync(0xffffffffu, bv, o); const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (vo > bv || (vo == bv && io < bi)) { bv = vo; bi = io; }
+    }
+    if ((tid & 31) == 0) { rv[tid >> 5] = bv; ri[tid >> 5] = bi; }
+    __syncthreads();
+    if (tid == 0) {
+      for (int w = 1; w < 8; ++w) if (rv[w] > bv || (rv[w] == bv && ri[w] < bi)) { bv = rv[w]; bi = ri[w]; }
+      idx[(long long)r * k + t] = bi;
+      if (bi < n) row[bi] = -INFINITY;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- out[(i*k + j)][c] = src[idx[i*k + j]][c]   (C % 4 == 0) -----------------------------------------------------
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ idx,
+                                                          long long n_out, int C, float* __restrict__ out) {
+  const int c4 = C >> 2;
+  const long long total = n_out * c4;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const long long r = e / c4; const int q = (int)(e % c4);
+    reinterpret_cast<float4*>(out)[e] = reinterpret_cast<const float4*>(src)[(long long)idx[r] * c4 + q];
+  }
+}
+
+// ---- relative neighbour coordinates: out[(i*k+j)][0..2] = coor[idx[i*k+j]] - coor[i], zero-padded to 32 -----------
+__global__ void __launch_bounds__(256) rel_coor_kernel(const float* __restrict__ coor /*[m][3]*/, const int32_t* __restrict__ idx,
+                                                       int m, int k, float* __restrict__ out /*[m*k][32]*/) {
+  const long long total = (long long)m * k * 32;
+  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const long long r = e >> 5; const int c = (int)(e & 31);
+    float v = 0.f;
+    if (c < 3) v = coor[(long long)idx[r] * 3 + c] - coor[(r / k) * 3 + c];
+    out[e] = v;
+  }
+}
+
+// ---- per-channel instance statistics over P rows of x [P][C] (InstanceNorm2d, affine=False, biased variance) ------
+__global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict__ x, long long P, int C, double* __restrict__ acc /*[C][2]*/) {
+  // thread -> channel c = tid % C, row lane = tid / C ; requires C <= 256 and 256 % C == 0
+  const int c = threadIdx.x % C, rl = threadIdx.x / C, rpb = 256 / C;
+  double s = 0, ss = 0;
+  for (long long r = (long long)blockIdx.x * rpb + rl; r < P; r += (long long)gridDim.x * rpb) {
+    const double v = x[r * C + c]; s += v; ss += v * v;
+  }
+  atomicAdd(&acc[2 * c], s); atomicAdd(&acc[2 * c + 1], ss);
+}
+__global__ void chan_stats_finish_kernel(const double* __restrict__ acc, long long P, int C, float* __restrict__ mean, float* __restrict__ rstd) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const double m = acc[2 * c] / (double)P;
+  double v = acc[2 * c + 1] / (double)P - m * m;
+  if (v < 0) v = 0;
+  mean[c] = (float)m; rstd[c] = (float)(1.0 / sqrt(v + 1e-5));
+}
+
+// ---- GEMM operand preparation: concat up to 3 sources along channels, optional per-source row broadcast and
+// L2 normalisation over its channels, optional instance-norm + ReLU, zero pad to Kout, tf32 hi/lo split ------------
+struct PrepArgs {
+  const float* src[3]; int C[3]; int row_div[3]; int l2norm[3]; int n_src;
+  const float* mean; const float* rstd; int relu;      // instance norm (applied to the single source) or NULL
+  long long P; int Kout;
+  float* hi; float* lo; float* plain;                  // plain (optional): the float32 value before the split
+};
+__global__ void __launch_bounds__(256) prep_rows_kernel(PrepArgs a) {
+  const int lane = threadIdx.x & 31;
+  const long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= a.P) return;
+  int off = 0;
+  for (int s = 0; s < a.n_src; ++s) {
+    const float* p = a.src[s] + (r / a.row_div[s]) * a.C[s];
+    float scale = 1.f;
+    if (a.l2norm[s]) {
+      float ss = 0.f;
+      for (int c = lane; c < a.C[s]; c += 32) ss += p[c] * p[c];
+      scale = 1.0f / sqrtf(warp_sum(ss));
+    }
+    for (int c = lane; c < a.C[s]; c += 32) {
+      float y = p[c] * scale;
+      if (a.mean) { y = (y - a.mean[c]) * a.rstd[c]; }
+      if (a.relu) y = fmaxf(y, 0.f);
+      uint32_t tb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tb) : "f"(y));
+      const float h = __uint_as_float(tb);
+      a.hi[r * a.Kout + off + c] = h; a.lo[r * a.Kout + off + c] = y - h;
+      if (a.plain) a.plain[r * a.Kout + off + c] = y;
+    }
+    off += a.C[s];
+  }
+  for (int c = off + lane; c < a.Kout; c += 32) { a.hi[r * a.Kout + c] = 0.f; a.lo[r * a.Kout + c] = 0.f; if (a.plain) a.plain[r * a.Kout + c] = 0.f; }
+}
+
+// ---- 4-head attention of each point over its k neighbours (rot_coh_match.py:84-119), projections already applied ---
+// Q [m][32], Kp / Vp [m*k][32]; channel c = d*4 + h.  One warp per point, lane = channel.
+__global__ void __launch_bounds__(256) mha_kernel(const float* __restrict__ Q, const float* __restrict__ Kp, const float* __restrict__ Vp,
+                                                  int m, int k, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (i >= m) return;
+  const float q = Q[(long long)i * 32 + lane];
+  float sc[16];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float v = -INFINITY;
+    if (j < k) {
+      v = q * Kp[((long long)i * k + j) * 32 + lane];
+      v += __shfl_xor_sync(0xffffffffu, v, 4); v += __shfl_xor_sync(0xffffffffu, v, 8); v += __shfl_xor_sync(0xffffffffu, v, 16);  // sum over d (lanes with equal h)
+      v = v / 2.8284271247461903f;            // / dim**.5, dim = 8
+    }
+    sc[j] = v; mx = fmaxf(mx, v);
+  }
+  float den = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) { sc[j] = (j < k) ? expf(sc[j] - mx) : 0.f; den += sc[j]; }
+  float o = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) if (j < k) o += (sc[j] / den) * Vp[((long long)i * k + j) * 32 + lane];
+  out[(long long)i * 32 + lane] = o;
+}
+
+// ---- [rind | column max over the points] -> [m][128] rows (120 used), rot_coh_match.py:203 ---------------------------
+__global__ void colmax60_kernel(const float* __restrict__ rind /*[m][60]*/, int m, float* __restrict__ cmax /*[60]*/) {
+  const int h = blockIdx.x; float v = -INFINITY;
+  for (int i = threadIdx.x; i < m; i += blockDim.x) v = fmaxf(v, rind[(long long)i * 60 + h]);
+  __shared__ float sm[256];
+  sm[threadIdx.x] = v; __syncthreads();
+  for (int s = blockDim.x / 2; s > 0; s >>= 1) { if (threadIdx.x < s) sm[threadIdx.x] = fmaxf(sm[threadIdx.x], sm[threadIdx.x + s]); __syncthreads(); }
+  if (threadIdx.x == 0) cmax[h] = sm[0];
+}
+__global__ void rind_rows_kernel(const float* __restrict__ rind, const float* __restrict__ cmax, int m, float* __restrict__ out /*[m][128]*/) {
+  const long long e = blockIdx.x * 256LL + threadIdx.x;
+  if (e >= (long long)m * 128) return;
+  const long long i = e >> 7; const int c = (int)(e & 127);
+  out[e] = (c < 60) ? rind[i * 60 + c] : (c < 120 ? cmax[c - 60] : 0.f);
+}
+
+// ---- Sinkhorn (rot_coh_match.py:277-319).  Z = [[S, alpha],[alpha, alpha]] is never materialised: S [m][n] + the bin.
+// rows:  u[i] = log_mu[i] - logsumexp_j(Z[i][j] + v[j])     (one CTA per row, coalesced)
+// cols:  v[j] = log_nu[j] - logsumexp_i(Z[i][j] + u[i])     (CTA = 32 columns x 8 row-lanes, online max/sum)
+struct SinkArgs { const float* S; int m, n, ld; float alpha; float norm; float* u; float* v; };
+
+__device__ __forceinline__ void lse_merge(float& mx, float& sm, float omx, float osm) {
+  const float nm = fmaxf(mx, omx);
+  if (nm == -INFINITY) { mx = nm; sm = 0.f; return; }
+  sm = sm * expf(mx - nm) + osm * expf(omx - nm); mx = nm;
+}
+
+__global__ void __launch_bounds__(256) sinkhorn_rows_kernel(SinkArgs a) {
+  __shared__ float smx[8], ssm[8];
+  const int i = blockIdx.x, tid = threadIdx.x;          // i in [0, m]  (row m = the dustbin row)
+  float mx = -INFINITY, sm = 0.f;
+  for (int j = tid; j <= a.n; j += 256) {
+    const float z = (i < a.m && j < a.n) ? a.S[(long long)i * a.ld + j] : a.alpha;
+    const float t = z + a.v[j];
+    if (t > mx) { sm = sm * expf(mx - t) + 1.f; mx = t; } else sm += expf(t - mx);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o); lse_merge(mx, sm, om, os); }
+  if ((tid & 31) == 0) { smx[tid >> 5] = mx; ssm[tid >> 5] = sm; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) lse_merge(mx, sm, smx[w], ssm[w]);
+    const float log_mu = (i < a.m) ? a.norm : (logf((float)a.n) + a.norm);
+    a.u[i] = log_mu - (mx + logf(sm));
+  }
+}
+
+__global__ void __launch_bounds__(256) sinkhorn_cols_kernel(SinkArgs a) {
+  __shared__ float smx[8][33], ssm[8][33];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;                 // j in [0, n]
+  float mx = -INFINITY, sm = 0.f;
+  if (j <= a.n) {
+    for (int i = rl; i <= a.m; i += 8) {
+      const float z = (i < a.m && j < a.n) ? a.S[(long long)i * a.ld + j] : a.alpha;
+      const float t = z + a.u[i];
+      if (t > mx) { sm = sm * expf(mx - t) + 1.f; mx = t; } else sm += expf(t - mx);
+    }
+  }
+  smx[rl][lane] = mx; ssm[rl][lane] = sm;
+  __syncthreads();
+  if (rl == 0 && j <= a.n) {
+    for (int w = 1; w < 8; ++w) lse_merge(mx, sm, smx[w][lane], ssm[w][lane]);
+    const float log_nu = (j < a.n) ? a.norm : (logf((float)a.m) + a.norm);
+    a.v[j] = log_nu - (mx + logf(sm));
+  }
+}
+
+// final assignment (rot_coh_match.py:369-379): row / column argmax of Z + u + v - norm on the inner [m][n] block
+__global__ void __launch_bounds__(256) ot_row_argmax_kernel(SinkArgs a, int32_t* __restrict__ idx0, float* __restrict__ max0) {
+  __shared__ float sv[8]; __shared__ int si[8];
+  const int i = blockIdx.x, tid = threadIdx.x;
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  for (int j = tid; j < a.n; j += 256) {
+    const float t = a.S[(long long)i * a.ld + j] + a.u[i] + a.v[j] - a.norm;
+    if (t > bv) { bv = t; bi = j; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float vo = __shfl_xor_sync(0xffffffffu, bv, o); const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (vo > bv || (vo == bv && io < bi)) { bv = vo; bi = io; }
+  }
+  if ((tid & 31) == 0) { sv[tid >> 5] = bv; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) if (sv[w] > bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    idx0[i] = bi; max0[i] = bv;
+  }
+}
+__global__ void __launch_bounds__(256) ot_col_argmax_kernel(SinkArgs a, int32_t* __restrict__ idx1) {
+  __shared__ float sv[8][33]; __shared__ int si[8][33];
+  const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + lane;
+  float bv = -INFINITY; int bi = 0x7fffffff;
+  if (j < a.n)
+    for (int i = rl; i < a.m; i += 8) {
+      const float t = a.S[(long long)i * a.ld + j] + a.u[i] + a.v[j] - a.norm;
+      if (t > bv) { bv = t; bi = i; }
+    }
+  sv[rl][lane] = bv; si[rl][lane] = bi;
+  __syncthreads();
+  if (rl == 0 && j < a.n) {
+    for (int w = 1; w < 8; ++w) if (sv[w][lane] > bv || (sv[w][lane] == bv && si[w][lane] < bi)) { bv = sv[w][lane]; bi = si[w][lane]; }
+    idx1[j] = bi;
+  }
+}
+// matches0 / matching_scores0 (rot_coh_match.py:371-378): mutual0 = (i == indices1[indices0[i]])
+__global__ void ot_mutual_kernel(const int32_t* __restrict__ idx0, const float* __restrict__ max0, const int32_t* __restrict__ idx1,
+                                 int m, int32_t* __restrict__ matches0, float* __restrict__ mscores0) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  const int j = idx0[i];
+  const bool mutual = (idx1[j] == i);
+  matches0[i] = mutual ? j : -1;
+  mscores0[i] = mutual ? expf(max0[i]) : 0.f;
+}
+
+}  // namespace roreg
