@@ -135,6 +135,33 @@ int roreg_rd_finalize(roreg_ctx* ctx, const float* raw, int n, float* feat_out, 
 int roreg_row_std60(roreg_ctx* ctx, const float* cor, int n, float* out, void* stream);
 int roreg_quat_normalize(roreg_ctx* ctx, const float* q_in, int ld, int K, float* q_out, void* stream);
 
+/* ---- a6-a11  glue of the rotation-coherence matcher Match_ot (network/rot_coh_match.py); the dense layers and the
+ * [m,n] score matrices (score_mat :8-12) use roreg_gemm, the R-indicator (:154-163) roreg_group_corr variant 2.   */
+/* Knn_index_extract :34-45: first k columns of the descending argsort of every row (ties -> lower column).        */
+int roreg_topk_rows(roreg_ctx* ctx, const float* S, int m, int n, int ld, int k, int32_t* idx, void* stream);
+/* Knn_feat_extract :48-60: out[r][:] = src[idx[r]][:]                                                              */
+int roreg_gather_rows(roreg_ctx* ctx, const float* src, const int32_t* idx, long long n_out, int C, float* out,
+                      void* stream);
+/* :194-195 knn_coor - coor on coordinates divided by `step` (coor_norm_step :328,:342-343); rows [(i*k+j)][32],
+ * 3 used, zero padded                                                                                              */
+int roreg_rel_coor(roreg_ctx* ctx, const float* coor, const int32_t* idx, int m, int k, float step, float* out,
+                   void* stream);
+/* nn.InstanceNorm2d(affine=False) statistics over all P positions of x [P][C] (:18,:68)                           */
+int roreg_chan_stats(roreg_ctx* ctx, const float* x, long long P, int C, float* mean, float* rstd, void* stream);
+/* GEMM operand preparation: channel concat of <= 3 sources (row broadcast by row_div, optional L2 normalisation
+ * over the source's channels :204-206), optional instance norm + ReLU, zero pad to Kout, tf32 hi/lo split.        */
+int roreg_prep_rows(roreg_ctx* ctx, int n_src, const float* const* src_host, const int32_t* C_host,
+                    const int32_t* rowdiv_host, const int32_t* l2_host, const float* mean, const float* rstd, int relu,
+                    long long P, int Kout, float* hi, float* lo, float* plain, void* stream);
+/* attention :84-92 + head layout of :105-119 on projected Q [m][32], K / V [m*k][32]                              */
+int roreg_mha(roreg_ctx* ctx, const float* Q, const float* Kp, const float* Vp, int m, int k, float* out, void* stream);
+/* :203  [R_ind ; max over the points] -> rows [m][128] (120 used)                                                  */
+int roreg_rind_rows(roreg_ctx* ctx, const float* rind, int m, float* out128, void* stream);
+/* sinkhorn_ot :277-319 (dustbin alpha, `iters` log-domain iterations; the (m+1)x(n+1) coupling matrix is never
+ * materialised) + the mutual assignment of :369-378.  u [m+1], v [n+1] are the final potentials.                  */
+int roreg_sinkhorn_match(roreg_ctx* ctx, const float* S, int m, int n, int ld, float alpha, int iters, float* u,
+                         float* v, int32_t* matches0, float* mscores0, void* stream);
+
 /* ---- batched engine: B independent pairs per call (the throughput path bench.py times) ------------
  * Clouds live in one arena: desc [n_clouds][n][32][60] float32, keys [n_clouds][n][3] float64.
  * pair_cloud [B][2] int32 = (cloud id0, cloud id1).  sample [B][2][keynum] int32 or NULL (identity,

@@ -455,6 +455,28 @@ def random_state_dict(kind, seed):
         sd["PartII_To_R_FC.6.bias"] = (np.array([3.0, 0, 0, 0]) + 0.02 * rng.standard_normal(4)).astype(F32)
     elif kind == "RD":
         rcc("eqv_encoder.0", 32, 64, 16)
+    elif kind == "RM":
+        def c1(name, cout, cin):
+            sd[name + ".weight"] = (rng.standard_normal((cout, cin, 1, 1)) / np.sqrt(cin)).astype(F32)
+            sd[name + ".bias"] = (0.1 * rng.standard_normal(cout)).astype(F32)
+
+        def mlp(p, cin, mid, cout):
+            c1(p + ".net.0", mid, cin); c1(p + ".net.3", cout, mid)
+            if cin != cout: c1(p + ".res", cout, cin)
+
+        def mhattn(p):
+            c1(p + ".merge", 32, 32)
+            for i in range(3): c1(p + f".proj.{i}", 32, 32)
+        for b in range(2):
+            for cg in ("cross_graph_s2t", "cross_graph_t2s"):
+                p = f"Graph.merge_blocks.{b}.{cg}"
+                mhattn(p + ".cross_attn"); mlp(p + ".merge", 96, 64, 32)
+            for sg in ("self_graph_s", "self_graph_t"):
+                p = f"Graph.merge_blocks.{b}.{sg}"
+                mhattn(p + ".self_attn"); mlp(p + ".pos_en", 3, 64, 32); mlp(p + ".ambiguity", 120, 128, 32)
+                mlp(p + ".val_en", 96, 64, 32); mlp(p + ".merge", 96, 64, 32)
+        mlp("final_mlp", 64, 64, 32)
+        sd["ot_layer.bin_score"] = np.array(1.0, F32)
     else:
         raise KeyError(kind)
     return sd

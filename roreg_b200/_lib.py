@@ -48,6 +48,14 @@ SIGNATURES = {
     "roreg_rd_finalize": (_i, [_p, _p, _i, _p, _p]),
     "roreg_row_std60": (_i, [_p, _p, _i, _p, _p]),
     "roreg_quat_normalize": (_i, [_p, _p, _i, _i, _p, _p]),
+    "roreg_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
+    "roreg_gather_rows": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p]),
+    "roreg_rel_coor": (_i, [_p, _p, _p, _i, _i, C.c_float, _p, _p]),
+    "roreg_chan_stats": (_i, [_p, _p, C.c_longlong, _i, _p, _p, _p]),
+    "roreg_prep_rows": (_i, [_p, _i, _p, _p, _p, _p, _p, _p, _i, C.c_longlong, _i, _p, _p, _p, _p]),
+    "roreg_mha": (_i, [_p, _p, _p, _p, _i, _i, _p, _p]),
+    "roreg_rind_rows": (_i, [_p, _p, _i, _p, _p]),
+    "roreg_sinkhorn_match": (_i, [_p, _p, _i, _i, _i, C.c_float, _i, _p, _p, _p, _p, _p]),
     "roreg_register_batch": (_i, [_p, C.POINTER(RoregBatch), _p]),
     "roreg_set_timing": (_i, [_p, _i]),
     "roreg_get_stage_ms": (_i, [_p, C.POINTER(C.c_float)]),

@@ -49,14 +49,14 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float* __restric
   }
 }
 
-// ---- relative neighbour coordinates: out[(i*k+j)][0..2] = coor[idx[i*k+j]] - coor[i], zero-padded to 32 -----------
+// ---- relative neighbour coordinates: out[(i*k+j)][0..2] = (coor[idx[i*k+j]] - coor[i]) in units of `step`, zero-padded to 32
 __global__ void __launch_bounds__(256) rel_coor_kernel(const float* __restrict__ coor /*[m][3]*/, const int32_t* __restrict__ idx,
-                                                       int m, int k, float* __restrict__ out /*[m*k][32]*/) {
+                                                       int m, int k, float step, float* __restrict__ out /*[m*k][32]*/) {
   const long long total = (long long)m * k * 32;
   for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
     const long long r = e >> 5; const int c = (int)(e & 31);
     float v = 0.f;
-    if (c < 3) v = coor[(long long)idx[r] * 3 + c] - coor[(r / k) * 3 + c];
+    if (c < 3) v = __fdiv_rn(coor[(long long)idx[r] * 3 + c], step) - __fdiv_rn(coor[(r / k) * 3 + c], step);   // keys / coor_norm_step (:342-343)
     out[e] = v;
   }
 }

@@ -7,6 +7,7 @@
 #include "kernels_corr_tc.cuh"
 #include "kernels_gemm_tc.cuh"
 #include "kernels_gconv.cuh"
+#include "kernels_matchot.cuh"
 
 using namespace roreg;
 
@@ -321,6 +322,121 @@ int roreg_quat_normalize(roreg_ctx* c, const float* q_in, int ld, int K, float* 
   RR_ARG(c, q_in && q_out && ld >= 4 && K >= 0);
   if (K == 0) return ROREG_OK;
   quat_normalize_kernel<<<(K + 127) / 128, 128, 0, (cudaStream_t)stream>>>(q_in, ld, K, q_out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Match_ot glue (network/rot_coh_match.py)
+// ------------------------------------------------------------------------------------------------
+static inline unsigned rr_blocks(roreg_ctx* c, long long work, int per_block) {
+  long long b = (work + per_block - 1) / per_block;
+  const long long cap = (long long)c->sm_count * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int roreg_topk_rows(roreg_ctx* c, const float* S, int m, int n, int ld, int k, int32_t* idx, void* stream) {
+  RR_ARG(c, S && idx && m >= 0 && n >= 1 && ld >= n && k >= 1 && k <= 16 && k <= n && n <= 11000);
+  if (m == 0) return ROREG_OK;
+  topk_rows_kernel<<<m, 256, n * sizeof(float), (cudaStream_t)stream>>>(S, n, ld, k, idx);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_gather_rows(roreg_ctx* c, const float* src, const int32_t* idx, long long n_out, int C, float* out, void* stream) {
+  RR_ARG(c, src && idx && out && n_out >= 0 && C >= 4 && (C % 4) == 0);
+  if (n_out == 0) return ROREG_OK;
+  gather_rows_kernel<<<rr_blocks(c, n_out * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(src, idx, n_out, C, out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_rel_coor(roreg_ctx* c, const float* coor, const int32_t* idx, int m, int k, float step, float* out, void* stream) {
+  RR_ARG(c, coor && idx && out && m >= 0 && k >= 1 && step > 0);
+  if (m == 0) return ROREG_OK;
+  rel_coor_kernel<<<rr_blocks(c, (long long)m * k * 32, 256), 256, 0, (cudaStream_t)stream>>>(coor, idx, m, k, step, out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_chan_stats(roreg_ctx* c, const float* x, long long P, int C, float* mean, float* rstd, void* stream) {
+  RR_ARG(c, x && mean && rstd && P >= 1 && C >= 1 && C <= 256 && (256 % C) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rr_ws_reserve(c, 4096 + sizeof(double) * 2 * 256);
+  if (rc) return rc;
+  double* acc = reinterpret_cast<double*>(c->ws);
+  RR_CUDA(c, cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  chan_stats_kernel<<<rr_blocks(c, P, 256 / C * 8), 256, 0, st>>>(x, P, C, acc);
+  RR_LAUNCH_CHECK(c);
+  chan_stats_finish_kernel<<<(C + 63) / 64, 64, 0, st>>>(acc, P, C, mean, rstd);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_prep_rows(roreg_ctx* c, int n_src, const float* const* src_host, const int32_t* C_host, const int32_t* rowdiv_host,
+                    const int32_t* l2_host, const float* mean, const float* rstd, int relu, long long P, int Kout, float* hi,
+                    float* lo, float* plain, void* stream) {
+  RR_ARG(c, n_src >= 1 && n_src <= 3 && src_host && C_host && hi && lo && P >= 0 && Kout >= 1);
+  RR_ARG(c, (mean == nullptr) == (rstd == nullptr));
+  if (P == 0) return ROREG_OK;
+  PrepArgs a{};
+  int tot = 0;
+  for (int s = 0; s < n_src; ++s) {
+    RR_ARG(c, src_host[s] != nullptr && C_host[s] >= 1);
+    a.src[s] = src_host[s]; a.C[s] = C_host[s]; a.row_div[s] = rowdiv_host ? rowdiv_host[s] : 1; a.l2norm[s] = l2_host ? l2_host[s] : 0;
+    RR_ARG(c, a.row_div[s] >= 1);
+    tot += C_host[s];
+  }
+  RR_ARG(c, tot <= Kout && (mean == nullptr || n_src == 1));
+  a.n_src = n_src; a.mean = mean; a.rstd = rstd; a.relu = relu; a.P = P; a.Kout = Kout; a.hi = hi; a.lo = lo; a.plain = plain;
+  prep_rows_kernel<<<(unsigned)((P + 7) / 8), 256, 0, (cudaStream_t)stream>>>(a);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_mha(roreg_ctx* c, const float* Q, const float* Kp, const float* Vp, int m, int k, float* out, void* stream) {
+  RR_ARG(c, Q && Kp && Vp && out && m >= 0 && k >= 1 && k <= 16);
+  if (m == 0) return ROREG_OK;
+  mha_kernel<<<(m + 7) / 8, 256, 0, (cudaStream_t)stream>>>(Q, Kp, Vp, m, k, out);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_rind_rows(roreg_ctx* c, const float* rind, int m, float* out128, void* stream) {
+  RR_ARG(c, rind && out128 && m >= 1);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rr_ws_reserve(c, 4096);
+  if (rc) return rc;
+  float* cmax = reinterpret_cast<float*>(c->ws);
+  colmax60_kernel<<<60, 256, 0, st>>>(rind, m, cmax);
+  RR_LAUNCH_CHECK(c);
+  rind_rows_kernel<<<(unsigned)(((long long)m * 128 + 255) / 256), 256, 0, st>>>(rind, cmax, m, out128);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
+int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, float alpha, int iters, float* u, float* v,
+                         int32_t* matches0, float* mscores0, void* stream) {
+  RR_ARG(c, S && u && v && matches0 && mscores0 && m >= 1 && n >= 1 && ld >= n && iters >= 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * m) + rr_align(sizeof(float) * m) + rr_align(sizeof(int32_t) * n) + 4096);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  int32_t* idx0 = ar.take<int32_t>(m); float* max0 = ar.take<float>(m); int32_t* idx1 = ar.take<int32_t>(n);
+  RR_CUDA(c, cudaMemsetAsync(u, 0, sizeof(float) * (m + 1), st));
+  RR_CUDA(c, cudaMemsetAsync(v, 0, sizeof(float) * (n + 1), st));
+  SinkArgs a{S, m, n, ld, alpha, -logf((float)(m + n)), u, v};
+  for (int it = 0; it < iters; ++it) {
+    sinkhorn_rows_kernel<<<m + 1, 256, 0, st>>>(a);
+    RR_LAUNCH_CHECK(c);
+    sinkhorn_cols_kernel<<<(n + 1 + 31) / 32, 256, 0, st>>>(a);
+    RR_LAUNCH_CHECK(c);
+  }
+  ot_row_argmax_kernel<<<m, 256, 0, st>>>(a, idx0, max0);
+  RR_LAUNCH_CHECK(c);
+  ot_col_argmax_kernel<<<(n + 31) / 32, 256, 0, st>>>(a, idx1);
+  RR_LAUNCH_CHECK(c);
+  ot_mutual_kernel<<<(m + 127) / 128, 128, 0, st>>>(idx0, max0, idx1, m, matches0, mscores0);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

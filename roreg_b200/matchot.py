@@ -1,0 +1,171 @@
+"""Rotation-coherence matcher Match_ot (network/rot_coh_match.py:323-390) on the B200 library, inference only.
+
+Host side = the layer schedule; all arithmetic runs in libroreg_b200.so: tcgen05 GEMMs for the 1x1 layers and the
+[m,n] score matrices (score_mat :8-12), group-correlation kernel (variant 2) for the R-indicator (:154-163), and the
+glue kernels of kernels_matchot.cuh (top-k instead of the full argsort, gathers, 4-head attention, instance-norm
+statistics, operand preparation, log-domain Sinkhorn).  Activations are channel-last rows [positions][C]."""
+import ctypes as C
+import numpy as np
+import torch
+
+from . import _lib, nets
+from .ops import _ptr, _stream
+
+
+def _pad32(c):
+    return -(-c // 32) * 32
+
+
+class MatchOT:
+    def __init__(self, ctx, sd, npass=3, sinkhorn_iters=100):
+        self.ctx, self.lib, self.npass, self.iters = ctx, ctx.lib, npass, sinkhorn_iters
+        self.g = nets.GroupNets(ctx, npass)
+        self.sd = sd
+        self.L = {}
+        self.alpha = float(sd["ot_layer.bin_score"])
+
+    # ---------------------------------------------------------------- helpers
+    def _f(self, *shape):
+        return torch.empty(shape, dtype=torch.float32, device=self.ctx.device)
+
+    def layer(self, name):
+        """conv1x1 `name` as a GEMM layer; input channels zero-padded to a multiple of 32."""
+        if name not in self.L:
+            W = np.asarray(self.sd[name + ".weight"], np.float32); O, Cin = W.shape[0], W.shape[1]
+            Wp = np.zeros((O, _pad32(Cin), 1, 1), np.float32); Wp[:, :Cin, 0, 0] = W.reshape(O, Cin)
+            self.L[name] = nets.Layer(self.ctx, Wp, self.sd[name + ".bias"])
+        return self.L[name]
+
+    def prep(self, srcs, P, Kout=None, row_div=None, l2=None, stats=None, relu=False, rows_alloc=None):
+        """concat(+normalise)(+instance norm, ReLU) -> tf32 (hi, lo) operand [P][Kout]."""
+        n = len(srcs); Cs = [int(s.shape[-1]) for s in srcs]
+        Kout = Kout or _pad32(sum(Cs))
+        R = rows_alloc or P
+        hi = torch.zeros((R, Kout), dtype=torch.float32, device=self.ctx.device) if R != P else self._f(R, Kout)
+        lo = torch.zeros_like(hi) if R != P else self._f(R, Kout)
+        sp = (C.c_void_p * n)(*[s.data_ptr() for s in srcs])
+        cp = (C.c_int32 * n)(*Cs)
+        rd = (C.c_int32 * n)(*(row_div or [1] * n))
+        lp = (C.c_int32 * n)(*(l2 or [0] * n))
+        mean, rstd = stats if stats is not None else (None, None)
+        rc = self.lib.roreg_prep_rows(self.ctx.h, n, sp, cp, rd, lp, _ptr(mean), _ptr(rstd), int(relu), P, Kout, _ptr(hi), _ptr(lo), None, _stream())
+        _lib.check(self.ctx.h, rc, "roreg_prep_rows")
+        return hi, lo
+
+    def conv(self, A, P, name, residual=None):
+        L = self.layer(name)
+        raw, _ = self.g.gemm(A, P, L, residual=residual, res_ld=L.O if residual is not None else 0, want_raw=True, want_act=False)
+        return raw
+
+    def stats(self, x, P, Cch):
+        mean = self._f(Cch); rstd = self._f(Cch)
+        rc = self.lib.roreg_chan_stats(self.ctx.h, _ptr(x), P, Cch, _ptr(mean), _ptr(rstd), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_chan_stats")
+        return mean, rstd
+
+    def mlp(self, A, P, p):
+        """mlp_2layer / Contextnorm (:14-32, :63-81): conv - InstanceNorm - ReLU - conv (+ 1x1 residual when in != out)."""
+        h = self.conv(A, P, p + ".net.0")
+        mid = h.shape[1]
+        A2 = self.prep([h], P, stats=self.stats(h, P, mid), relu=True)
+        res = self.conv(A, P, p + ".res") if (p + ".res.weight") in self.sd else None
+        return self.conv(A2, P, p + ".net.3", residual=res)
+
+    def score(self, a, m, b, n):
+        """score_mat (:8-12): S[m][n] = a . b^T on the tensor cores (operand rows padded to the 256-row N tile)."""
+        A = self.prep([a], m)
+        rows = -(-n // 256) * 256
+        W = self.prep([b], n, rows_alloc=rows)
+        S = self._f(m, n)
+        NT = min(256, -(-n // 16) * 16)
+        rc = self.lib.roreg_gemm(self.ctx.h, _ptr(A[0]), _ptr(A[1]), m, 32, _ptr(W[0]), _ptr(W[1]), rows, n, NT, self.npass, None, None, 0,
+                                 _ptr(S), n, None, None, 0, None, None, 0, _stream())
+        _lib.check(self.ctx.h, rc, "roreg_gemm(score)")
+        return S
+
+    def topk(self, S, m, n, k):
+        idx = torch.empty((m, k), dtype=torch.int32, device=self.ctx.device)
+        rc = self.lib.roreg_topk_rows(self.ctx.h, _ptr(S), m, n, n, k, _ptr(idx), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_topk_rows")
+        return idx
+
+    def gather(self, src, idx, Cch):
+        n_out = idx.numel()
+        out = self._f(n_out, Cch)
+        rc = self.lib.roreg_gather_rows(self.ctx.h, _ptr(src), _ptr(idx), n_out, Cch, _ptr(out), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_gather_rows")
+        return out
+
+    def mha(self, query, key_A, val_A, m, k, p):
+        """MultiHeadedAttention (:95-119): key_A / val_A are prepared operands [m*k][32]."""
+        Q = self.conv(self.prep([query], m), m, p + ".proj.0")
+        Kp = self.conv(key_A, m * k, p + ".proj.1")
+        Vp = self.conv(val_A, m * k, p + ".proj.2")
+        att = self._f(m, 32)
+        rc = self.lib.roreg_mha(self.ctx.h, _ptr(Q), _ptr(Kp), _ptr(Vp), m, k, _ptr(att), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_mha")
+        return self.conv(self.prep([att], m), m, p + ".merge")
+
+    # ---------------------------------------------------------------- blocks
+    def cross_block(self, src, m, tgt, n, src_eqv, tgt_eqv, featinv, k, s2t, p):
+        """Cross_attention_block.forward (:132-165)."""
+        S = self.score(src, m, tgt, n)
+        knn = self.topk(S, m, n, k)
+        del S
+        nn = knn[:, 0].contiguous()
+        knn_fea = self.gather(tgt, knn, 32)
+        kA = self.prep([knn_fea], m * k)
+        feat = self.mha(src, kA, kA, m, k, p + ".cross_attn")
+        feat = self.mlp(self.prep([featinv, src, feat], m), m, p + ".merge")
+        if s2t:    # sum_{f,g} S[f,P[g,h]] T_nn[f,g]
+            rind, _ = self.ctx.group_corr(src_eqv, tgt_eqv, None, nn, variant=2, want_argmax=False)
+        else:      # sum_{f,g} T_nn[f,P[g,h]] S[f,g]   (:162-163)
+            ident = torch.arange(m, dtype=torch.int32, device=self.ctx.device)
+            rind, _ = self.ctx.group_corr(tgt_eqv, src_eqv, nn, ident, variant=2, want_argmax=False)
+        return feat, rind                                   # [m][32], [m][60]
+
+    def self_block(self, feat, m, coor, rind, featinv, k, p):
+        """Self_attention_block.forward (:187-210)."""
+        S = self.score(feat, m, feat, m)
+        knn = self.topk(S, m, m, k)
+        del S
+        knn_fea = self.gather(feat, knn, 32)
+        rel = self._f(m * k, 32)
+        rc = self.lib.roreg_rel_coor(self.ctx.h, _ptr(coor), _ptr(knn), m, k, C.c_float(0.025), _ptr(rel), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_rel_coor")
+        pe = self.mlp(self.prep([rel], m * k, Kout=32), m * k, p + ".pos_en")
+        r2 = self._f(m, 128)
+        rc = self.lib.roreg_rind_rows(self.ctx.h, _ptr(rind), m, _ptr(r2), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_rind_rows")
+        conf = self.mlp(self.prep([r2], m, Kout=128), m, p + ".ambiguity")
+        vA = self.prep([pe, knn_fea, conf], m * k, row_div=[1, 1, k], l2=[1, 1, 1])          # :204-207
+        value = self.mlp(vA, m * k, p + ".val_en")
+        kA = self.prep([knn_fea], m * k, l2=[1])
+        out = self.mha(feat, kA, self.prep([value], m * k), m, k, p + ".self_attn")
+        return self.mlp(self.prep([featinv, feat, out], m), m, p + ".merge")
+
+    # ---------------------------------------------------------------- forward
+    def forward(self, src_eqv, tgt_eqv, keys_src, keys_tgt):
+        """src_eqv / tgt_eqv: [m,32,60] / [n,32,60] float32 (the batch's feats0 / feats1), keys_*: [m,3] float32.
+        Returns matches0 [m] int32 (-1 = unmatched) and matching_scores0 [m] float32 (device tensors)."""
+        ctx = self.ctx
+        m, n = src_eqv.shape[0], tgt_eqv.shape[0]
+        s_inv = ctx.inv_pool(src_eqv, None, normalise=False); t_inv = ctx.inv_pool(tgt_eqv, None, normalise=False)
+        sc = keys_src.contiguous(); tc = keys_tgt.contiguous()       # divided by coor_norm_step inside roreg_rel_coor (:342-343)
+        src, tgt = s_inv, t_inv
+        for li, k in enumerate((16, 8)):
+            p = f"Graph.merge_blocks.{li}"
+            s2t, r_s = self.cross_block(src, m, tgt, n, src_eqv, tgt_eqv, s_inv, k, True, p + ".cross_graph_s2t")
+            eh_s = self.self_block(s2t, m, sc, r_s, s_inv, k, p + ".self_graph_s")
+            t2s, r_t = self.cross_block(tgt, n, src, m, tgt_eqv, src_eqv, t_inv, k, False, p + ".cross_graph_t2s")
+            eh_t = self.self_block(t2s, n, tc, r_t, t_inv, k, p + ".self_graph_t")
+            src, tgt = eh_s, eh_t
+        s_fin = self.mlp(self.prep([s_inv, src], m), m, "final_mlp")
+        t_fin = self.mlp(self.prep([t_inv, tgt], n), n, "final_mlp")
+        S = self.score(s_fin, m, t_fin, n)
+        u = self._f(m + 1); v = self._f(n + 1)
+        matches0 = torch.empty(m, dtype=torch.int32, device=ctx.device); ms0 = self._f(m)
+        rc = self.lib.roreg_sinkhorn_match(ctx.h, _ptr(S), m, n, n, C.c_float(self.alpha), self.iters, _ptr(u), _ptr(v), _ptr(matches0),
+                                           _ptr(ms0), _stream())
+        _lib.check(ctx.h, rc, "roreg_sinkhorn_match")
+        return matches0, ms0

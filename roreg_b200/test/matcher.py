@@ -94,13 +94,50 @@ class mutual():
 
 
 class yoho_mat():
-    """test/matcher.py:111-210 - rotation-coherence matcher (Match_ot).  SURVEY.md section 8(f) rank 2:
-    the graph blocks + Sinkhorn kernels are not in this build; constructing the plugin fails loudly
-    rather than running the PyTorch network (no fallback paths in the product)."""
+    """test/matcher.py:111-210 - rotation-coherence matcher (Match_ot, --RM)."""
 
     def __init__(self, cfg):
-        raise NotImplementedError("yoho_mat (--RM, Match_ot) kernels are not part of this build; "
-                                  "use the mutual matcher ('matmul')")
+        from .extractor import load_state_dict
+        from .. import matchot
+        self.cfg = cfg
+        self.ctx = context(cfg)
+        self.best_model_fn = f'{self.cfg.model_fn}/RM/model_best.pth'
+        self.npass = int(getattr(cfg, "net_passes", 3))
+        self.network = matchot.MatchOT(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass)
+
+    def get_ot_match(self, feats_src, feats_tgt, keys_src, keys_tgt):
+        """test/matcher.py:131-150 on device tensors: pairs [K,2] = (index in 'source', its match), scores [K]."""
+        matches0, scores = self.network.forward(feats_src, feats_tgt, keys_src, keys_tgt)
+        matches0 = matches0.cpu().numpy(); scores = scores.cpu().numpy()
+        sel = np.where(matches0 != -1)[0]
+        if sel.shape[0] < 3:
+            return None, scores[sel]
+        return np.stack([sel, matches0[sel]], axis=1).astype(np.int64), scores[sel]
 
     def run(self, dataset, keynum=2500):
-        raise NotImplementedError
+        self.sampler = NMS_sample(keynum, 5, self.cfg)
+        Save_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
+        make_non_exists_dir(Save_dir)
+        Save_score_dir = f'{Save_dir}/scores'
+        make_non_exists_dir(Save_score_dir)
+        datasetname = feature_dataset_name(dataset)
+        Feature_dir = f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature'
+        print(f'Matching the keypoints with rotation coherence matcher on {dataset.name}')
+        cache = CloudCache(self.ctx)
+        for pair in tqdm.tqdm(dataset.pair_ids):
+            id0, id1 = pair
+            feats0 = cache.get(f'{Feature_dir}/{id0}.npy')
+            feats1 = cache.get(f'{Feature_dir}/{id1}.npy')
+            sample0, sample1 = _sample_pair(self.cfg, dataset, datasetname, self.sampler, id0, id1,
+                                            feats0.shape[0], feats1.shape[0], keynum)
+            s0 = self.ctx.dev(sample0.astype(np.int64)); s1 = self.ctx.dev(sample1.astype(np.int64))
+            f0 = feats0[s0].contiguous(); f1 = feats1[s1].contiguous()                # plumbing: row selection of the sampled keypoints
+            keys0 = self.ctx.dev(dataset.get_kps(id0)[sample0].astype(np.float32))
+            keys1 = self.ctx.dev(dataset.get_kps(id1)[sample1].astype(np.float32))
+            # NOTE THE SWAP (test/matcher.py:192-197): the network's "source" (feats0/keys0) is cloud id1
+            matches, scores = self.get_ot_match(f1, f0, keys1, keys0)
+            if matches is None:
+                raise TypeError("ones() takes 1 positional argument")                 # np.ones(1,2) in the reference (:201)
+            matches_in_former = np.concatenate([sample0[matches[:, 1]][:, None], sample1[matches[:, 0]][:, None]], axis=1)
+            np.save(f'{Save_dir}/{id0}-{id1}.npy', matches_in_former)
+            np.save(f'{Save_score_dir}/{id0}-{id1}.npy', scores)

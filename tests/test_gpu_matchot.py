@@ -1,0 +1,98 @@
+"""Rotation-coherence matcher on the GPU: building blocks against NumPy, MatchOT.forward against the oracle, and the
+yoho_mat plugin against the files the UNMODIFIED reference wrote (tests/golden/rm300.npz)."""
+import os
+import types
+import numpy as np
+import pytest
+import torch
+from conftest import load_golden
+from oracle import roreg_oracle as O
+from roreg_b200 import synth
+from test_oracle_golden import _replay_rm
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    yield c
+    c.close()
+
+
+def _np(t):
+    return t.cpu().numpy()
+
+
+def test_topk_gather_stats(ctx):
+    from roreg_b200 import matchot
+    mo = matchot.MatchOT(ctx, O.random_state_dict("RM", 1))
+    rng = np.random.default_rng(0)
+    S = rng.standard_normal((77, 1300)).astype(np.float32)
+    S[5, 10] = S[5, 900] = 9.0                                   # tie: lower column first
+    idx = _np(mo.topk(ctx.dev(S), 77, 1300, 16))
+    ref = np.argsort(-S, axis=1, kind="stable")[:, :16]
+    assert np.array_equal(idx, ref)
+    src = rng.standard_normal((1300, 32)).astype(np.float32)
+    g = _np(mo.gather(ctx.dev(src), ctx.dev(ref.astype(np.int32)), 32))
+    assert np.array_equal(g, src[ref.reshape(-1)])
+    x = rng.standard_normal((5000, 64)).astype(np.float32) * 3 + 1
+    mean, rstd = mo.stats(ctx.dev(x), 5000, 64)
+    assert np.abs(_np(mean) - x.mean(0)).max() < 1e-5 and np.abs(_np(rstd) - 1 / np.sqrt(x.var(0) + 1e-5)).max() < 1e-5
+
+
+def test_sinkhorn_against_oracle(ctx):
+    from roreg_b200 import matchot, _lib
+    from roreg_b200.ops import _ptr, _stream
+    import ctypes as C
+    rng = np.random.default_rng(1)
+    m, n = 211, 190
+    S = (rng.standard_normal((m, n)) * 3).astype(np.float32)
+    u = torch.empty(m + 1, dtype=torch.float32, device=ctx.device); v = torch.empty(n + 1, dtype=torch.float32, device=ctx.device)
+    m0 = torch.empty(m, dtype=torch.int32, device=ctx.device); s0 = torch.empty(m, dtype=torch.float32, device=ctx.device)
+    rc = ctx.lib.roreg_sinkhorn_match(ctx.h, _ptr(ctx.dev(S)), m, n, n, C.c_float(0.7), 100, _ptr(u), _ptr(v), _ptr(m0), _ptr(s0), _stream())
+    _lib.check(ctx.h, rc, "sinkhorn")
+    Z = O.log_sinkhorn(S, np.float32(0.7), 100)
+    norm = -np.log(np.float32(m + n))
+    got = S + _np(u)[:m, None] + _np(v)[None, :n] - norm
+    assert np.abs(got - Z[:m, :n]).max() < 2e-4
+    inner = Z[:-1, :-1]; i0 = inner.argmax(1); i1 = inner.argmax(0)
+    mut = np.arange(m) == i1[i0]
+    assert np.array_equal(_np(m0), np.where(mut, i0, -1))
+    assert np.abs(_np(s0) - np.where(mut, np.exp(inner.max(1)), 0)).max() < 1e-4
+
+
+def test_match_ot_forward_against_oracle(ctx, tables):
+    from roreg_b200 import matchot
+    pr = synth.make_pair(58, n=400)
+    sd = O.random_state_dict("RM", 104)
+    mo = matchot.MatchOT(ctx, sd, npass=3)
+    m0, s0 = mo.forward(ctx.dev(pr["feats1"]), ctx.dev(pr["feats0"]), ctx.dev(pr["keys1"].astype(np.float32)), ctx.dev(pr["keys0"].astype(np.float32)))
+    torch.cuda.synchronize()
+    r0, rs0, _, _, Z = O.match_ot_forward(pr["feats1"], pr["feats0"], pr["keys1"], pr["keys0"], sd, tables.perm)
+    agree = (_np(m0) == r0).mean()
+    assert agree > 0.98, agree                                    # float32 top-k / argmax near ties may flip a few assignments
+    both = (_np(m0) == r0) & (r0 >= 0)
+    assert np.abs(_np(s0)[both] - rs0[both]).max() < 1e-3 * max(1.0, rs0.max())
+
+
+def test_yoho_mat_plugin_reproduces_reference_files(tmp_path):
+    import roreg_b200.test as rt
+    z, n, keynum, _, seeds = load_golden("rm300")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/rm", with_fcgf=False)
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    model_fn = str(tmp_path / "ckpt"); os.makedirs(f"{model_fn}/RM")
+    torch.save({"best_para": 0, "network_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in O.random_state_dict("RM", 104).items()}},
+               f"{model_fn}/RM/model_best.pth")
+    cfg = types.SimpleNamespace(output_cache_fn=cache, model_fn=model_fn, SO3_related_files=None, backbone="FCGF", bs_GF=1250, bs_ET=1000,
+                                RD=False, RM=True, match_n=0.5, ransac_ird=0.1)
+    np.random.seed(2468)
+    rt.name2matcher["yoho_mat"](cfg).run(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        m = np.load(f"{cache}/synth/rm/match_{keynum}/{id0}-{id1}.npy"); s = np.load(f"{cache}/synth/rm/match_{keynum}/scores/{id0}-{id1}.npy")
+        ref = z[f"match_{id0}-{id1}"]
+        a = {tuple(r) for r in m.tolist()}; b = {tuple(r) for r in ref.tolist()}
+        assert len(a ^ b) <= max(2, len(b) // 50), (len(a), len(b), len(a ^ b))
+        if np.array_equal(m, ref):
+            assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-3

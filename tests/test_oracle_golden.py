@@ -91,3 +91,30 @@ def test_kat_planted_pose(tables):
     best, ov, _ = O.oneshot_ransac(k0, k1, np.ones(k0.shape[0]), H, 0.1)
     assert best == 17 and ov == 1.0
     assert np.abs(O.refine(k0, k1, H[17], np.ones(k0.shape[0]), 0.1)[:3] - pr["gt"]).max() < 1e-9
+
+
+def _replay_rm(ds, keynum, seed, fn):
+    """yoho_mat.run's host logic (test/matcher.py:166-210) around a Match_ot forward `fn(feats_src, feats_tgt, keys_src, keys_tgt)`."""
+    np.random.seed(seed)
+    res = []
+    for (id0, id1) in ds.pair_ids:
+        f0 = ds.get_feats(id0); f1 = ds.get_feats(id1)
+        s0 = np.arange(f0.shape[0]); s1 = np.arange(f1.shape[0])
+        np.random.shuffle(s0); np.random.shuffle(s1)
+        s0 = s0[:keynum]; s1 = s1[:keynum]
+        m0, sc0 = fn(f1[s1], f0[s0], ds.get_kps(id1)[s1].astype(np.float32), ds.get_kps(id0)[s0].astype(np.float32))
+        sel = np.where(m0 != -1)[0]
+        pairs = np.stack([sel, m0[sel]], 1)
+        res.append((np.stack([s0[pairs[:, 1]], s1[pairs[:, 0]]], 1), sc0[sel]))
+    return res
+
+
+def test_match_ot_against_reference_outputs(tables):
+    """Match_ot restatement vs the files the reference's yoho_mat.run wrote (tests/golden/make_golden_rm.py)."""
+    z, n, keynum, _, seeds = load_golden("rm300")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/rm", with_fcgf=False)
+    sd = O.random_state_dict("RM", 104)
+    out = _replay_rm(ds, keynum, 2468, lambda a, b, ka, kb: O.match_ot_forward(a, b, ka, kb, sd, tables.perm)[:2])
+    for (id0, id1), (m, s) in zip(ds.pair_ids, out):
+        assert np.array_equal(m, z[f"match_{id0}-{id1}"])
+        assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-5
