@@ -117,4 +117,4 @@ def test_match_ot_against_reference_outputs(tables):
     out = _replay_rm(ds, keynum, 2468, lambda a, b, ka, kb: O.match_ot_forward(a, b, ka, kb, sd, tables.perm)[:2])
     for (id0, id1), (m, s) in zip(ds.pair_ids, out):
         assert np.array_equal(m, z[f"match_{id0}-{id1}"])
-        assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-5
+        assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-4          # stated tolerance; matches are bit-exact
