@@ -85,7 +85,13 @@ def test_yohoc_run_device_mode(tmp_path):
     assert os.path.exists(f"{cache}/{ds.name}/match_500/yohoc/400iters/pre.log")
 
 
-def test_unbuilt_plugins_fail_loudly():
+def test_missing_checkpoint_raises_like_the_reference():
+    """`raise ValueError("No model exists")` when a checkpoint is absent (test/matcher.py:129, test/detector.py:24)."""
     import roreg_b200.test as rt
-    with pytest.raises(NotImplementedError):
-        rt.yoho_mat(_cfg("/tmp"))
+    cfg = _cfg("/tmp", model_fn="/nonexistent")
+    with pytest.raises(ValueError):
+        rt.yoho_mat(cfg)
+    with pytest.raises(ValueError):
+        rt.yoho_det(cfg)
+    with pytest.raises(ValueError):
+        rt.yoho_des(cfg).run(types.SimpleNamespace(name="x", pc_ids=[], pair_ids=[]))
