@@ -28,9 +28,9 @@ constexpr int CT_STAGES = 2;                              // raw landing buffers
 constexpr int CT_RAW_BOX = 32 * 64 * 4;                   // [32 f][64 h] f32 = 8 KB (one descriptor row, h padded to 64)
 constexpr int CT_RAW_BYTES = 4 * CT_RAW_BOX;              // X0 | X1 | Y0 | Y1 = 32 KB per stage
 constexpr int CT_OPER_BYTES = 128 * 32 * 4;               // one K-major operand: 128 rows x 32 f = 16 KB
-constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB (single-buffered)
-constexpr int CT_GS_BYTES = 2 * 64 * 64 * 4;              // transposed Gram of both matches
-constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;
+constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB, double-buffered: convert(i+1) overlaps MMA(i)
+constexpr int CT_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h]
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + 2 * CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 232,224 B of the 232,448 B limit
 constexpr int CT_THREADS = 320;
 
 struct CorrTcArgs {
@@ -45,12 +45,12 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
                                                                       const __grid_constant__ CUtensorMap mapY, CorrTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* tiles = smem + CT_STAGES * CT_RAW_BYTES;                                        // Xhi | Xlo | Yhi | Ylo
-  float* Gs = reinterpret_cast<float*>(tiles + CT_TILES_BYTES);                            // [2][64 g][64 h]
+  uint8_t* tiles0 = smem + CT_STAGES * CT_RAW_BYTES;                                       // 2 x (Xhi | Xlo | Yhi | Ylo)
+  float* Gs = reinterpret_cast<float*>(tiles0 + 2 * CT_TILES_BYTES);                       // [2][60 g][64 h]
   uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + CT_GS_BYTES;                            // 3600 B
   float* red_v = reinterpret_cast<float*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_v + 2);   // [2] each
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tabs + 3600 + 16) + 7) & ~uintptr_t(7));
-  // barriers: 0..1 raw_full[s], 2..3 raw_free[s], 4 conv_done, 5 tiles_free, 6..7 mma_done[acc], 8..9 acc_free[acc]
+  // barriers: 0..1 raw_full[s], 2..3 raw_free[s], 4..5 conv_done[t], 6..7 mma_done[t] (accumulator t ready AND operand tiles t free), 8..9 acc_free[t]
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -61,7 +61,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     for (int s = 0; s < 2; ++s) {
       mbar_init(BAR(0 + s), 1); mbar_init(BAR(2 + s), 128); mbar_init(BAR(6 + s), 1); mbar_init(BAR(8 + s), 128);
     }
-    mbar_init(BAR(4), 128); mbar_init(BAR(5), 1);
+    mbar_init(BAR(4), 128); mbar_init(BAR(5), 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -112,10 +112,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         int p, k0; if (item_count(item, p, k0) <= 0) continue;
         const int acc = it & 1; const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(BAR(4), it & 1);                     // operand tiles written and visible to the async proxy
+        mbar_wait(BAR(4 + acc), aph);                  // operand tiles written and visible to the async proxy
         mbar_wait(BAR(8 + acc), aph ^ 1);              // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tb = smem_u32(tiles);
+        const uint32_t tb = smem_u32(tiles0 + acc * CT_TILES_BYTES);
         const uint32_t xhi = tb, xlo = tb + CT_OPER_BYTES, yhi = tb + 2 * CT_OPER_BYTES, ylo = tb + 3 * CT_OPER_BYTES;
         const uint32_t d_tmem = tmem_base + acc * 128;
         const uint32_t aop[3] = {xhi, xlo, xhi}, bop[3] = {yhi, yhi, ylo};
@@ -124,7 +124,6 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
-        umma_commit(BAR(5));                           // operand tiles reusable by the convert warps
         umma_commit(BAR(6 + acc));                     // accumulator ready for the epilogue
         ++it;
       }
@@ -139,7 +138,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       int p, k0; if (item_count(item, p, k0) <= 0) continue;
       const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
       mbar_wait(BAR(0 + st), ph);                      // raw tile landed
-      mbar_wait(BAR(5), (it & 1) ^ 1);                 // MMAs of the previous item no longer read the operand tiles
+      const int ts = it & 1;
+      mbar_wait(BAR(6 + ts), ph ^ 1);                  // the MMAs of item it-2 no longer read operand tiles `ts`
+      uint8_t* tiles = tiles0 + ts * CT_TILES_BYTES;
       const float* raw = reinterpret_cast<const float*>(smem + st * CT_RAW_BYTES);
       const int m = ct >> 6, h = ct & 63;
 #pragma unroll
@@ -160,7 +161,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
-      mbar_arrive(BAR(4));                             // conv_done
+      mbar_arrive(BAR(4 + ts));                        // conv_done[ts]
       mbar_arrive(BAR(2 + st));                        // raw buffer free for the next TMA
       ++it;
     }
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
     const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
-    float* G = Gs + m * 64 * 64;
+    float* G = Gs + m * 60 * 64;
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; const int avail = item_count(item, p, k0);

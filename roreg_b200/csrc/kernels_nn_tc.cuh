@@ -16,6 +16,7 @@
 //   warps 2-5   epilogue       tcgen05.ld 32x32b.x32 -> running argmin; TMEM double-buffered (2 x 128 cols)
 #pragma once
 #include <cuda.h>
+#include <stdlib.h>
 #include "common.cuh"
 #include "kernels_match.cuh"
 
@@ -88,6 +89,7 @@ struct NNTcArgs {
   const float* nrm_half;      // [rows] 0.5*|x|^2
   int S, B;                   // rows per (pair, side); pairs
   int32_t* nn01; int32_t* nn10;  // [B][S]
+  int passes;                  // 3 = hi.hi + lo.hi + hi.lo (default); 1 / 2 only for bottleneck experiments (ROREG_DEBUG_NN_PASSES)
 };
 
 __global__ void __launch_bounds__(192, 1) nn_tc_kernel(const __grid_constant__ CUtensorMap mapA,
@@ -271,7 +273,7 @@ static inline int nn_tc_launch_both(roreg_ctx* c, const float* inv, int S, int B
   const int nrb = (S + TC_BM - 1) / TC_BM;
   const int items = B * 2 * nrb;
   const int grid = items < c->sm_count ? items : c->sm_count;
-  NNTcArgs a{nrm_half, S, B, nn01, nn10};
+  NNTcArgs a{nrm_half, S, B, nn01, nn10, 3};
   nn_tc_kernel<<<grid, 192, TC_SMEM_BYTES, st>>>(mA, mB, a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
@@ -387,9 +389,11 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
           const uint32_t aop[3] = {ahi, alo, ahi}, bop[3] = {bhi, bhi, blo};
 #pragma unroll
           for (int c = 0; c < 3; ++c)
+            if (c < a.passes) {
 #pragma unroll
-            for (int kk = 0; kk < TC_KC / 8; ++kk)
-              umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+              for (int kk = 0; kk < TC_KC / 8; ++kk)
+                umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+            }
           umma_commit(BAR(6 + st));
           umma_commit(BAR(10 + par));
         }
@@ -488,7 +492,8 @@ static inline int nn_tc2_launch_both(roreg_ctx* c, const float* inv, int S, int 
   const int nrb = (S + TC_BM - 1) / TC_BM;
   const int items = B * 2 * nrb;
   const int grid = items < c->sm_count ? items : c->sm_count;
-  NNTcArgs a{nrm_half, S, B, nn01, nn10};
+  NNTcArgs a{nrm_half, S, B, nn01, nn10, 3};
+  if (const char* e = getenv("ROREG_DEBUG_NN_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) a.passes = v; }
   nn_tc2_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mH, a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
