@@ -304,8 +304,18 @@ def main():
         ach = amount / dur / 1e9; peak = hbm_peak; unit = "GB/s"
     else:
         ach = amount / dur / 1e12; peak = tc_peak; unit = "TFLOP/s"
+    traffic = None
+    try:       # dram__bytes_read+write of the dominant stage's main kernel from the committed ncu --set full capture, scaled to B pairs
+        tj = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json")))["kernels"]
+        kname = {"nn": "nn_tc2_kernel", "group_corr": "group_corr_tc_kernel", "score_select": "ransac_score_kernel"}.get(dom)
+        if kname in tj:
+            traffic = tj[kname]["dram_bytes_per_launch"] / tj[kname]["pairs_per_launch"] * B
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                "traffic": None, "peak_source": src, "stage_ms_per_step": stage_ms,
+                "traffic": traffic, "peak_source": src, "stage_ms_per_step": stage_ms,
+                "fused_step": {"algorithmic_bytes": B * (2 * n * 7680 + 2 * n * 128 + kavg * (2 * 7680 + 12)), "ms": sum(stage_ms.values()),
+                               "hbm_frac": B * (2 * n * 7680 + 2 * n * 128 + kavg * (2 * 7680 + 12)) / (sum(stage_ms.values()) * 1e-3) / 1e9 / hbm_peak},
                 "note": "algorithmic bytes/flops per step (B pairs) / CUDA-event duration of that stage inside the timed region"}
 
     if rank == 0:

@@ -24,13 +24,13 @@
 
 namespace roreg {
 
-constexpr int CT_STAGES = 2;                              // raw landing buffers (TMA double-buffered)
+constexpr int CT_STAGES = 4;                              // raw landing buffers: 4 x 32 KB in flight per SM hide the HBM latency (run 13: 2 stages capped the kernel at 2.1 TB/s)
 constexpr int CT_RAW_BOX = 32 * 64 * 4;                   // [32 f][64 h] f32 = 8 KB (one descriptor row, h padded to 64)
 constexpr int CT_RAW_BYTES = 4 * CT_RAW_BOX;              // X0 | X1 | Y0 | Y1 = 32 KB per stage
 constexpr int CT_OPER_BYTES = 128 * 32 * 4;               // one K-major operand: 128 rows x 32 f = 16 KB
-constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB, double-buffered: convert(i+1) overlaps MMA(i)
+constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB, single-buffered (double-buffering them bought nothing in run 13)
 constexpr int CT_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h]
-constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + 2 * CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 232,224 B of the 232,448 B limit
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 232,224 B of the 232,448 B limit
 constexpr int CT_THREADS = 320;
 
 struct CorrTcArgs {
@@ -46,11 +46,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles0 = smem + CT_STAGES * CT_RAW_BYTES;                                       // 2 x (Xhi | Xlo | Yhi | Ylo)
-  float* Gs = reinterpret_cast<float*>(tiles0 + 2 * CT_TILES_BYTES);                       // [2][60 g][64 h]
+  float* Gs = reinterpret_cast<float*>(tiles0 + CT_TILES_BYTES);                           // [2][60 g][64 h]
   uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + CT_GS_BYTES;                            // 3600 B
   float* red_v = reinterpret_cast<float*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_v + 2);   // [2] each
   uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tabs + 3600 + 16) + 7) & ~uintptr_t(7));
-  // barriers: 0..1 raw_full[s], 2..3 raw_free[s], 4..5 conv_done[t], 6..7 mma_done[t] (accumulator t ready AND operand tiles t free), 8..9 acc_free[t]
+  // barriers: 0..3 raw_full[s], 4..7 raw_free[s], 8 conv_done, 9 tiles_free, 10..11 mma_done[acc], 12..13 acc_free[acc]
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -58,10 +58,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 
   for (int e = threadIdx.x; e < 3600; e += CT_THREADS) tabs[e] = a.tab[e];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(BAR(0 + s), 1); mbar_init(BAR(2 + s), 128); mbar_init(BAR(6 + s), 1); mbar_init(BAR(8 + s), 128);
-    }
-    mbar_init(BAR(4), 128); mbar_init(BAR(5), 128);
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(BAR(0 + s), 1); mbar_init(BAR(4 + s), 128); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(10 + s), 1); mbar_init(BAR(12 + s), 128); }
+    mbar_init(BAR(8), 128); mbar_init(BAR(9), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -89,8 +88,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         int p, k0; const int avail = item_count(item, p, k0);
         if (avail <= 0) continue;
-        const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(BAR(2 + st), ph ^ 1);                // convert warps have consumed this raw buffer
+        const int st = it % CT_STAGES; const uint32_t ph = (it / CT_STAGES) & 1;
+        mbar_wait(BAR(4 + st), ph ^ 1);                // convert warps have consumed this raw buffer
         uint8_t* sb = smem + st * CT_RAW_BYTES;
         mbar_expect_tx(BAR(0 + st), CT_RAW_BYTES);
         for (int m = 0; m < 2; ++m) {
@@ -112,10 +111,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
         int p, k0; if (item_count(item, p, k0) <= 0) continue;
         const int acc = it & 1; const uint32_t aph = (it >> 1) & 1;
-        mbar_wait(BAR(4 + acc), aph);                  // operand tiles written and visible to the async proxy
-        mbar_wait(BAR(8 + acc), aph ^ 1);              // accumulator drained
+        mbar_wait(BAR(8), it & 1);                     // operand tiles written and visible to the async proxy
+        mbar_wait(BAR(12 + acc), aph ^ 1);             // accumulator drained
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t tb = smem_u32(tiles0 + acc * CT_TILES_BYTES);
+        const uint32_t tb = smem_u32(tiles0);
         const uint32_t xhi = tb, xlo = tb + CT_OPER_BYTES, yhi = tb + 2 * CT_OPER_BYTES, ylo = tb + 3 * CT_OPER_BYTES;
         const uint32_t d_tmem = tmem_base + acc * 128;
         const uint32_t aop[3] = {xhi, xlo, xhi}, bop[3] = {yhi, yhi, ylo};
@@ -124,7 +123,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk)
             umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
-        umma_commit(BAR(6 + acc));                     // accumulator ready for the epilogue
+        umma_commit(BAR(9));                           // operand tiles reusable by the convert warps
+        umma_commit(BAR(10 + acc));                    // accumulator ready for the epilogue
         ++it;
       }
     }
@@ -136,11 +136,10 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; if (item_count(item, p, k0) <= 0) continue;
-      const int st = it & 1; const uint32_t ph = (it >> 1) & 1;
+      const int st = it % CT_STAGES; const uint32_t ph = (it / CT_STAGES) & 1;
       mbar_wait(BAR(0 + st), ph);                      // raw tile landed
-      const int ts = it & 1;
-      mbar_wait(BAR(6 + ts), ph ^ 1);                  // the MMAs of item it-2 no longer read operand tiles `ts`
-      uint8_t* tiles = tiles0 + ts * CT_TILES_BYTES;
+      mbar_wait(BAR(9), (it & 1) ^ 1);                 // the MMAs of the previous item no longer read the operand tiles
+      uint8_t* tiles = tiles0;
       const float* raw = reinterpret_cast<const float*>(smem + st * CT_RAW_BYTES);
       const int m = ct >> 6, h = ct & 63;
 #pragma unroll
@@ -161,8 +160,8 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
-      mbar_arrive(BAR(4 + ts));                        // conv_done[ts]
-      mbar_arrive(BAR(2 + st));                        // raw buffer free for the next TMA
+      mbar_arrive(BAR(8));                             // conv_done
+      mbar_arrive(BAR(4 + st));                        // raw buffer free for the next TMA
       ++it;
     }
   } else {
@@ -176,7 +175,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       int p, k0; const int avail = item_count(item, p, k0);
       if (avail <= 0) continue;
       const int acc = it & 1; const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(BAR(6 + acc), ph);
+      mbar_wait(BAR(10 + acc), ph);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 128 + m * 64;
       uint32_t r[64];
@@ -193,7 +192,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       }
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(BAR(8 + acc));                       // accumulator free as soon as it sits in registers
+      mbar_arrive(BAR(12 + acc));                      // accumulator free as soon as it sits in registers
       // transposed store: Gs[m][g][h]; a warp writes 32 consecutive h -> conflict-free
 #pragma unroll
       for (int g = 0; g < 60; ++g) G[g * 64 + h] = __uint_as_float(r[g]);

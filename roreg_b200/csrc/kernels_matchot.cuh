@@ -191,24 +191,37 @@ __global__ void __launch_bounds__(256) sinkhorn_rows_kernel(SinkArgs a) {
   }
 }
 
-__global__ void __launch_bounds__(256) sinkhorn_cols_kernel(SinkArgs a) {
-  __shared__ float smx[8][33], ssm[8][33];
+// 32 columns x 32 row-lanes per CTA; every thread keeps 4 independent online (max, sum) pairs so that 4 loads are
+// in flight per thread (the first version - 8 row-lanes, one dependent chain - was L2-latency bound: 200 us per pass).
+__global__ void __launch_bounds__(1024) sinkhorn_cols_kernel(SinkArgs a) {
+  __shared__ float smx[32][33], ssm[32][33];
   const int lane = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + lane;                 // j in [0, n]
-  float mx = -INFINITY, sm = 0.f;
+  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
   if (j <= a.n) {
-    for (int i = rl; i <= a.m; i += 8) {
-      const float z = (i < a.m && j < a.n) ? a.S[(long long)i * a.ld + j] : a.alpha;
-      const float t = z + a.u[i];
-      if (t > mx) { sm = sm * expf(mx - t) + 1.f; mx = t; } else sm += expf(t - mx);
+    for (int i0 = rl; i0 <= a.m; i0 += 128) {
+      float t[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int i = i0 + 32 * q;
+        t[q] = -INFINITY;
+        if (i <= a.m) t[q] = ((i < a.m && j < a.n) ? a.S[(long long)i * a.ld + j] : a.alpha) + a.u[i];
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (t[q] > mx[q]) { sm[q] = sm[q] * expf(mx[q] - t[q]) + 1.f; mx[q] = t[q]; }
+        else if (t[q] > -INFINITY) sm[q] += expf(t[q] - mx[q]);
+      }
     }
   }
-  smx[rl][lane] = mx; ssm[rl][lane] = sm;
+  lse_merge(mx[0], sm[0], mx[1], sm[1]); lse_merge(mx[2], sm[2], mx[3], sm[3]); lse_merge(mx[0], sm[0], mx[2], sm[2]);
+  smx[rl][lane] = mx[0]; ssm[rl][lane] = sm[0];
   __syncthreads();
   if (rl == 0 && j <= a.n) {
-    for (int w = 1; w < 8; ++w) lse_merge(mx, sm, smx[w][lane], ssm[w][lane]);
+    float m0 = mx[0], s0 = sm[0];
+    for (int w = 1; w < 32; ++w) lse_merge(m0, s0, smx[w][lane], ssm[w][lane]);
     const float log_nu = (j < a.n) ? a.norm : (logf((float)a.m) + a.norm);
-    a.v[j] = log_nu - (mx + logf(sm));
+    a.v[j] = log_nu - (m0 + logf(s0));
   }
 }
 

@@ -499,8 +499,231 @@ static inline int nn_tc2_launch_both(roreg_ctx* c, const float* inv, int S, int 
   return ROREG_OK;
 }
 
+
+// =====================================================================================================
+// v3 (nn mode 3): ONE Gram per pair.  Run 13 showed v2's time does not change when 8 of its 12 MMAs are
+// removed: the kernel is paced by reading the accumulators out of TMEM (~55 B/clk/SM), and v1/v2 read every
+// element twice because the column direction re-computes the Gram with the operand roles swapped.  v3 computes
+// each 128x128 tile once and takes both minima from the same registers:
+//   rows    : running (min, argmin) per thread over the column tiles, as before;
+//   columns : warp-wide integer min (redux.sync) of the order-preserving bit pattern of d2/2 over the 32 rows a
+//             warp holds, a second redux for the smallest row attaining it, the four lane-quadrants are merged in
+//             shared memory and one 64-bit atomicMin per column publishes (key << 32 | row): the lexicographic
+//             (distance, row) minimum, i.e. torch.min's first-index tie rule, independent of the arrival order.
+// =====================================================================================================
+struct NNTc3Args {
+  const float* nrm_half; int S, B;
+  int32_t* nn01;                       // [B][S]
+  unsigned long long* col_best;        // [B][S] packed (key << 32 | row), pre-set to all ones
+};
+
+__global__ void nn_tc3_unpack_kernel(const unsigned long long* __restrict__ col_best, long long n, int32_t* __restrict__ nn10) {
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  if (i < n) nn10[i] = (int32_t)(col_best[i] & 0xffffffffull);
+}
+
+__global__ void __launch_bounds__(T2_THREADS, 1) nn_tc3_kernel(const __grid_constant__ CUtensorMap mapH, NNTc3Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + T2_TILE_BYTES;
+  float* sNb = reinterpret_cast<float*>(smem + T2_TILE_BYTES * (1 + T2_STAGES));   // [2][128]
+  float* mrg_v = sNb + 2 * TC_BN; int* mrg_j = reinterpret_cast<int*>(mrg_v + 128);  // [128] each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(mrg_j + 128);
+  __shared__ uint32_t tmem_base_s;
+  __shared__ uint32_t col_key[2][4][128];      // [tile parity][lane quadrant][column]
+  __shared__ uint32_t col_row[2][4][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar0 = smem_u32(bars);
+  auto BAR = [&](int i) { return bar0 + 8u * i; };
+  if (threadIdx.x == 0) {
+    mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(6 + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(10 + s), 1); mbar_init(BAR(12 + s), 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(256) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = tmem_base_s;
+
+  const int nrb = (a.S + TC_BM - 1) / TC_BM;
+  const int nct = (a.S + TC_BN - 1) / TC_BN;
+  const int n_items = a.B * nrb;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t it_b = 0, a_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int rb = item % nrb, p = item / nrb;
+        const int a_row0 = (p * 2) * a.S + rb * TC_BM;          // rows of cloud 0 search ...
+        const int b_row_base = (p * 2 + 1) * a.S;               // ... the rows of cloud 1
+        mbar_wait(BAR(1), a_phase ^ 1);
+        mbar_expect_tx(BAR(0), T2_TILE_BYTES);
+        for (int c = 0; c < 2; ++c) tma_load_2d(smem_u32(sA + c * TC_BOX_BYTES), &mapH, c * TC_KC, a_row0, BAR(0));
+        a_phase ^= 1;
+        for (int ct = 0; ct < nct; ++ct, ++it_b) {
+          const int st = it_b % T2_STAGES; const uint32_t ph = (it_b / T2_STAGES) & 1;
+          mbar_wait(BAR(6 + st), ph ^ 1);
+          mbar_expect_tx(BAR(2 + st), T2_TILE_BYTES);
+          for (int c = 0; c < 2; ++c)
+            tma_load_2d(smem_u32(sB + st * T2_TILE_BYTES + c * TC_BOX_BYTES), &mapH, c * TC_KC, b_row_base + ct * TC_BN, BAR(2 + st));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      uint32_t it_b = 0, it_t = 0, a_phase = 0;
+      const uint32_t ahi = smem_u32(sA), alo = ahi + TC_BOX_BYTES;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(BAR(0), a_phase); a_phase ^= 1;
+        for (int ct = 0; ct < nct; ++ct, ++it_b, ++it_t) {
+          const int st = it_b % T2_STAGES; const uint32_t ph = (it_b / T2_STAGES) & 1;
+          const int par = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+          mbar_wait(BAR(2 + st), ph);
+          mbar_wait(BAR(12 + par), tph ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t bhi = smem_u32(sB + st * T2_TILE_BYTES), blo = bhi + TC_BOX_BYTES;
+          const uint32_t d_tmem = tmem_base + par * TC_BN;
+          const uint32_t aop[3] = {ahi, alo, ahi}, bop[3] = {bhi, bhi, blo};
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int kk = 0; kk < TC_KC / 8; ++kk)
+              umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+          umma_commit(BAR(6 + st));
+          umma_commit(BAR(10 + par));
+        }
+        umma_commit(BAR(1));
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
+    const int row_in_tile = q * 32 + lane;
+    const int et = threadIdx.x - 64;
+    uint32_t it_t = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int rb = item % nrb, p = item / nrb;
+      const int b_row_base = (p * 2 + 1) * a.S;
+      const int row = rb * TC_BM + row_in_tile;
+      const bool row_ok = row < a.S;
+      const float nah = row_ok ? a.nrm_half[(p * 2) * a.S + row] : 0.f;
+      float best_v = INFINITY; int best_j = 0x7fffffff;
+      for (int ct = 0; ct < nct; ++ct, ++it_t) {
+        const int par = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+        if (et < TC_BN) {
+          const int j = ct * TC_BN + et;
+          sNb[par * TC_BN + et] = (j < a.S) ? a.nrm_half[b_row_base + j] : INFINITY;
+        }
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        mbar_wait(BAR(10 + par), tph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + par * TC_BN + hf * 64;
+        uint32_t r0[32], r1[32];
+        RR_TMEM_LD32(r0, taddr);
+        RR_TMEM_LD32(r1, taddr + 32);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(BAR(12 + par));
+        const float* nbs = sNb + par * TC_BN + hf * 64;
+        uint32_t my_key[2] = {0xffffffffu, 0xffffffffu}, my_row[2] = {0x7fffffffu, 0x7fffffffu};
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const uint32_t* rg = half ? r1 : r0;
+          float m = INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = nbs[half * 32 + j] - __uint_as_float(rg[j]);          // (d2 - |a|^2) / 2 : row-direction key
+            m = fminf(m, v);
+            // column direction: d2/2 = |a|^2/2 + v >= 0 -> its bit pattern orders like the value
+            const uint32_t kb = row_ok ? __float_as_uint(fmaxf(nah + v, 0.f)) : 0xffffffffu;
+            const uint32_t mn = __reduce_min_sync(0xffffffffu, kb);
+            const uint32_t rw = __reduce_min_sync(0xffffffffu, (kb == mn) ? (uint32_t)row : 0x7fffffffu);
+            if (lane == j) { my_key[half] = mn; my_row[half] = rw; }
+          }
+          if (m < best_v) {
+            int jj = 31;
+#pragma unroll
+            for (int j = 31; j >= 0; --j) if (nbs[half * 32 + j] - __uint_as_float(rg[j]) == m) jj = j;
+            best_v = m; best_j = ct * TC_BN + hf * 64 + half * 32 + jj;
+          }
+        }
+        col_key[par][q][hf * 64 + lane] = my_key[0]; col_row[par][q][hf * 64 + lane] = my_row[0];
+        col_key[par][q][hf * 64 + 32 + lane] = my_key[1]; col_row[par][q][hf * 64 + 32 + lane] = my_row[1];
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (et < TC_BN) {                                  // one thread per column: merge the 4 lane quadrants, publish
+          const int j = ct * TC_BN + et;
+          if (j < a.S) {
+            unsigned long long best = 0xffffffffffffffffull;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+              const unsigned long long c = ((unsigned long long)col_key[par][qq][et] << 32) | col_row[par][qq][et];
+              best = c < best ? c : best;
+            }
+            atomicMin(a.col_best + (long long)p * a.S + j, best);
+          }
+        }
+      }
+      if (hf == 1) { mrg_v[row_in_tile] = best_v; mrg_j[row_in_tile] = best_j; }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (hf == 0) {
+        if (mrg_v[row_in_tile] < best_v) { best_v = mrg_v[row_in_tile]; best_j = mrg_j[row_in_tile]; }
+        if (row_ok) a.nn01[(long long)p * a.S + row] = best_j;
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+    }
+  }
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
+}
+
+static inline int nn_tc3_launch_both(roreg_ctx* c, const float* inv, int S, int B, float* H, float* nrm_half,
+                                     unsigned long long* col_best, int32_t* nn01, int32_t* nn10, cudaStream_t st) {
+  const long long rows = (long long)B * 2 * S;
+  nn_tc2_prep_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(inv, (int)rows, H, nrm_half);
+  RR_LAUNCH_CHECK(c);
+  RR_CUDA(c, cudaMemsetAsync(col_best, 0xff, sizeof(unsigned long long) * (size_t)B * S, st));
+  CUtensorMap mH;
+  {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+      void* p = nullptr; cudaDriverEntryPointQueryResult qres;
+      cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+      if (e != cudaSuccess || !p || qres != cudaDriverEntryPointSuccess) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled entry point unavailable"); return ROREG_ERR_CUDA; }
+      fn = (PFN_encodeTiled)p;
+    }
+    const cuuint64_t dims[2] = {64, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {64 * sizeof(float)};
+    const cuuint32_t box[2] = {(cuuint32_t)TC_KC, (cuuint32_t)TC_BM};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&mH, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)H, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(H) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(c, cudaFuncSetAttribute(nn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
+    attr_set = true;
+  }
+  const int nrb = (S + TC_BM - 1) / TC_BM;
+  const int items = B * nrb;
+  const int grid = items < c->sm_count ? items : c->sm_count;
+  NNTc3Args a{nrm_half, S, B, nn01, col_best};
+  nn_tc3_kernel<<<grid, T2_THREADS, T2_SMEM_BYTES, st>>>(mH, a);
+  RR_LAUNCH_CHECK(c);
+  const long long n = (long long)B * S;
+  nn_tc3_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(col_best, n, nn10);
+  RR_LAUNCH_CHECK(c);
+  return ROREG_OK;
+}
+
 static inline size_t nn_tc_workspace_bytes(long long rows) {
-  return 2 * rr_align(sizeof(float) * rows * TC_KEXT) + rr_align(sizeof(float) * rows) + 1024;
+  return 2 * rr_align(sizeof(float) * rows * TC_KEXT) + rr_align(sizeof(float) * rows) + rr_align(sizeof(unsigned long long) * rows) + 1024;
 }
 
 }  // namespace roreg

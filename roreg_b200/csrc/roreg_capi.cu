@@ -119,7 +119,7 @@ int roreg_knn(roreg_ctx* c, const float* target, int n, const float* source, int
 
 int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, int n1, int mode,
                        int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream) {
-  RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode >= 0 && mode <= 2));
+  RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode >= 0 && mode <= 3));
   cudaStream_t st = (cudaStream_t)stream;
   if (mode >= 1 && n0 != n1) {
     snprintf(c->err, sizeof(c->err), "nn mode 1 (tcgen05 Gram) needs n0 == n1 in the single-pair entry");
@@ -137,9 +137,11 @@ int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, i
     float* Ahat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
     float* Bhat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
     float* nh = ar.take<float>(2 * (size_t)n0);
+    unsigned long long* cb = ar.take<unsigned long long>((size_t)n0);
     RR_CUDA(c, cudaMemcpyAsync(inv2, f0, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
     RR_CUDA(c, cudaMemcpyAsync(inv2 + (size_t)n0 * RR_F, f1, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
-    if (mode == 2) { if ((rc = nn_tc2_launch_both(c, inv2, n0, 1, Ahat, nh, w01, w10, st))) return rc; }
+    if (mode == 3) { if ((rc = nn_tc3_launch_both(c, inv2, n0, 1, Ahat, nh, cb, w01, w10, st))) return rc; }
+    else if (mode == 2) { if ((rc = nn_tc2_launch_both(c, inv2, n0, 1, Ahat, nh, w01, w10, st))) return rc; }
     else if ((rc = nn_tc_launch_both(c, inv2, n0, 1, Ahat, Bhat, nh, w01, w10, st))) return rc;
   } else {
     if ((rc = launch_nn(c, mode, f0, f1, 0, 0, n0, n1, w01, nullptr, 0, 1, st))) return rc;   // KNN(feats1, feats0): rows of cloud0 search cloud1
@@ -429,7 +431,7 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
   for (int it = 0; it < iters; ++it) {
     sinkhorn_rows_kernel<<<m + 1, 256, 0, st>>>(a);
     RR_LAUNCH_CHECK(c);
-    sinkhorn_cols_kernel<<<(n + 1 + 31) / 32, 256, 0, st>>>(a);
+    sinkhorn_cols_kernel<<<(n + 1 + 31) / 32, 1024, 0, st>>>(a);
     RR_LAUNCH_CHECK(c);
   }
   ot_row_argmax_kernel<<<m, 256, 0, st>>>(a, idx0, max0);
@@ -458,7 +460,7 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
                 rr_align(sizeof(int32_t) * (size_t)B * S) + 4 * rr_align(sizeof(int32_t) * (size_t)B) +
                 rr_align(sizeof(int32_t) * (size_t)B * 128) + rr_align(sizeof(double) * (size_t)B * 60) + 8192;
   if (b->nn_mode >= 1) need += nn_tc_workspace_bytes((long long)B * 2 * S);
-  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 2);
+  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 3);
   int rc = rr_ws_reserve(c, need);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
@@ -485,7 +487,9 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* nh = ar.take<float>((size_t)B * 2 * S);
-    if (b->nn_mode == 2) { if ((rc = nn_tc2_launch_both(c, inv, S, B, Ahat, nh, nn01, nn10, st))) return rc; }
+    unsigned long long* cb = ar.take<unsigned long long>((size_t)B * S);
+    if (b->nn_mode == 3) { if ((rc = nn_tc3_launch_both(c, inv, S, B, Ahat, nh, cb, nn01, nn10, st))) return rc; }
+    else if (b->nn_mode == 2) { if ((rc = nn_tc2_launch_both(c, inv, S, B, Ahat, nh, nn01, nn10, st))) return rc; }
     else if ((rc = nn_tc_launch_both(c, inv, S, B, Ahat, Bhat, nh, nn01, nn10, st))) return rc;
   } else {
     if ((rc = launch_nn(c, 0, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;

@@ -321,7 +321,7 @@ def _check_nn_tc(idx, target, source):
     return int(bad.sum())
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 @pytest.mark.parametrize("n", [1200, 128, 131, 700, 300])
 def test_mutual_match_tensor_core_mode(ctx, n, mode):
     """nn mode 1: tcgen05 (kind::tf32, 3xTF32 split) Gram + TMEM-side running argmin; indices must equal the
@@ -341,7 +341,7 @@ def test_mutual_match_tensor_core_mode(ctx, n, mode):
             assert np.array_equal(m, ref)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_register_batch_tensor_core_nn(ctx, tables, mode):
     seeds = [91, 92, 93]; n = 900
     prs = [synth.make_pair(s, n=n) for s in seeds]
