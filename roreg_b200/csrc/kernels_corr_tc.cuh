@@ -39,6 +39,7 @@ struct CorrTcArgs {
   const int32_t* n_matches; int K, B;
   const uint8_t* tab;
   float* cor_out; int32_t* argmax_out;
+  int dbg_passes, dbg_skip;          // bottleneck experiments only (ROREG_DEBUG_CORR_PASSES / ROREG_DEBUG_CORR_SKIP): defaults 3 / 0
 };
 
 __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __grid_constant__ CUtensorMap mapX,
@@ -120,9 +121,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         const uint32_t aop[3] = {xhi, xlo, xhi}, bop[3] = {yhi, yhi, ylo};
 #pragma unroll
         for (int c = 0; c < 3; ++c)
+          if (c < a.dbg_passes) {
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk)
-            umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+            for (int kk = 0; kk < 4; ++kk)
+              umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, (c | kk) ? 1u : 0u);
+          }
         umma_commit(BAR(9));                           // operand tiles reusable by the convert warps
         umma_commit(BAR(10 + acc));                    // accumulator ready for the epilogue
         ++it;
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       uint8_t* tiles = tiles0;
       const float* raw = reinterpret_cast<const float*>(smem + st * CT_RAW_BYTES);
       const int m = ct >> 6, h = ct & 63;
+      if (!(a.dbg_skip & 2))
 #pragma unroll
       for (int op = 0; op < 2; ++op) {                 // 0: X, 1: Y
         const float* src = raw + (op * 2 + m) * (CT_RAW_BOX / 4) + h;
@@ -170,6 +174,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
     const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
     float* G = Gs + m * 60 * 64;
+    // this thread always sums the generalised diagonal a = h: keep its 60 table bytes in registers
+    uint32_t trow[15];
+#pragma unroll
+    for (int w4 = 0; w4 < 15; ++w4) {
+      const uint8_t* t = tabs + (h < RR_G ? h : 0) * 60 + 4 * w4;
+      trow[w4] = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+    }
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; const int avail = item_count(item, p, k0);
@@ -198,11 +209,18 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       for (int g = 0; g < 60; ++g) G[g * 64 + h] = __uint_as_float(r[g]);
       asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");
       float c = -INFINITY;
-      if (h < RR_G) {
-        c = 0.f;
-        const uint8_t* t = tabs + h * 60;
-#pragma unroll 10
-        for (int g = 0; g < RR_G; ++g) c += G[g * 64 + t[g]];
+      if (a.dbg_skip & 1) c = G[h];
+      else if (h < RR_G) {
+        float c4[4] = {0.f, 0.f, 0.f, 0.f};                  // four independent chains (the sum order differs from g = 0..59 only in rounding)
+#pragma unroll
+        for (int w4 = 0; w4 < 15; ++w4) {
+          const uint32_t tw = trow[w4];
+          c4[0] += G[(4 * w4 + 0) * 64 + (tw & 0xff)];
+          c4[1] += G[(4 * w4 + 1) * 64 + ((tw >> 8) & 0xff)];
+          c4[2] += G[(4 * w4 + 2) * 64 + ((tw >> 16) & 0xff)];
+          c4[3] += G[(4 * w4 + 3) * 64 + (tw >> 24)];
+        }
+        c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
       }
       const bool valid = m < avail;
       const long long w = (long long)p * a.K + k0 + m;

@@ -330,6 +330,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
   uint64_t* bars = reinterpret_cast<uint64_t*>(mrg_j + 128);
   // barriers: 0 a_full, 1 a_empty, 2..5 b_full, 6..9 b_empty, 10..11 tmem_full, 12..13 tmem_empty
   __shared__ uint32_t tmem_base_s;
+  __shared__ __align__(16) float sNbW[8 * 2 * 64];      // [epilogue warp][tile parity][64 columns]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -413,11 +414,14 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
       float best_v = INFINITY; int best_j = 0x7fffffff;
       for (int ct = 0; ct < nct; ++ct, ++it_t) {
         const int par = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
-        if (et < TC_BN) {
-          const int j = ct * TC_BN + et;
-          sNb[par * TC_BN + et] = (j < a.S) ? a.nrm_half[b_row_base + j] : INFINITY;
+        // per-warp staging of the 64 column half-norms this warp needs (no CTA-wide barrier per tile)
+        float* nbw = sNbW + ((warp - 2) * 2 + par) * 64;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = ct * TC_BN + hf * 64 + u * 32 + lane;
+          nbw[u * 32 + lane] = (j < a.S) ? __ldg(a.nrm_half + b_row_base + j) : INFINITY;
         }
-        asm volatile("bar.sync 1, 256;" ::: "memory");
+        __syncwarp();
         mbar_wait(BAR(10 + par), tph);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + par * TC_BN + hf * 64;
@@ -427,7 +431,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         mbar_arrive(BAR(12 + par));                     // accumulator free: the MMA of tile t+2 may start
-        const float4* nb4 = reinterpret_cast<const float4*>(sNb + par * TC_BN + hf * 64);
+        const float4* nb4 = reinterpret_cast<const float4*>(nbw);
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
           const uint32_t* rg = half ? r1 : r0;
@@ -439,7 +443,7 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
                                fminf(nb.z - __uint_as_float(rg[4 * j4 + 2]), nb.w - __uint_as_float(rg[4 * j4 + 3]))));
           }
           if (m < best_v) {                             // rare: find the first column attaining the new minimum
-            const float* nbs = sNb + par * TC_BN + hf * 64 + half * 32;
+            const float* nbs = nbw + half * 32;
             int jj = 31;
 #pragma unroll
             for (int j = 31; j >= 0; --j) if (nbs[j] - __uint_as_float(rg[j]) == m) jj = j;

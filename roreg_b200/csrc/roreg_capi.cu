@@ -158,7 +158,7 @@ int roreg_group_corr(roreg_ctx* c, const float* X, const int32_t* idxX, const fl
   RR_ARG(c, X && Y && K >= 0 && (variant == 1 || variant == 2) && (cor_out || argmax_out));
   if (K == 0) return ROREG_OK;
   if (c->corr_mode == 1) {
-    CorrTcArgs t{idxX, idxY, 1, nullptr, 0, nullptr, K, 1, (variant == 1) ? c->d_perm8 : c->d_permT8, cor_out, argmax_out};
+    CorrTcArgs t{idxX, idxY, 1, nullptr, 0, nullptr, K, 1, (variant == 1) ? c->d_perm8 : c->d_permT8, cor_out, argmax_out, 3, 0};
     return group_corr_tc_launch(c, X, 1LL << 25, Y, 1LL << 25, t, (cudaStream_t)stream);   // row bound unknown here: indices are trusted
   }
   CorrArgs a{};
@@ -507,7 +507,9 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   co.pair_cloud = b->pair_cloud; co.n = b->n; co.n_matches = b->n_matches; co.K = S; co.B = B;
   co.tab = c->d_perm8; co.cor_out = nullptr; co.argmax_out = b->dr_index;
   if (c->corr_mode == 1) {
-    CorrTcArgs t{b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index};
+    CorrTcArgs t{b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index, 3, 0};
+    if (const char* e = getenv("ROREG_DEBUG_CORR_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) t.dbg_passes = v; }
+    if (const char* e = getenv("ROREG_DEBUG_CORR_SKIP")) t.dbg_skip = atoi(e);
     const long long rows = (long long)b->n_clouds * b->n;
     if ((rc = group_corr_tc_launch(c, b->desc, rows, b->desc, rows, t, st))) return rc;
   } else {
