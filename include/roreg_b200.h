@@ -135,6 +135,17 @@ int roreg_rd_finalize(roreg_ctx* ctx, const float* raw, int n, float* feat_out, 
 int roreg_row_std60(roreg_ctx* ctx, const float* cor, int n, float* out, void* stream);
 int roreg_quat_normalize(roreg_ctx* ctx, const float* q_in, int ld, int K, float* q_out, void* stream);
 
+/* ---- all-pairs 60-rotation correlation (north_star kernel 1; a strict superset of what the reference evaluates,
+ * SURVEY.md section 8(0)):  best[n][m] = max_a cor_a(n,m), best_a = argmax_a (first maximum) with
+ * cor_a(n,m) = sum_{f,g} X[n,f,P[a,g]] Y[m,f,g]  (test/estimator.py:85-89 on every pair), and per row n the
+ * rotation-invariant nearest neighbour nn[n] = argmin_m |X_n|^2 + |Y_m|^2 - 2 best[n][m] with its rotation nn_a and
+ * distance nn_dist (nn / nn_a / nn_dist may be NULL).  X_*, Y_* are the channel-last tf32 hi/lo rows [(n*60+g)][32]
+ * that roreg_pack_descriptors writes (viewed as [n][1920]); 60 tcgen05 GEMMs whose A-operand K-chunks are permuted
+ * through the TMA coordinate, running (max, argmax) in the epilogue.  best [N][M] float32, best_a [N][M] uint8.       */
+int roreg_group_corr_allpairs(roreg_ctx* ctx, const float* X_hi, const float* X_lo, int N, const float* Y_hi,
+                              const float* Y_lo, int M, int npass, float* best, uint8_t* best_a, int32_t* nn,
+                              int32_t* nn_a, float* nn_dist, void* stream);
+
 /* ---- a6-a11  glue of the rotation-coherence matcher Match_ot (network/rot_coh_match.py); the dense layers and the
  * [m,n] score matrices (score_mat :8-12) use roreg_gemm, the R-indicator (:154-163) roreg_group_corr variant 2.   */
 /* Knn_index_extract :34-45: first k columns of the descending argsort of every row (ties -> lower column).        */

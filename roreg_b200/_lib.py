@@ -48,6 +48,7 @@ SIGNATURES = {
     "roreg_rd_finalize": (_i, [_p, _p, _i, _p, _p]),
     "roreg_row_std60": (_i, [_p, _p, _i, _p, _p]),
     "roreg_quat_normalize": (_i, [_p, _p, _i, _i, _p, _p]),
+    "roreg_group_corr_allpairs": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p]),
     "roreg_topk_rows": (_i, [_p, _p, _i, _i, _i, _i, _p, _p]),
     "roreg_gather_rows": (_i, [_p, _p, _p, C.c_longlong, _i, _p, _p]),
     "roreg_rel_coor": (_i, [_p, _p, _p, _i, _i, C.c_float, _p, _p]),

@@ -13,6 +13,7 @@
 struct roreg_ctx {
   int device;
   int sm_count;
+  uint8_t h_perm8[3600]; // host copy of P
   uint8_t* d_perm8;     // [60][60]  P[a][g]            (variant 1 table)
   uint8_t* d_permT8;    // [60][60]  P[g][h] stored [h][g]  (variant 2 table)
   int32_t* d_nei;       // [60][13]

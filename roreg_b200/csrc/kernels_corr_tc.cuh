@@ -16,8 +16,8 @@
 //
 //   warp 0      TMA producer     8 boxes (2 matches x {X,Y} x 2 h-halves) per stage
 //   warp 1      MMA issuer       3 x 4 tcgen05.mma kind::tf32 (M=N=128, K=8), commit -> mbarrier
-//   warps 2-9   convert          hi/lo split + transpose in shared memory, fence.proxy.async, arrive
-//   warps 10-13 epilogue         tcgen05.ld -> smem transpose -> diagonal sums -> argmax
+//   warps 2-5   convert          hi/lo split + transpose in shared memory, fence.proxy.async, arrive
+//   warps 6-9   epilogue         tcgen05.ld -> smem transpose -> diagonal sums -> argmax
 #pragma once
 #include "kernels_nn_tc.cuh"
 #include "kernels_corr.cuh"
@@ -31,7 +31,7 @@ constexpr int CT_OPER_BYTES = 128 * 32 * 4;               // one K-major operand
 constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB, single-buffered (double-buffering them bought nothing in run 13)
 constexpr int CT_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h]
 constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 232,224 B of the 232,448 B limit
-constexpr int CT_THREADS = 448;                           // TMA, MMA, 8 convert warps, 4 epilogue warps
+constexpr int CT_THREADS = 320;                           // TMA, MMA, 4 convert warps, 4 epilogue warps (8 convert warps measured slower, run 17)
 
 struct CorrTcArgs {
   const int32_t* idxX; const int32_t* idxY; int idx_stride;
@@ -59,9 +59,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 
   for (int e = threadIdx.x; e < 3600; e += CT_THREADS) tabs[e] = a.tab[e];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(BAR(0 + s), 1); mbar_init(BAR(4 + s), 256); }
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(BAR(0 + s), 1); mbar_init(BAR(4 + s), 128); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(10 + s), 1); mbar_init(BAR(12 + s), 128); }
-    mbar_init(BAR(8), 256); mbar_init(BAR(9), 1);
+    mbar_init(BAR(8), 128); mbar_init(BAR(9), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -152,12 +152,11 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         ++it;
       }
     }
-  } else if (warp < 10) {
+  } else if (warp < 6) {
     // ===================== convert: split hi/lo and transpose into K-major SW128 operand tiles ============
     // raw[f][h] (h contiguous, pitch 64) -> tile row r = (match, h), 128 B of f per row, 16-B chunk c = f/4
     // stored at chunk position c ^ (r % 8)  (the 128-byte swizzle TMA / UMMA use).
-    const int ct = (threadIdx.x - 64) & 127;           // operand row (match = ct/64, h = ct%64)
-    const int chalf = (threadIdx.x - 64) >> 7;         // two threads per row: 16-B chunks 0..3 / 4..7
+    const int ct = threadIdx.x - 64;                   // 0..127 == operand row (match = ct/64, h = ct%64)
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; if (item_count(item, p, k0) <= 0) continue;
@@ -174,8 +173,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         uint8_t* thi = tiles + (op * 2) * CT_OPER_BYTES + ct * 128;
         uint8_t* tlo = thi + CT_OPER_BYTES;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const int c = chalf * 4 + cc;
+        for (int c = 0; c < 8; ++c) {
           float4 hv, lv; float x; uint32_t t;
           x = src[(4 * c + 0) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.x = __uint_as_float(t); lv.x = x - hv.x;
           x = src[(4 * c + 1) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.y = __uint_as_float(t); lv.y = x - hv.y;

@@ -126,4 +126,44 @@ __global__ void quat_normalize_kernel(const float* __restrict__ q_in, int ld, in
   q_out[4 * i] = w / nrm; q_out[4 * i + 1] = x / nrm; q_out[4 * i + 2] = y / nrm; q_out[4 * i + 3] = z / nrm;
 }
 
+// ---- all-pairs tail: squared norms of the channel-last rows and the per-row minimum of
+// dist(n,m) = |X_n|^2 + |Y_m|^2 - 2 max_a cor_a(n,m)    ---------------------------------------
+__global__ void __launch_bounds__(256) row_sqnorm_kernel(const float* __restrict__ hi, const float* __restrict__ lo, long long rows, int K,
+                                                         float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long r = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float s = 0.f;
+  for (int c = lane; c < K; c += 32) { const float v = hi[r * K + c] + (lo ? lo[r * K + c] : 0.f); s += v * v; }
+  s = warp_sum(s);
+  if (lane == 0) out[r] = s;
+}
+
+__global__ void __launch_bounds__(256) allpairs_rowmin_kernel(const float* __restrict__ best, const uint8_t* __restrict__ besta, int N, int M,
+                                                              const float* __restrict__ nx, const float* __restrict__ ny,
+                                                              int32_t* __restrict__ nn, int32_t* __restrict__ nn_a, float* __restrict__ nn_dist) {
+  __shared__ float sv[8]; __shared__ int si[8];
+  const int n = blockIdx.x, tid = threadIdx.x;
+  float bv = INFINITY; int bi = 0x7fffffff;
+  for (int m = tid; m < M; m += 256) {
+    const float d = nx[n] + ny[m] - 2.f * best[(long long)n * M + m];
+    if (d < bv) { bv = d; bi = m; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float vo = __shfl_xor_sync(0xffffffffu, bv, o); const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (vo < bv || (vo == bv && io < bi)) { bv = vo; bi = io; }
+  }
+  if ((tid & 31) == 0) { sv[tid >> 5] = bv; si[tid >> 5] = bi; }
+  __syncthreads();
+  if (tid == 0) {
+    for (int w = 1; w < 8; ++w) if (sv[w] < bv || (sv[w] == bv && si[w] < bi)) { bv = sv[w]; bi = si[w]; }
+    nn[n] = bi; nn_dist[n] = bv; nn_a[n] = besta[(long long)n * M + bi];
+  }
+}
+
+__global__ void fill_f32_kernel(float* __restrict__ p, long long n, float v) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) p[i] = v;
+}
+
 }  // namespace roreg

@@ -31,6 +31,11 @@ struct GemmArgs {
   float* raw_out; int raw_ld;
   float* act_hi; float* act_lo; int act_ld;
   const float* bn_scale; const float* bn_shift; int relu;
+  // all-pairs group correlation (roreg_group_corr_allpairs): the K axis is 60 chunks of 32 channels, one per group
+  // element; rotation `a` pairs A-chunk P[a][g] with W-chunk g, i.e. the A operand's column coordinate of k-chunk g is
+  // a_cols[g] - a permutation applied by the TMA coordinate alone, no data movement.
+  const int32_t* a_cols;       // [Kdim/32] A column (element) coordinate per k-chunk, or NULL = kc*32
+  uint8_t* amax_arg; int amax_id;   // if set: raw_out / amax_arg hold a running (max, argmax id) instead of being overwritten
 };
 
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
@@ -41,9 +46,11 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
   // barriers: 0..3 full, 4..7 empty, 8..9 tmem_full, 10..11 tmem_empty
   __shared__ uint32_t tmem_base_s;
+  __shared__ int32_t acols_s[256];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  for (int i = threadIdx.x; i < a.Kdim / GM_KC && i < 256; i += blockDim.x) acols_s[i] = a.a_cols ? a.a_cols[i] : i * GM_KC;
   if (threadIdx.x == 0) {
     for (int s = 0; s < GM_STAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), 128); }
@@ -77,7 +84,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
           mbar_expect_tx(BAR(st), stage_tx);
           uint8_t* sb = smem + st * GM_STAGE_BYTES;
           // pass 0: A_hi.W_hi   pass 1: A_lo.W_hi   pass 2: A_hi.W_lo
-          tma_load_2d(smem_u32(sb), (pass == 1) ? &mapAlo : &mapAhi, kc * GM_KC, mt * GM_BM, BAR(st));
+          tma_load_2d(smem_u32(sb), (pass == 1) ? &mapAlo : &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
           tma_load_2d(smem_u32(sb + GM_A_BYTES), (pass == 2) ? &mapWlo : &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
         }
       }
@@ -138,7 +145,12 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
               x[j] = val;
             }
             const bool full = (o + 3 < a.O);
-            if (a.raw_out) {
+            if (a.amax_arg) {          // running (max, argmax) over successive launches; strict '>' keeps the first maximum
+              for (int j = 0; j < 4 && o + j < a.O; ++j) {
+                const long long ix = r * a.raw_ld + o + j;
+                if (x[j] > a.raw_out[ix]) { a.raw_out[ix] = x[j]; a.amax_arg[ix] = (uint8_t)a.amax_id; }
+              }
+            } else if (a.raw_out) {
               float* p = a.raw_out + r * a.raw_ld + o;
               if (full && ((a.raw_ld & 3) == 0)) *reinterpret_cast<float4*>(p) = make_float4(x[0], x[1], x[2], x[3]);
               else for (int j = 0; j < 4 && o + j < a.O; ++j) p[j] = x[j];
@@ -194,7 +206,7 @@ static inline int gemm_make_map(roreg_ctx* c, CUtensorMap* m, const float* base,
 static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo,
                                  long long w_rows, GemmArgs a, cudaStream_t st) {
   if (a.R <= 0) return ROREG_OK;
-  if (a.Kdim % GM_KC || a.NT % 16 || a.NT < 16 || a.NT > 256 || (a.npass != 1 && a.npass != 3) || (a.npass == 3 && (!A_lo || !W_lo))) {
+  if (a.Kdim / GM_KC > 256 || a.Kdim % GM_KC || a.NT % 16 || a.NT < 16 || a.NT > 256 || (a.npass != 1 && a.npass != 3) || (a.npass == 3 && (!A_lo || !W_lo))) {
     snprintf(c->err, sizeof(c->err), "gemm_tc_launch: unsupported shape Kdim=%d NT=%d npass=%d", a.Kdim, a.NT, a.npass);
     return ROREG_ERR_UNSUPPORTED;
   }

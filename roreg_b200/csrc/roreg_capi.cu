@@ -11,6 +11,12 @@
 
 using namespace roreg;
 
+static inline unsigned rr_blocks(roreg_ctx* c, long long work, int per_block) {
+  long long b = (work + per_block - 1) / per_block;
+  const long long cap = (long long)c->sm_count * 32;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
 extern "C" {
 
 int roreg_version(void) { return 100; }
@@ -35,6 +41,7 @@ int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const 
       pT8[g * 60 + a] = (uint8_t)v;       // pT8[h][g] = P[g][h]
     }
   for (int i = 0; i < 540; ++i) r32[i] = (float)rot[i];
+  memcpy(c->h_perm8, p8, 3600);
   RR_CUDA(c, cudaMalloc(&c->d_perm8, 3600));
   RR_CUDA(c, cudaMalloc(&c->d_permT8, 3600));
   RR_CUDA(c, cudaMalloc(&c->d_nei, 60 * 13 * sizeof(int32_t)));
@@ -328,14 +335,45 @@ int roreg_quat_normalize(roreg_ctx* c, const float* q_in, int ld, int K, float* 
   return ROREG_OK;
 }
 
+// all-pairs 60-rotation correlation (north_star kernel 1): 60 K-permuted tcgen05 GEMMs with a
+// running (max, argmax) epilogue; X / Y are the channel-last tf32-split descriptors from roreg_pack_descriptors
+int roreg_group_corr_allpairs(roreg_ctx* c, const float* X_hi, const float* X_lo, int N, const float* Y_hi, const float* Y_lo, int M,
+                              int npass, float* best, uint8_t* best_a, int32_t* nn, int32_t* nn_a, float* nn_dist, void* stream) {
+  RR_ARG(c, X_hi && Y_hi && best && best_a && N >= 1 && M >= 1 && (npass == 1 || (npass == 3 && X_lo && Y_lo)));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * 60 * 60) + rr_align(sizeof(float) * N) + rr_align(sizeof(float) * M) + 4096);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  int32_t* cols = ar.take<int32_t>(3600); float* nx = ar.take<float>(N); float* ny = ar.take<float>(M);
+  // column coordinate of k-chunk g for rotation a: P[a][g]*32   (cor_a = sum_g <X[:,P[a,g]], Y[:,g]>, test/estimator.py:85-89)
+  {
+    static int32_t h_cols[3600];
+    for (int i = 0; i < 3600; ++i) h_cols[i] = (int32_t)c->h_perm8[i] * 32;
+    RR_CUDA(c, cudaMemcpyAsync(cols, h_cols, sizeof(h_cols), cudaMemcpyHostToDevice, st));
+  }
+  fill_f32_kernel<<<rr_blocks(c, (long long)N * M, 256), 256, 0, st>>>(best, (long long)N * M, -INFINITY);
+  RR_LAUNCH_CHECK(c);
+  for (int a_id = 0; a_id < 60; ++a_id) {
+    GemmArgs g{};
+    g.R = N; g.Kdim = 1920; g.O = M; g.NT = M >= 256 ? 256 : ((M + 15) / 16) * 16; g.n_ntiles = (M + g.NT - 1) / g.NT; g.npass = npass;
+    g.raw_out = best; g.raw_ld = M; g.a_cols = cols + a_id * 60; g.amax_arg = best_a; g.amax_id = a_id;
+    if ((rc = gemm_tc_launch(c, X_hi, X_lo, Y_hi, Y_lo, M, g, st))) return rc;
+  }
+  if (nn) {
+    RR_ARG(c, nn_a && nn_dist);
+    row_sqnorm_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(X_hi, X_lo, N, 1920, nx);
+    RR_LAUNCH_CHECK(c);
+    row_sqnorm_kernel<<<(unsigned)((M + 7) / 8), 256, 0, st>>>(Y_hi, Y_lo, M, 1920, ny);
+    RR_LAUNCH_CHECK(c);
+    allpairs_rowmin_kernel<<<N, 256, 0, st>>>(best, best_a, N, M, nx, ny, nn, nn_a, nn_dist);
+    RR_LAUNCH_CHECK(c);
+  }
+  return ROREG_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Match_ot glue (network/rot_coh_match.py)
 // ------------------------------------------------------------------------------------------------
-static inline unsigned rr_blocks(roreg_ctx* c, long long work, int per_block) {
-  long long b = (work + per_block - 1) / per_block;
-  const long long cap = (long long)c->sm_count * 32;
-  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
-}
 
 int roreg_topk_rows(roreg_ctx* c, const float* S, int m, int n, int ld, int k, int32_t* idx, void* stream) {
   RR_ARG(c, S && idx && m >= 0 && n >= 1 && ld >= n && k >= 1 && k <= 16 && k <= n && n <= 11000);

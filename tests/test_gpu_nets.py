@@ -149,3 +149,47 @@ def test_net_plugins_reproduce_reference_files(tmp_path):
         r = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")
         assert int(r["recalltime"]) == int(z[f"yohoo_recall_{id0}-{id1}"])
         assert np.abs(r["trans"] - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("npass,tol", [(3, 1e-4), (1, 2e-2)])
+def test_group_corr_allpairs(ctx, tables, npass, tol):
+    """All-pairs 60-rotation correlation (north_star kernel 1): max_a / argmax_a of cor_a(n,m) for every (n,m) against the
+    float64 restatement of test/estimator.py:85-89 on every pair, and the rotation-invariant NN per row."""
+    import ctypes as C
+    from roreg_b200 import nets, _lib
+    from roreg_b200.ops import _ptr, _stream
+    pr = synth.make_pair(71, n=200)
+    X = pr["feats1"][:150]; Y = pr["feats0"][:130]
+    g = nets.GroupNets(ctx, npass)
+    xh, xl = g.pack([ctx.dev(X)], [None], [0], None, X.shape[0]); yh, yl = g.pack([ctx.dev(Y)], [None], [0], None, Y.shape[0])
+    N, M = X.shape[0], Y.shape[0]
+    best = torch.empty((N, M), dtype=torch.float32, device=ctx.device); ba = torch.empty((N, M), dtype=torch.uint8, device=ctx.device)
+    nn = torch.empty(N, dtype=torch.int32, device=ctx.device); nna = torch.empty(N, dtype=torch.int32, device=ctx.device)
+    nd = torch.empty(N, dtype=torch.float32, device=ctx.device)
+    rc = ctx.lib.roreg_group_corr_allpairs(ctx.h, _ptr(xh), _ptr(xl), N, _ptr(yh), _ptr(yl), M, npass, _ptr(best), _ptr(ba), _ptr(nn), _ptr(nna),
+                                           _ptr(nd), _stream())
+    _lib.check(ctx.h, rc, "roreg_group_corr_allpairs")
+    torch.cuda.synchronize()
+    # float64 reference: cor[n,m,a] = sum_{f,g} X[n,f,P[a,g]] Y[m,f,g]
+    Xp = X.astype(np.float64)[:, :, tables.perm]            # [N,32,60(a),60(g)]
+    cor = np.einsum("nfag,mfg->nma", Xp, Y.astype(np.float64))
+    ref_best = cor.max(2); ref_a = cor.argmax(2)
+    assert np.abs(_np(best) - ref_best).max() < tol * 10                   # |cor| <= 60
+    top2 = np.sort(cor, axis=2)[:, :, -2:]
+    clear = (top2[:, :, 1] - top2[:, :, 0]) > tol * 20
+    assert (_np(ba)[clear] == ref_a[clear]).all()
+    dist = (X.astype(np.float64) ** 2).sum((1, 2))[:, None] + (Y.astype(np.float64) ** 2).sum((1, 2))[None] - 2 * ref_best
+    part = np.partition(dist, 1, axis=1)
+    ok = (part[:, 1] - part[:, 0]) > tol * 40
+    assert (_np(nn)[ok] == dist.argmin(1)[ok]).all()
+    assert np.abs(_np(nd) - dist.min(1))[ok].max() < tol * 40
+    # planted rotation: Y rows that are group-permuted copies of X rows must be found with their rotation index
+    a = 17
+    Y2 = np.ascontiguousarray(X[:64][:, :, tables.perm[a]])
+    yh2, yl2 = g.pack([ctx.dev(Y2)], [None], [0], None, 64)
+    best2 = torch.empty((N, 64), dtype=torch.float32, device=ctx.device); ba2 = torch.empty((N, 64), dtype=torch.uint8, device=ctx.device)
+    rc = ctx.lib.roreg_group_corr_allpairs(ctx.h, _ptr(xh), _ptr(xl), N, _ptr(yh2), _ptr(yl2), 64, npass, _ptr(best2), _ptr(ba2), _ptr(nn), _ptr(nna),
+                                           _ptr(nd), _stream())
+    _lib.check(ctx.h, rc, "roreg_group_corr_allpairs")
+    torch.cuda.synchronize()
+    assert (_np(nn)[:64] == np.arange(64)).all() and (_np(nna)[:64] == a).all()       # Des2R(X, X[:,:,P[a]]) = a on the diagonal
