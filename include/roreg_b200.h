@@ -184,7 +184,8 @@ typedef struct {
   const int32_t* pair_cloud;
   const int32_t* sample;
   int32_t nn_mode;            /* roreg_mutual_match mode                                            */
-  int32_t estimator;          /* 0 = yohoc (coarse-rotation-guided), 1 = yohoo (hypotheses given)   */
+  int32_t estimator;          /* 0 = yohoc (coarse-rotation-guided), 1 = hypotheses given (hyp_host_svd),
+                                 2 = stop after Des2R (then roreg_estimate_batch with ET hypotheses)  */
   int32_t max_iter;           /* RANSAC iterations (hypotheses scored)                              */
   double ird;                 /* inlier radius, cfg.ransac_ird                                      */
   uint64_t seed;              /* device RNG seed (estimator 0 with triplets == NULL)                */
@@ -200,6 +201,10 @@ typedef struct {
 } roreg_batch;
 
 int roreg_register_batch(roreg_ctx* ctx, const roreg_batch* batch, void* stream);
+/* one-shot RANSAC + refinement (test/estimator.py:426-439) of every pair of the batch on caller-provided
+ * hypotheses [B][max_iter][3][4] float64 (n_hyp [B] valid per pair, NULL = all), after estimator = 2.               */
+int roreg_estimate_batch(roreg_ctx* ctx, const roreg_batch* batch, const double* hyps, const int32_t* n_hyp,
+                         void* stream);
 
 /* Per-stage device timing of the last roreg_register_batch call (measurement hook for bench.py; events are
  * recorded on the call's stream).  Stages: 0 inv_pool, 1 nn (both directions), 2 mutual compaction,

@@ -489,7 +489,7 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
                 b->recall && b->best_overlap);
   RR_ARG(c, b->B >= 1 && b->n >= 1 && b->keynum >= 1 && b->keynum <= b->n && b->max_iter >= 1 && b->ird > 0);
   RR_ARG(c, b->sample || b->keynum == b->n);
-  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd));
+  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd) || b->estimator == 2);
   cudaStream_t st = (cudaStream_t)stream;
   const int B = b->B, S = b->keynum, H = b->max_iter;
   const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
@@ -557,6 +557,10 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     RR_LAUNCH_CHECK(c);
   }
   RR_MARK(4);
+  if (b->estimator == 2) {                 // matcher + Des2R only: the caller generates hypotheses (ET network) and calls roreg_estimate_batch
+    if (c->timing) { for (int i = 5; i <= ROREG_N_STAGES; ++i) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); c->ev_valid = 1; }
+    return ROREG_OK;
+  }
   // 5. hypotheses
   MatchView mv{};
   mv.keys0 = b->keys; mv.keys1 = b->keys; mv.pair_cloud = b->pair_cloud; mv.n = b->n; mv.matches = b->matches;
@@ -588,6 +592,32 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   RR_LAUNCH_CHECK(c);
   RR_MARK(7);
   if (c->timing) c->ev_valid = 1;
+  return ROREG_OK;
+}
+
+// steps 6-7 of the batched engine on caller-provided hypotheses (yohoo: ET network + test/estimator.py:349-366):
+// hyps [B][H][3][4] float64, n_hyp [B] valid hypotheses per pair (NULL = H); uses batch->matches / n_matches from a
+// preceding roreg_register_batch(estimator = 2) and writes poses / recall / best_overlap.
+int roreg_estimate_batch(roreg_ctx* c, const roreg_batch* b, const double* hyps, const int32_t* n_hyp, void* stream) {
+  RR_ARG(c, b && hyps && b->keys && b->pair_cloud && b->matches && b->n_matches && b->poses && b->recall && b->best_overlap);
+  RR_ARG(c, b->B >= 1 && b->keynum >= 1 && b->max_iter >= 1 && b->ird > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int B = b->B, S = b->keynum, H = b->max_iter;
+  const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
+  int rc = rr_ws_reserve(c, rr_align(sizeof(double) * (size_t)B * tiles * H) + 4096);
+  if (rc) return rc;
+  rr_arena ar{(char*)c->ws, 0};
+  double* partial = ar.take<double>((size_t)B * tiles * H);
+  MatchView mv{};
+  mv.keys0 = b->keys; mv.keys1 = b->keys; mv.pair_cloud = b->pair_cloud; mv.n = b->n; mv.matches = b->matches;
+  mv.cap = S; mv.n_matches = b->n_matches; mv.K = S; mv.scores = nullptr; mv.scores_f64 = 0; mv.scores_pair_stride = 0;
+  if ((rc = score_and_select(c, mv, S, hyps, (long long)H * 12, nullptr, n_hyp, H, b->ird, partial, nullptr, b->recall,
+                             b->best_overlap, B, st))) return rc;
+  RefineArgs ra{};
+  ra.mv = mv; ra.T_in = nullptr; ra.hyps = hyps; ra.hyp_pair_stride = (long long)H * 12; ra.order = nullptr;
+  ra.best_id = b->recall; ra.rad0 = b->ird * 2.0; ra.rad1 = b->ird; ra.rounds = 2; ra.T_out = b->poses; ra.inlier_mask = nullptr; ra.mask_stride = S;
+  refine_kernel<<<B, 512, 0, st>>>(ra);
+  RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }
 

