@@ -406,7 +406,6 @@ __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_cons
     const int q = warp & 3;
     const int hf = (warp - 2) >> 2;                     // warps 2..5 -> columns 0..63, warps 6..9 -> 64..127
     const int row_in_tile = q * 32 + lane;
-    const int et = threadIdx.x - 64;                    // 0..255
     uint32_t it_t = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int rb = item % nrb, d = (item / nrb) & 1, p = item / (2 * nrb);

@@ -94,8 +94,9 @@ int64_t roreg_launch_count(roreg_ctx* c) { return c ? c->launches : -1; }
 // ------------------------------------------------------------------------------------------------
 int roreg_inv_pool(roreg_ctx* c, const float* eqv, const int32_t* sample, int n_out, int normalise,
                    float* out, void* stream) {
-  RR_ARG(c, eqv && out && n_out >= 0);
-  if (n_out == 0) return ROREG_OK;
+  RR_ARG(c, n_out >= 0);
+  if (n_out == 0) return ROREG_OK;                 // empty input: nothing to do (pointers may be NULL)
+  RR_ARG(c, eqv && out);
   PoolArgs a{eqv, nullptr, sample, 0, n_out, n_out, normalise, out};
   inv_pool_kernel<<<(n_out + 7) / 8, 256, 0, (cudaStream_t)stream>>>(a);
   RR_LAUNCH_CHECK(c);
