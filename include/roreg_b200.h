@@ -74,7 +74,9 @@ int roreg_group_corr(roreg_ctx* ctx, const float* X, const int32_t* idxX, const 
                      void* stream);
 
 /* Arithmetic of the 60x60 Gram inside roreg_group_corr / roreg_register_batch: 0 = float32 FMA on CUDA cores
- * (default), 1 = tcgen05 tensor cores with the 3xTF32 split (float32-class products, different summation order). */
+ * (default), 1 = tcgen05 tensor cores with the 3xTF32 split (float32-class products, different summation order),
+ * two matches per pipeline item and one CTA per SM, 2 = the same arithmetic, one match per item and two co-resident
+ * CTAs per SM (the fast one; results identical to mode 1).                                                        */
 int roreg_set_corr_mode(roreg_ctx* ctx, int mode);
 
 /* ---- a17  test/estimator.py:349-366 + utils/r_eval.py:90-106:

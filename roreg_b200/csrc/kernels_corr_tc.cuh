@@ -4,7 +4,9 @@
 // stacked per MMA (M = N = 128: rows = (match, h), columns = (match, g); the two off-diagonal 64x64
 // blocks are unused - the tensor pipe has the head-room, the kernel is HBM-bound on the 2 x 7680 B it
 // must gather per match).  A descriptor row [32 f][60 h] lands in shared memory exactly as it lies in
-// HBM (TMA box [32 f] x [64 h], no swizzle; columns 60..63 are zero-filled by the tensor map's bound).
+// HBM: ONE 7680-byte cp.async.bulk per row (a 256-byte-aligned contiguous run = 60 full 128-byte lines).
+// (Rounds 1-21 used a 2-D tensor-map box [32 f] x [64 h]; its 240-byte, sector-straddling box rows were
+// issued one by one and capped the bare load skeleton at ~4 TB/s - run 16.)
 // Accuracy: 3xTF32.  A "convert" warp group reads the landed tile, splits hi = tf32(x), lo = x - hi and
 // writes both TRANSPOSED into the K-major SWIZZLE_128B operand layout the NN kernel already uses
 // ([128 rows = (match,h)] x [32 f]), and the issuer runs (hi,hi) + (lo,hi) + (hi,lo) into one TMEM
@@ -14,10 +16,10 @@
 // Epilogue: each thread owns one Gram row in TMEM, writes it transposed to shared memory and thread a
 // sums the generalised diagonal  cor[a] = sum_g G[tab[a][g]][g]  (tab = P: variant 1, P^T: variant 2).
 //
-//   warp 0      TMA producer     8 boxes (2 matches x {X,Y} x 2 h-halves) per stage
+//   warp 0      TMA producer     4 bulk copies (2 matches x {X,Y}) of 7680 B per stage
 //   warp 1      MMA issuer       3 x 4 tcgen05.mma kind::tf32 (M=N=128, K=8), commit -> mbarrier
-//   warps 2-5   convert          hi/lo split + transpose in shared memory, fence.proxy.async, arrive
-//   warps 6-9   epilogue         tcgen05.ld -> smem transpose -> diagonal sums -> argmax
+//   next CW     convert          hi/lo split + transpose in shared memory, fence.proxy.async, arrive   (CW = 4 or 8 warps)
+//   last 4      epilogue         tcgen05.ld -> smem transpose -> diagonal sums -> argmax
 #pragma once
 #include "kernels_nn_tc.cuh"
 #include "kernels_corr.cuh"
@@ -25,25 +27,34 @@
 namespace roreg {
 
 constexpr int CT_STAGES = 4;                              // raw landing buffers: 4 x 32 KB in flight per SM hide the HBM latency (run 13: 2 stages capped the kernel at 2.1 TB/s)
-constexpr int CT_RAW_BOX = 32 * 64 * 4;                   // [32 f][64 h] f32 = 8 KB (one descriptor row, h padded to 64)
-constexpr int CT_RAW_BYTES = 4 * CT_RAW_BOX;              // X0 | X1 | Y0 | Y1 = 32 KB per stage
+constexpr int CT_RAW_BOX = 32 * 60 * 4;                   // [32 f][60 h] f32 = 7680 B: one descriptor row exactly as in HBM
+constexpr int CT_RAW_BYTES = 4 * CT_RAW_BOX;              // X0 | X1 | Y0 | Y1 = 30 KB per stage
 constexpr int CT_OPER_BYTES = 128 * 32 * 4;               // one K-major operand: 128 rows x 32 f = 16 KB
 constexpr int CT_TILES_BYTES = 4 * CT_OPER_BYTES;         // Xhi | Xlo | Yhi | Ylo = 64 KB, single-buffered (double-buffering them bought nothing in run 13)
 constexpr int CT_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h]
-constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 232,224 B of the 232,448 B limit
-constexpr int CT_THREADS = 320;                           // TMA, MMA, 4 convert warps, 4 epilogue warps (8 convert warps measured slower, run 17)
+constexpr int CT_SMEM_BYTES = CT_STAGES * CT_RAW_BYTES + CT_TILES_BYTES + CT_GS_BYTES + 3600 + 16 + 256 + 1024;   // 224,032 B of the 232,448 B limit
+template <int CW> struct CtThreads { static constexpr int value = 64 + 32 * CW + 128; };   // TMA, MMA, CW convert warps, 4 epilogue warps
 
 struct CorrTcArgs {
+  const float* X; const float* Y;    // descriptor arrays [rows][32][60]; filled in by group_corr_tc_launch
   const int32_t* idxX; const int32_t* idxY; int idx_stride;
   const int32_t* pair_cloud; int n;
   const int32_t* n_matches; int K, B;
   const uint8_t* tab;
   float* cor_out; int32_t* argmax_out;
   int dbg_passes, dbg_skip;          // bottleneck experiments only (ROREG_DEBUG_CORR_PASSES / ROREG_DEBUG_CORR_SKIP): defaults 3 / 0
+  long long* trace;                  // mode 2 only, ROREG_DEBUG_CORR_TRACE=<file>: clock64 stamps [256 items][12 events] of CTA 0
 };
 
-__global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __grid_constant__ CUtensorMap mapX,
-                                                                      const __grid_constant__ CUtensorMap mapY, CorrTcArgs a) {
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <int CW>
+__global__ void __launch_bounds__(CtThreads<CW>::value, 1) group_corr_tc_kernel(CorrTcArgs a) {
+  constexpr int CT_THREADS = CtThreads<CW>::value;
+  constexpr int CONV_THREADS = 32 * CW;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* tiles0 = smem + CT_STAGES * CT_RAW_BYTES;                                       // 2 x (Xhi | Xlo | Yhi | Ylo)
@@ -59,9 +70,9 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
 
   for (int e = threadIdx.x; e < 3600; e += CT_THREADS) tabs[e] = a.tab[e];
   if (threadIdx.x == 0) {
-    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(BAR(0 + s), 1); mbar_init(BAR(4 + s), 128); }
+    for (int s = 0; s < CT_STAGES; ++s) { mbar_init(BAR(0 + s), 1); mbar_init(BAR(4 + s), CONV_THREADS); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(10 + s), 1); mbar_init(BAR(12 + s), 128); }
-    mbar_init(BAR(8), 128); mbar_init(BAR(9), 1);
+    mbar_init(BAR(8), CONV_THREADS); mbar_init(BAR(9), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       uint32_t it = 0;
       for (long long base = blockIdx.x; base < n_items; base += 32LL * gridDim.x) {
         const long long item = base + (long long)lane * gridDim.x;
-        int avail = 0; int cx[2] = {0, 0}, cy[2] = {0, 0};
+        int avail = 0; long long cx[2] = {0, 0}, cy[2] = {0, 0};   // row numbers in X / Y
         if (item < n_items) {
           int p, k0; avail = item_count(item, p, k0);
           if (avail > 0) {
@@ -102,24 +113,24 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
               long long rx = a.idxX ? a.idxX[w * a.idx_stride] : k;
               long long ry = a.idxY ? a.idxY[w * a.idx_stride] : k;
               if (a.pair_cloud) { rx += (long long)a.pair_cloud[2 * p + 1] * a.n; ry += (long long)a.pair_cloud[2 * p] * a.n; }
-              cx[m] = (int)(rx * 32); cy[m] = (int)(ry * 32);
+              cx[m] = rx; cy[m] = ry;
             }
           }
         }
         for (int l = 0; l < 32; ++l) {
           const int av = __shfl_sync(0xffffffffu, avail, l);
-          const int x0 = __shfl_sync(0xffffffffu, cx[0], l), x1 = __shfl_sync(0xffffffffu, cx[1], l);
-          const int y0 = __shfl_sync(0xffffffffu, cy[0], l), y1 = __shfl_sync(0xffffffffu, cy[1], l);
+          const long long x0 = __shfl_sync(0xffffffffu, cx[0], l), x1 = __shfl_sync(0xffffffffu, cx[1], l);
+          const long long y0 = __shfl_sync(0xffffffffu, cy[0], l), y1 = __shfl_sync(0xffffffffu, cy[1], l);
           if (av <= 0) continue;                         // uniform across the warp (shuffled value)
           if (lane == 0) {
             const int st = it % CT_STAGES; const uint32_t ph = (it / CT_STAGES) & 1;
             mbar_wait(BAR(4 + st), ph ^ 1);              // convert warps have consumed this raw buffer
             uint8_t* sb = smem + st * CT_RAW_BYTES;
             mbar_expect_tx(BAR(0 + st), CT_RAW_BYTES);
-            tma_load_2d(smem_u32(sb + 0 * CT_RAW_BOX), &mapX, 0, x0, BAR(0 + st));
-            tma_load_2d(smem_u32(sb + 2 * CT_RAW_BOX), &mapY, 0, y0, BAR(0 + st));
-            tma_load_2d(smem_u32(sb + 1 * CT_RAW_BOX), &mapX, 0, x1, BAR(0 + st));
-            tma_load_2d(smem_u32(sb + 3 * CT_RAW_BOX), &mapY, 0, y1, BAR(0 + st));
+            bulk_load_1d(smem_u32(sb + 0 * CT_RAW_BOX), a.X + x0 * RR_ROW, CT_RAW_BOX, BAR(0 + st));
+            bulk_load_1d(smem_u32(sb + 2 * CT_RAW_BOX), a.Y + y0 * RR_ROW, CT_RAW_BOX, BAR(0 + st));
+            bulk_load_1d(smem_u32(sb + 1 * CT_RAW_BOX), a.X + x1 * RR_ROW, CT_RAW_BOX, BAR(0 + st));
+            bulk_load_1d(smem_u32(sb + 3 * CT_RAW_BOX), a.Y + y1 * RR_ROW, CT_RAW_BOX, BAR(0 + st));
           }
           ++it;
           __syncwarp();
@@ -152,11 +163,13 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
         ++it;
       }
     }
-  } else if (warp < 6) {
+  } else if (warp < 2 + CW) {
     // ===================== convert: split hi/lo and transpose into K-major SW128 operand tiles ============
-    // raw[f][h] (h contiguous, pitch 64) -> tile row r = (match, h), 128 B of f per row, 16-B chunk c = f/4
-    // stored at chunk position c ^ (r % 8)  (the 128-byte swizzle TMA / UMMA use).
-    const int ct = threadIdx.x - 64;                   // 0..127 == operand row (match = ct/64, h = ct%64)
+    // raw[f][h] (h contiguous, pitch 60) -> tile row r = (match, h), 128 B of f per row, 16-B chunk c = f/4
+    // stored at chunk position c ^ (r % 8)  (the 128-byte swizzle TMA / UMMA use).  Rows h = 60..63 are zeros.
+    // CW = 4: a thread converts its row of X and of Y; CW = 8: threads 0..127 take X, 128..255 take Y.
+    const int cid = threadIdx.x - 64;
+    const int ct = cid & 127;                          // operand row (match = ct/64, h = ct%64)
     uint32_t it = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       int p, k0; if (item_count(item, p, k0) <= 0) continue;
@@ -166,19 +179,21 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
       uint8_t* tiles = tiles0;
       const float* raw = reinterpret_cast<const float*>(smem + st * CT_RAW_BYTES);
       const int m = ct >> 6, h = ct & 63;
+      const bool live = h < RR_G;
       if (!(a.dbg_skip & 2))
 #pragma unroll
-      for (int op = 0; op < 2; ++op) {                 // 0: X, 1: Y
-        const float* src = raw + (op * 2 + m) * (CT_RAW_BOX / 4) + h;
+      for (int o = 0; o < (CW == 8 ? 1 : 2); ++o) {    // 0: X, 1: Y
+        const int op = (CW == 8) ? (cid >> 7) : o;
+        const float* src = raw + (op * 2 + m) * (CT_RAW_BOX / 4) + (live ? h : 0);
         uint8_t* thi = tiles + (op * 2) * CT_OPER_BYTES + ct * 128;
         uint8_t* tlo = thi + CT_OPER_BYTES;
 #pragma unroll
         for (int c = 0; c < 8; ++c) {
           float4 hv, lv; float x; uint32_t t;
-          x = src[(4 * c + 0) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.x = __uint_as_float(t); lv.x = x - hv.x;
-          x = src[(4 * c + 1) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.y = __uint_as_float(t); lv.y = x - hv.y;
-          x = src[(4 * c + 2) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.z = __uint_as_float(t); lv.z = x - hv.z;
-          x = src[(4 * c + 3) * 64]; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.w = __uint_as_float(t); lv.w = x - hv.w;
+          x = live ? src[(4 * c + 0) * RR_G] : 0.f; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.x = __uint_as_float(t); lv.x = x - hv.x;
+          x = live ? src[(4 * c + 1) * RR_G] : 0.f; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.y = __uint_as_float(t); lv.y = x - hv.y;
+          x = live ? src[(4 * c + 2) * RR_G] : 0.f; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.z = __uint_as_float(t); lv.z = x - hv.z;
+          x = live ? src[(4 * c + 3) * RR_G] : 0.f; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x)); hv.w = __uint_as_float(t); lv.w = x - hv.w;
           const int pos = (c ^ (ct & 7)) * 16;
           *reinterpret_cast<float4*>(thi + pos) = hv;
           *reinterpret_cast<float4*>(tlo + pos) = lv;
@@ -191,7 +206,7 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                            // TMEM lane quadrant of this warp
+    const int q = warp & 3;                            // TMEM lane quadrant of this warp (warp id mod 4, for CW = 4 and 8 alike)
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
     const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
     float* G = Gs + m * 60 * 64;
@@ -268,43 +283,27 @@ __global__ void __launch_bounds__(CT_THREADS, 1) group_corr_tc_kernel(const __gr
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256) : "memory");
 }
 
-// tensor map over a descriptor array viewed as [rows*32][60] float32, box [32 f][64 h] (h 60..63 zero-filled), no swizzle
-static inline int corr_tc_make_map(roreg_ctx* c, CUtensorMap* m, const float* base, long long rows) {
-  CUtensorMap tmp;
-  (void)tmp;
-  static PFN_encodeTiled fn = nullptr;
-  if (!fn) {
-    void* p = nullptr; cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !p || qres != cudaDriverEntryPointSuccess) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled entry point unavailable"); return ROREG_ERR_CUDA; }
-    fn = (PFN_encodeTiled)p;
+template <int CW>
+static inline int group_corr_tc_launch_cw(roreg_ctx* c, const CorrTcArgs& a, int grid, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
+    attr_set = true;
   }
-  const cuuint64_t dims[2] = {(cuuint64_t)RR_G, (cuuint64_t)rows * RR_F};
-  const cuuint64_t strides[1] = {(cuuint64_t)RR_G * sizeof(float)};
-  const cuuint32_t box[2] = {64, 32};
-  const cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(desc) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
+  group_corr_tc_kernel<CW><<<grid, CtThreads<CW>::value, CT_SMEM_BYTES, st>>>(a);
+  RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }
 
-static inline int group_corr_tc_launch(roreg_ctx* c, const float* X, long long rowsX, const float* Y, long long rowsY,
-                                       const CorrTcArgs& a, cudaStream_t st) {
-  CUtensorMap mX, mY;
-  int rc;
-  if ((rc = corr_tc_make_map(c, &mX, X, rowsX))) return rc;
-  if ((rc = corr_tc_make_map(c, &mY, Y, rowsY))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-    attr_set = true;
-  }
+// X, Y: descriptor arrays [rows][32][60] float32 (a row = 7680 B, so any 16-byte aligned base keeps every bulk copy aligned)
+static inline int group_corr_tc_launch(roreg_ctx* c, const float* X, const float* Y, CorrTcArgs a, cudaStream_t st) {
+  RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
+  a.X = X; a.Y = Y;
   const long long items = (long long)a.B * ((a.K + 1) / 2);
   const int grid = (int)(items < c->sm_count ? items : c->sm_count);
-  group_corr_tc_kernel<<<grid, CT_THREADS, CT_SMEM_BYTES, st>>>(mX, mY, a);
-  RR_LAUNCH_CHECK(c);
-  return ROREG_OK;
+  static int cw = 0;
+  if (!cw) { cw = 4; if (const char* e = getenv("ROREG_DEBUG_CORR_CW")) if (atoi(e) == 8) cw = 8; }
+  return cw == 8 ? group_corr_tc_launch_cw<8>(c, a, grid, st) : group_corr_tc_launch_cw<4>(c, a, grid, st);
 }
 
 }  // namespace roreg

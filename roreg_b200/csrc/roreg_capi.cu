@@ -5,6 +5,8 @@
 #include "kernels_ransac.cuh"
 #include "kernels_nn_tc.cuh"
 #include "kernels_corr_tc.cuh"
+#include "kernels_corr_tc2.cuh"
+#include "kernels_nn_tc4.cuh"
 #include "kernels_gemm_tc.cuh"
 #include "kernels_gconv.cuh"
 #include "kernels_matchot.cuh"
@@ -67,7 +69,7 @@ int roreg_ctx_destroy(roreg_ctx* c) {
 }
 
 int roreg_set_corr_mode(roreg_ctx* c, int mode) {
-  RR_ARG(c, mode == 0 || mode == 1);
+  RR_ARG(c, mode >= 0 && mode <= 2);
   c->corr_mode = mode;
   return ROREG_OK;
 }
@@ -127,20 +129,30 @@ int roreg_knn(roreg_ctx* c, const float* target, int n, const float* source, int
 
 int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, int n1, int mode,
                        int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream) {
-  RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode >= 0 && mode <= 3));
+  RR_ARG(c, f0 && f1 && matches && n_matches && n0 >= 1 && n1 >= 1 && (mode >= 0 && mode <= 4));
   cudaStream_t st = (cudaStream_t)stream;
   if (mode >= 1 && n0 != n1) {
     snprintf(c->err, sizeof(c->err), "nn mode 1 (tcgen05 Gram) needs n0 == n1 in the single-pair entry");
     return ROREG_ERR_UNSUPPORTED;
   }
   size_t need = rr_align(sizeof(int32_t) * n0) + rr_align(sizeof(int32_t) * n1) + 4096;
-  if (mode >= 1) need += rr_align(sizeof(float) * 2 * (size_t)n0 * RR_F) + nn_tc_workspace_bytes(2LL * n0);
+  if (mode == 4) need += rr_align(sizeof(float) * 2 * (size_t)n0 * RR_F) + nn_tc4_workspace_bytes(1, n0) + 2048;
+  else if (mode >= 1) need += rr_align(sizeof(float) * 2 * (size_t)n0 * RR_F) + nn_tc_workspace_bytes(2LL * n0);
   int rc = rr_ws_reserve(c, need);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
   int32_t* w01 = nn01 ? nn01 : ar.take<int32_t>(n0);
   int32_t* w10 = nn10 ? nn10 : ar.take<int32_t>(n1);
-  if (mode >= 1) {
+  if (mode == 4) {
+    float* inv2 = ar.take<float>(2 * (size_t)n0 * RR_F);
+    const size_t NT = (size_t)(n0 + TC_BM - 1) / TC_BM;
+    ar.off = (ar.off + 1023) & ~size_t(1023);
+    uint8_t* img = ar.take<uint8_t>(2 * NT * T4_TILE_BYTES);
+    unsigned long long* rowpart = ar.take<unsigned long long>(NT * NT * TC_BM);
+    RR_CUDA(c, cudaMemcpyAsync(inv2, f0, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
+    RR_CUDA(c, cudaMemcpyAsync(inv2 + (size_t)n0 * RR_F, f1, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
+    if ((rc = nn_tc4_launch_both(c, inv2, n0, 1, img, rowpart, w01, w10, st))) return rc;
+  } else if (mode >= 1) {
     float* inv2 = ar.take<float>(2 * (size_t)n0 * RR_F);
     float* Ahat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
     float* Bhat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
@@ -165,9 +177,10 @@ int roreg_group_corr(roreg_ctx* c, const float* X, const int32_t* idxX, const fl
                      int K, int variant, float* cor_out, int32_t* argmax_out, void* stream) {
   RR_ARG(c, X && Y && K >= 0 && (variant == 1 || variant == 2) && (cor_out || argmax_out));
   if (K == 0) return ROREG_OK;
-  if (c->corr_mode == 1) {
-    CorrTcArgs t{idxX, idxY, 1, nullptr, 0, nullptr, K, 1, (variant == 1) ? c->d_perm8 : c->d_permT8, cor_out, argmax_out, 3, 0};
-    return group_corr_tc_launch(c, X, 1LL << 25, Y, 1LL << 25, t, (cudaStream_t)stream);   // row bound unknown here: indices are trusted
+  if (c->corr_mode >= 1) {
+    CorrTcArgs t{nullptr, nullptr, idxX, idxY, 1, nullptr, 0, nullptr, K, 1, (variant == 1) ? c->d_perm8 : c->d_permT8, cor_out, argmax_out, 3, 0, nullptr};
+    return c->corr_mode == 2 ? group_corr_tc2_launch(c, X, Y, t, (cudaStream_t)stream)
+                             : group_corr_tc_launch(c, X, Y, t, (cudaStream_t)stream);   // indices are trusted
   }
   CorrArgs a{};
   a.X = X; a.Y = Y; a.idxX = idxX; a.idxY = idxY; a.idx_stride = 1; a.pair_cloud = nullptr; a.n = 0;
@@ -498,8 +511,9 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
                 rr_align(sizeof(double) * (size_t)B * H * 12) + rr_align(sizeof(double) * (size_t)B * tiles * H) +
                 rr_align(sizeof(int32_t) * (size_t)B * S) + 4 * rr_align(sizeof(int32_t) * (size_t)B) +
                 rr_align(sizeof(int32_t) * (size_t)B * 128) + rr_align(sizeof(double) * (size_t)B * 60) + 8192;
-  if (b->nn_mode >= 1) need += nn_tc_workspace_bytes((long long)B * 2 * S);
-  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 3);
+  if (b->nn_mode == 4) need += nn_tc4_workspace_bytes(B, S) + 2048;
+  else if (b->nn_mode >= 1) need += nn_tc_workspace_bytes((long long)B * 2 * S);
+  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 4);
   int rc = rr_ws_reserve(c, need);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
@@ -522,7 +536,13 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   RR_MARK(1);
   // 2. 1-NN both ways  (test/matcher.py:94-97)
   const long long ps = 2LL * S * RR_F;
-  if (b->nn_mode >= 1) {
+  if (b->nn_mode == 4) {
+    const size_t NT = (size_t)(S + TC_BM - 1) / TC_BM;
+    ar.off = (ar.off + 1023) & ~size_t(1023);
+    uint8_t* img = ar.take<uint8_t>((size_t)B * 2 * NT * T4_TILE_BYTES);
+    unsigned long long* rowpart = ar.take<unsigned long long>((size_t)B * NT * NT * TC_BM);
+    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowpart, nn01, nn10, st))) return rc;
+  } else if (b->nn_mode >= 1) {
     float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* nh = ar.take<float>((size_t)B * 2 * S);
@@ -545,12 +565,11 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   co.X = b->desc; co.Y = b->desc; co.idxX = b->matches + 1; co.idxY = b->matches; co.idx_stride = 2;
   co.pair_cloud = b->pair_cloud; co.n = b->n; co.n_matches = b->n_matches; co.K = S; co.B = B;
   co.tab = c->d_perm8; co.cor_out = nullptr; co.argmax_out = b->dr_index;
-  if (c->corr_mode == 1) {
-    CorrTcArgs t{b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index, 3, 0};
+  if (c->corr_mode >= 1) {
+    CorrTcArgs t{nullptr, nullptr, b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index, 3, 0, nullptr};
     if (const char* e = getenv("ROREG_DEBUG_CORR_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) t.dbg_passes = v; }
     if (const char* e = getenv("ROREG_DEBUG_CORR_SKIP")) t.dbg_skip = atoi(e);
-    const long long rows = (long long)b->n_clouds * b->n;
-    if ((rc = group_corr_tc_launch(c, b->desc, rows, b->desc, rows, t, st))) return rc;
+    if ((rc = (c->corr_mode == 2 ? group_corr_tc2_launch(c, b->desc, b->desc, t, st) : group_corr_tc_launch(c, b->desc, b->desc, t, st)))) return rc;
   } else {
     const long long total = (long long)B * S;
     const int grid = (int)(total < (long long)c->sm_count * 8 ? total : (long long)c->sm_count * 8);

@@ -321,7 +321,7 @@ def _check_nn_tc(idx, target, source):
     return int(bad.sum())
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 @pytest.mark.parametrize("n", [1200, 128, 131, 700, 300])
 def test_mutual_match_tensor_core_mode(ctx, n, mode):
     """nn mode 1: tcgen05 (kind::tf32, 3xTF32 split) Gram + TMEM-side running argmin; indices must equal the
@@ -341,7 +341,22 @@ def test_mutual_match_tensor_core_mode(ctx, n, mode):
             assert np.array_equal(m, ref)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_mutual_match_mode4_duplicates_pick_first_index(ctx):
+    """nn mode 4 (one Gram, column sweep): exact duplicate rows produce bit-equal distances; both directions must then
+    return the LOWER index, as torch.min does (rows spread over several 128-row tiles and both column halves)."""
+    rng = np.random.default_rng(11)
+    f0 = rng.standard_normal((700, 32)).astype(np.float32); f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+    f1 = rng.standard_normal((700, 32)).astype(np.float32); f1 /= np.linalg.norm(f1, axis=1, keepdims=True)
+    f1[40] = f0[5]; f1[300] = f0[5]; f1[650] = f0[5]          # row 5 of cloud 0 has three identical nearest columns
+    f0[100] = f1[77]; f0[400] = f1[77]; f0[690] = f1[77]      # column 77 of cloud 1 has three identical nearest rows
+    m, cnt, nn01, nn10 = ctx.mutual_match(ctx.dev(f0), ctx.dev(f1), 4)
+    torch.cuda.synchronize()
+    assert int(_np(nn01)[5]) == 40 and int(_np(nn10)[77]) == 100
+    assert int(_np(nn10)[40]) == 5 and int(_np(nn10)[300]) == 5 and int(_np(nn10)[650]) == 5
+    assert int(_np(nn01)[100]) == 77 and int(_np(nn01)[400]) == 77 and int(_np(nn01)[690]) == 77
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3, 4])
 def test_register_batch_tensor_core_nn(ctx, tables, mode):
     seeds = [91, 92, 93]; n = 900
     prs = [synth.make_pair(s, n=n) for s in seeds]
@@ -359,12 +374,12 @@ def test_register_batch_tensor_core_nn(ctx, tables, mode):
         assert len(a ^ b) <= 4          # the two NN arithmetics may differ on a handful of near ties only
 
 
-# ---------------------------------------------------------------------------------------- corr mode 1 (tcgen05)
-@pytest.fixture(scope="module")
-def ctx_tc():
+# ---------------------------------------------------------------------------------------- corr modes 1, 2 (tcgen05)
+@pytest.fixture(scope="module", params=[1, 2], ids=["corr1", "corr2"])
+def ctx_tc(request):
     from roreg_b200 import ops
     c = ops.Context(0)
-    c.set_corr_mode(1)
+    c.set_corr_mode(request.param)
     yield c
     c.close()
 
