@@ -76,7 +76,8 @@ int roreg_group_corr(roreg_ctx* ctx, const float* X, const int32_t* idxX, const 
 /* Arithmetic of the 60x60 Gram inside roreg_group_corr / roreg_register_batch: 0 = float32 FMA on CUDA cores
  * (default), 1 = tcgen05 tensor cores with the 3xTF32 split (float32-class products, different summation order),
  * two matches per pipeline item and one CTA per SM, 2 = the same arithmetic, one match per item and two co-resident
- * CTAs per SM (the fast one; results identical to mode 1).                                                        */
+ * CTAs per SM (results identical to mode 1), 3 = float16 two-accumulator split (x = hi + 2^-11 lo', same accuracy class),
+ * operands converted straight from registers into MN-major tiles - the shared-memory-lean, fastest one.            */
 int roreg_set_corr_mode(roreg_ctx* ctx, int mode);
 
 /* ---- a17  test/estimator.py:349-366 + utils/r_eval.py:90-106:

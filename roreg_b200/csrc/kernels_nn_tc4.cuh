@@ -1,81 +1,115 @@
 // kernels_nn_tc4.cuh - mutual-NN search, nn mode 4: ONE Gram per pair, both directions from the same accumulators,
-// norms folded into the contraction, epilogue free of shared-memory traffic.
+// norms folded into the contraction, float16 two-accumulator arithmetic, epilogue free of shared-memory traffic.
 //
-// What runs 12/13/23 established about modes 1-3:
+// What runs 12/13/23/26/28 established about modes 1-3 and the first (3xTF32) cut of this kernel:
 //   * reading accumulators out of TMEM is not the limit (818 B/clk/SM with 8 warps, scripts/tmem_bench.cu);
 //   * a K = 8 tf32 MMA with both operands in shared memory reads 8 KB per 64 clk = the SM's whole shared-memory
-//     bandwidth, so every LDS the epilogue issues (column norms) competes with the tensor pipe (mode-2 inner loop:
-//     430 -> 814 clk per tile once MMAs run beside it);
-//   * modes 1/2 compute the Gram twice (once per direction): 2 x 1600 tiles of 832 tensor-pipe clocks per pair and
-//     3.3 GB of operand tiles streamed L2 -> SM per 32 pairs.
+//     bandwidth, so every LDS the epilogue issues (column norms) competes with the tensor pipe;
+//   * modes 1/2 compute the Gram twice (once per direction) and stream 3.3 GB of operand tiles L2 -> SM per 32 pairs;
+//   * FSETP / FMNMX / SEL / PRMT issue at half rate: at 5.5 such instructions per accumulator element the epilogue,
+//     not the tensor pipe, paced the 3xTF32 cut (1460 of 2300 clk per tile, profiles/r01_run28_nn4_timeline.txt), and
+//     its 48 KB tiles made the L2 -> SM stream (2.5 GB per 32 pairs) the next wall.
 // Mode 4 therefore
-//   * folds -|a|^2/2 - |b|^2/2 into the MMA as a 13th K-step (extended operand columns [-n_hi, -n_lo, 1, 1] x
-//     [1, 1, -n_hi, -n_lo]), so an accumulator element IS -d^2/2 and the epilogue is compares on registers only;
+//   * splits x = hi + lo with hi = fp16(x), lo' = fp16((x - hi) * 2^11) and keeps TWO accumulators per tile,
+//       D1 = hi.hi,   D2 = lo'.hi + hi.lo',   value = D1 + 2^-11 * D2
+//     (products of 11-bit mantissas are exact in the f32 accumulator; only lo.lo ~ 2^-22 is dropped, as with 3xTF32):
+//     operand rows are 128 B instead of 256 B and a tile costs 8 kind::f16 MMAs (512 clk) instead of 13 tf32 ones;
+//   * folds -|a|^2/2 - |b|^2/2 into both accumulators through one extra K-step each (the half-norm is carried as three
+//     fp16 pieces n1 + 2^-11 (n2 + n3)), so  value = -d^2/2  and the epilogue never touches shared memory;
 //   * makes a CTA own a 128-column block of cloud 1 (stationary B tile) and sweep all row tiles of cloud 0 through
 //     it: the column direction (nn10) is a per-thread running maximum over the sweep, kept in registers
-//     (cmax[64] + packed tile indices) and reduced across lanes once per item; the row direction (nn01) is the
-//     per-tile maximum of the 64 registers a thread holds, published as a packed (value, column) key per
-//     (row, column block) and reduced by a small finishing kernel;
+//     (cmax[64] + packed tile indices) and reduced across lanes once per item; the row direction (nn01) only
+//     records the maximum VALUE of every (row, 64-column chunk) and which of its eight 8-column groups holds it
+//     - 0.8 instruction per element - and two small kernels finish it: best chunk per row, then the exact index
+//     among that group's 8 columns in the REFERENCE's float32 difference-form arithmetic (utils/knn_search.py:33-38);
 //   * reads operands from a tile-major, pre-swizzled image written by the prep kernel (exactly the bytes of the
 //     SWIZZLE_128B K-major shared-memory layout), so a tile is ONE contiguous cp.async.bulk - no tensor maps.
 //
-//   warp 0      producer   48 KB bulk copies: stationary tile once per item, streaming tiles through 3 stages
-//   warp 1      MMA        13 x tcgen05.mma kind::tf32 (M = N = 128, K = 8) per tile into 4 TMEM accumulators
-//   warps 2-9   epilogue   tcgen05.ld 32x32b.x32 x2 -> column running max / row max + first index
+//   warp 0      producer   32 KB bulk copies: stationary tile once per item, streaming tiles through 5 stages
+//   warp 1      MMA        8 x tcgen05.mma kind::f16 (M = N = 128, K = 16) per tile, 2 x (D1 | D2) in TMEM
+//   warps 2-9   epilogue   tcgen05.ld 32x32b.x32 -> FFMA combine -> column running max / chunk-row max
 #pragma once
+#include <cuda_fp16.h>
 #include "kernels_nn_tc.cuh"
 
 namespace roreg {
 
-constexpr int T4_TILE_BYTES = 3 * TC_BOX_BYTES;                  // [hi | lo | ext] = 48 KB per 128-row tile
-constexpr int T4_STAGES = 3;
-constexpr int T4_ACC = 4;                                        // TMEM accumulators (4 x 128 columns = all 512)
+constexpr int T4_TILE_BYTES = 2 * TC_BOX_BYTES;                  // [hi | lo'] box + extension box = 32 KB per 128-row tile
+constexpr int T4_STAGES = 5;
 constexpr int T4_THREADS = 64 + 256;
-constexpr int T4_SMEM_BYTES = T4_TILE_BYTES * (1 + T4_STAGES) + 128 * 8 /*row merge*/ + 2 * 4 * 64 * 8 /*column merge*/ + 1024 + 256;
-constexpr float T4_PAD_NORM = 1e30f;                             // half-norm of a padding row: its distances lose every comparison
+constexpr int T4_SMEM_BYTES = T4_TILE_BYTES * (1 + T4_STAGES) + 2 * 4 * 64 * 8 /*column merge*/ + 1024 + 256;
+constexpr float T4_PAD_NORM = 30000.f;                           // half-norm of a padding row (fp16-representable): loses every comparison
+constexpr float T4_LO_SCALE = 2048.f, T4_LO_UNSCALE = 1.f / 2048.f;
+// kind::f16 (A, B = F16, K-major), D = f32, M = 128, N = 128
+constexpr uint32_t T4_IDESC = (1u << 4) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
-// element (r, k) of a [128 x 32 f32] K-major SWIZZLE_128B box: 16-byte chunk k/4 of row r sits at chunk (k/4) ^ (r % 8)
-__device__ __forceinline__ int t4_sw128(int r, int k) { return r * 128 + ((((k >> 2) ^ (r & 7))) << 4) + ((k & 3) << 2); }
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
+}
 
-// ---- prep: pooled features [B*2][S][32] -> tile images [B*2][NT][48 KB] ---------------------------------------
+// byte offset of fp16 element (r, k), k < 64, in a [128 x 128 B] K-major SWIZZLE_128B box:
+// 16-byte chunk (2k / 16) of row r sits at chunk position (2k / 16) ^ (r % 8)
+__device__ __forceinline__ int t4_sw128_h(int r, int k) { return r * 128 + ((((k >> 3) ^ (r & 7))) << 4) + ((k & 7) << 1); }
+
+// ---- prep: pooled features [B*2][S][32] -> tile images [B*2][NT][32 KB] ---------------------------------------
+// box 0, row r: hi[0..31] | lo'[0..31];  box 1, row r (64 fp16 columns):
+//   0..15  row-role extension     [-n1, 1, -n2, -n3, 1, 1, 0...]
+//   16..31 column-role, for D1    [ 1, -n1, 0...]
+//   32..47 column-role, for D2    [ 0, 0, 1, 1, -n2, -n3, 0...]
+// so that  ext_row . ext_col1 = -na1 - nb1  and  ext_row . ext_col2 = -(na2 + na3) - (nb2 + nb3).
 __global__ void __launch_bounds__(256) nn_tc4_prep_kernel(const float* __restrict__ inv, int S, int NT, long long total_rows,
                                                           uint8_t* __restrict__ img) {
-  const long long gr = blockIdx.x * 8LL + (threadIdx.x >> 5);    // padded row number over all (pair, side)
+  // a warp converts 4 consecutive padded rows: the 4 loads are issued before anything is used (the kernel is latency-bound)
+  const long long gr0 = (blockIdx.x * 8LL + (threadIdx.x >> 5)) * 4;    // padded row number over all (pair, side)
   const int lane = threadIdx.x & 31;
-  if (gr >= total_rows) return;
-  const int Sp = NT * TC_BM;
-  const long long ps = gr / Sp; const int rr = (int)(gr % Sp);   // (pair, side), row within the padded cloud
-  const int t = rr >> 7, r = rr & 127;
-  uint8_t* tile = img + (ps * NT + t) * (long long)T4_TILE_BYTES;
-  float x = 0.f;
-  if (rr < S) x = inv[(ps * S + rr) * 32 + lane];
-  uint32_t hb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
-  const float hi = __uint_as_float(hb);
-  const float lo = x - hi;
-  const float nh = (rr < S) ? 0.5f * warp_sum(x * x) : T4_PAD_NORM;
-  uint32_t nb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(nb) : "f"(nh));
-  const float n_hi = __uint_as_float(nb);
-  uint32_t lb;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lb) : "f"(nh - n_hi));
-  const float n_lo = __uint_as_float(lb);
-  // extended columns: 0..7 = row-role vector (A operand), 8..15 = column-role vector (B operand), 16..31 unused
-  float e = 0.f;
-  if (lane == 0 || lane == 10) e = -n_hi;
-  else if (lane == 1 || lane == 11) e = -n_lo;
-  else if (lane == 2 || lane == 3 || lane == 8 || lane == 9) e = 1.f;
-  const int off = t4_sw128(r, lane);
-  *reinterpret_cast<float*>(tile + off) = hi;
-  *reinterpret_cast<float*>(tile + TC_BOX_BYTES + off) = lo;
-  *reinterpret_cast<float*>(tile + 2 * TC_BOX_BYTES + off) = e;
+  if (gr0 >= total_rows) return;
+  const int Sp = NT * TC_BM;                                             // multiple of 4: the 4 rows share (pair, side) and tile
+  const long long ps = gr0 / Sp; const int rr0 = (int)(gr0 % Sp);
+  float xs[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) xs[u] = (rr0 + u < S) ? inv[(ps * S + rr0 + u) * 32 + lane] : 0.f;
+  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int rr = rr0 + u, t = rr >> 7, r = rr & 127;
+    uint8_t* tile = img + (ps * NT + t) * (long long)T4_TILE_BYTES;
+    const float x = xs[u];
+    const __half hi = __float2half_rn(x);
+    const __half lo = __float2half_rn((x - __half2float(hi)) * T4_LO_SCALE);
+    const float nh = (rr < S) ? 0.5f * warp_sum(x * x) : T4_PAD_NORM;
+    const __half n1 = __float2half_rn(nh);
+    const float r1 = (nh - __half2float(n1)) * T4_LO_SCALE;
+    const __half n2 = __float2half_rn(r1);
+    const __half n3 = __float2half_rn(r1 - __half2float(n2));
+    // lane L stores 32-bit word L of the 128-byte row: words 0..15 = hi pairs, 16..31 = lo' pairs (one coalesced row per warp)
+    {
+      const uint32_t hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
+      const int s0 = (2 * lane) & 31;
+      const uint32_t h0 = __shfl_sync(0xffffffffu, hb, s0), h1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
+      const uint32_t l0 = __shfl_sync(0xffffffffu, lb, s0), l1 = __shfl_sync(0xffffffffu, lb, s0 + 1);
+      const uint32_t word = lane < 16 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
+      *reinterpret_cast<uint32_t*>(tile + t4_sw128_h(r, 2 * lane)) = word;
+    }
+    // extension box: lane writes columns 2*lane, 2*lane+1
+    __half e0 = zero, e1 = zero;
+    if (lane == 0) { e0 = __hneg(n1); e1 = one; }              // cols 0,1
+    else if (lane == 1) { e0 = __hneg(n2); e1 = __hneg(n3); }   // cols 2,3
+    else if (lane == 2) { e0 = one; e1 = one; }                // cols 4,5
+    else if (lane == 8) { e0 = one; e1 = __hneg(n1); }         // cols 16,17
+    else if (lane == 17) { e0 = one; e1 = one; }               // cols 34,35
+    else if (lane == 18) { e0 = __hneg(n2); e1 = __hneg(n3); }  // cols 36,37
+    *reinterpret_cast<__half2*>(tile + TC_BOX_BYTES + t4_sw128_h(r, 2 * lane)) = __halves2half2(e0, e1);
+  }
 }
 
 struct NNTc4Args {
   const uint8_t* img;                  // [B*2][NT] tile images
   int S, NT, B;
-  unsigned long long* rowpart;         // [B][NT column blocks][NT*128 rows]  packed (ordered value << 32 | ~column)
+  float* rowval;                       // [B][2*NT chunks][NT*128 rows]  max over the chunk's 64 columns of -d^2/2
+  uint8_t* rowgid;                     // same shape: which of the chunk's eight 8-column groups holds that maximum (first one)
   int32_t* nn10;                       // [B][S]
+  long long* trace;                    // TRACE instantiation only (ROREG_DEBUG_NN_TRACE=<file>): clock64 stamps [CTA][256 tiles][8 events]
 };
 
 __device__ __forceinline__ uint32_t t4_ord(float v) {            // monotone float -> uint
@@ -87,24 +121,55 @@ __device__ __forceinline__ void t4_bulk(uint32_t dst, const void* src, uint32_t 
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <int PASSES>
+// spin without reading the clock on the success path; a lost arrive still ends in a trap, never a hung GPU
+__device__ __forceinline__ void t4_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+// tcgen05.mma / commit issued by one elected lane of a converged warp
+__device__ __forceinline__ void t4_umma(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t accum) {
+  asm volatile("{\n.reg .pred p, e;\nelect.sync _|e, 0xffffffff;\nsetp.ne.b32 p, %4, 0;\n@e tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+               ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(T4_IDESC), "r"(accum) : "memory");
+}
+__device__ __forceinline__ void t4_commit(uint32_t bar) {
+  asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
+}
+
+// if (v > cmax) { cmax = v; byte `slot` of ctile = t; }   as FSETP + @p FADD (FMA pipe) + @p PRMT
+__device__ __forceinline__ void t4_col_update(float& cmax, uint32_t& ctile, float v, uint32_t t, int slot) {
+#define T4_CU(SEL) asm("{\n.reg .pred p;\nsetp.gt.f32 p, %2, %0;\n@p add.f32 %0, %2, 0f80000000;\n@p prmt.b32 %1, %1, %3, " #SEL ";\n}" \
+                       : "+f"(cmax), "+r"(ctile) : "f"(v), "r"(t))
+  switch (slot) {
+    case 0: T4_CU(0x3214); break;
+    case 1: T4_CU(0x3240); break;
+    case 2: T4_CU(0x3410); break;
+    default: T4_CU(0x4210); break;
+  }
+#undef T4_CU
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sB = smem;                                   // stationary tile (cloud 1 block), 48 KB
-  uint8_t* sA = smem + T4_TILE_BYTES;                   // T4_STAGES x 48 KB streaming tiles (cloud 0)
-  unsigned long long* mrg = reinterpret_cast<unsigned long long*>(smem + T4_TILE_BYTES * (1 + T4_STAGES));   // [128] row keys of the upper column half
-  unsigned long long* cmg = mrg + 128;                  // [2 halves][4 quadrants][64 columns] column candidates
+  uint8_t* sB = smem;                                   // stationary tile (cloud 1 block), 32 KB
+  uint8_t* sA = smem + T4_TILE_BYTES;                   // T4_STAGES x 32 KB streaming tiles (cloud 0)
+  unsigned long long* cmg = reinterpret_cast<unsigned long long*>(smem + T4_TILE_BYTES * (1 + T4_STAGES));   // [2 halves][4 quadrants][64 columns]
   uint64_t* bars = reinterpret_cast<uint64_t*>(cmg + 2 * 4 * 64);
-  // barriers: 0 b_full, 1 b_empty, 2..4 a_full, 5..7 a_empty, 8..11 tmem_full, 12..15 tmem_empty
+  // barriers: 0 b_full, 1 b_empty, 2..6 a_full, 7..11 a_empty, 12..13 tmem_full, 14..15 tmem_empty
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
     mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
-    for (int s = 0; s < T4_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(5 + s), 1); }
-    for (int s = 0; s < T4_ACC; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(12 + s), 256); }
+    for (int s = 0; s < T4_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(7 + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(12 + s), 1); mbar_init(BAR(14 + s), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -116,6 +181,8 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = tmem_base_s;
 
+  // unpredicated on purpose (see kernels_corr_tc2.cuh): event e of this CTA's i-th tile
+#define T4_TRACE(i, e) do { if (TRACE) a.trace[((size_t)blockIdx.x * 256 + ((i) < 255u ? (i) : 255u)) * 8 + (e)] = clock64(); } while (0)
   const int NT = a.NT;
   const int n_items = a.B * NT;                         // item = (pair, 128-column block of cloud 1)
 
@@ -132,39 +199,47 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
         b_phase ^= 1;
         for (int t = 0; t < NT; ++t, ++it_a) {
           const int st = it_a % T4_STAGES; const uint32_t ph = (it_a / T4_STAGES) & 1;
-          mbar_wait(BAR(5 + st), ph ^ 1);
+          t4_wait(BAR(7 + st), ph ^ 1);
+          T4_TRACE(it_a, 0);
           mbar_expect_tx(BAR(2 + st), T4_TILE_BYTES);
           t4_bulk(smem_u32(sA + st * T4_TILE_BYTES), imgA + (long long)t * T4_TILE_BYTES, T4_TILE_BYTES, BAR(2 + st));
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      uint32_t it_a = 0, it_t = 0, b_phase = 0;
-      const uint32_t bhi = smem_u32(sB), blo = bhi + TC_BOX_BYTES, bex = bhi + 2 * TC_BOX_BYTES + 32;   // column-role ext = logical columns 8..15
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        mbar_wait(BAR(0), b_phase); b_phase ^= 1;
-        for (int t = 0; t < NT; ++t, ++it_a, ++it_t) {
-          const int st = it_a % T4_STAGES; const uint32_t ph = (it_a / T4_STAGES) & 1;
-          const int acc = it_t % T4_ACC; const uint32_t tph = (it_t / T4_ACC) & 1;
-          mbar_wait(BAR(2 + st), ph);
-          mbar_wait(BAR(12 + acc), tph ^ 1);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t ahi = smem_u32(sA + st * T4_TILE_BYTES), alo = ahi + TC_BOX_BYTES, aex = ahi + 2 * TC_BOX_BYTES;
-          const uint32_t d_tmem = tmem_base + acc * TC_BN;
-          // the norm step first: it is the one that must never be dropped (passes < 3 is a debug knob)
-          umma_tf32(d_tmem, umma_desc_sw128(aex), umma_desc_sw128(bex), TC_IDESC, 0u);
-          const uint32_t aop[3] = {ahi, alo, ahi}, bop[3] = {bhi, bhi, blo};
-#pragma unroll
-          for (int c = 0; c < PASSES; ++c)                // compile-time count: no run-time predicate near the descriptor moves
-#pragma unroll
-            for (int kk = 0; kk < TC_KC / 8; ++kk)
-              umma_tf32(d_tmem, umma_desc_sw128(aop[c] + kk * 32), umma_desc_sw128(bop[c] + kk * 32), TC_IDESC, 1u);
-          umma_commit(BAR(5 + st));
-          umma_commit(BAR(8 + acc));
-        }
-        umma_commit(BAR(1));
+    // the whole warp walks the loop (no divergent region around the tcgen05 instructions), one elected lane issues
+    uint32_t it_a = 0, it_t = 0, b_phase = 0;
+    // descriptor low words (start address >> 4 | LBO field); the high word (SBO = 1024 B, version 1, SWIZZLE_128B) is a constant.
+    // column-role operands (stationary): hi at +0/+32, lo' at +64/+96 of box 0; extension vectors at +32 (D1) / +64 (D2) of box 1
+    constexpr uint64_t DHI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+    const uint32_t b0 = ((smem_u32(sB) >> 4) & 0x3FFF) | (1u << 16);
+    const uint32_t a00 = ((smem_u32(sA) >> 4) & 0x3FFF) | (1u << 16);
+    auto D = [&](uint32_t lo) -> uint64_t { return DHI | lo; };
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      t4_wait(BAR(0), b_phase); b_phase ^= 1;
+      for (int t = 0; t < NT; ++t, ++it_a, ++it_t) {
+        const int st = it_a % T4_STAGES; const uint32_t ph = (it_a / T4_STAGES) & 1;
+        const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+        t4_wait(BAR(2 + st), ph);
+        if (lane == 0) T4_TRACE(it_t, 1);
+        t4_wait(BAR(14 + acc), tph ^ 1);
+        if (lane == 0) T4_TRACE(it_t, 2);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a0 = a00 + st * (T4_TILE_BYTES >> 4);            // 16-byte units: hi +0/+2, lo' +4/+6, extension box +1024
+        const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
+        t4_umma(d1, D(a0 + 1024), D(b0 + 1024 + 2), 0u);                // -na1 - nb1
+        t4_umma(d1, D(a0), D(b0), 1u);                                  // hi.hi
+        t4_umma(d1, D(a0 + 2), D(b0 + 2), 1u);
+        t4_umma(d2, D(a0 + 1024), D(b0 + 1024 + 4), 0u);                // -(na2 + na3) - (nb2 + nb3)
+        t4_umma(d2, D(a0 + 4), D(b0), 1u);                              // lo'.hi
+        t4_umma(d2, D(a0 + 6), D(b0 + 2), 1u);
+        t4_umma(d2, D(a0), D(b0 + 4), 1u);                              // hi.lo'
+        t4_umma(d2, D(a0 + 2), D(b0 + 6), 1u);
+        t4_commit(BAR(7 + st));
+        t4_commit(BAR(12 + acc));
+        if (lane == 0) T4_TRACE(it_t, 3);
       }
+      t4_commit(BAR(1));
     }
   } else {
     // ===================== epilogue: 8 warps, warp -> (lane quadrant q, column half hf) =====================
@@ -180,41 +255,48 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
       for (int e = 0; e < 64; ++e) cmax[e] = -INFINITY;
 #pragma unroll
       for (int e = 0; e < 16; ++e) ctile[e] = 0;
-      unsigned long long* rp = a.rowpart + ((long long)p * NT + j) * Sp;
+      float* rv = a.rowval + ((long long)p * 2 * NT + 2 * j + hf) * Sp;
+      uint8_t* rg = a.rowgid + ((long long)p * 2 * NT + 2 * j + hf) * Sp;
       for (int t = 0; t < NT; ++t, ++it_t) {
-        const int acc = it_t % T4_ACC; const uint32_t tph = (it_t / T4_ACC) & 1;
-        mbar_wait(BAR(8 + acc), tph);
+        const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
+        t4_wait(BAR(12 + acc), tph);
+        if (threadIdx.x == 64) T4_TRACE(it_t, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * TC_BN + hf * 64;
-        uint32_t r[64];
-        RR_TMEM_LD32(r, taddr);
-        { uint32_t* r2 = r + 32; RR_TMEM_LD32(r2, taddr + 32); }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        mbar_arrive(BAR(12 + acc));                     // accumulator free: the MMA of tile t+4 may start
-        // column direction: running maximum of -d^2/2 over the rows this lane sees; strict '>' + increasing t = first row wins ties
-        float m0 = -INFINITY, m1 = -INFINITY;
+        const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + hf * 64;
+        float g8[8];                                    // maxima of the eight 8-column groups of this thread's 64 columns
 #pragma unroll
-        for (int e = 0; e < 64; ++e) {
-          const float v = __uint_as_float(r[e]);
-          if (v > cmax[e]) ctile[e >> 2] = __byte_perm(ctile[e >> 2], (uint32_t)t, (0x3210 & ~(0xF << (4 * (e & 3)))) | (4 << (4 * (e & 3))));
-          cmax[e] = fmaxf(cmax[e], v);
-          if (e & 1) m1 = fmaxf(m1, v); else m0 = fmaxf(m0, v);
-        }
-        const float m = fmaxf(m0, m1);
-        // row direction: first column attaining the tile-row maximum
-        int j4[4] = {64, 64, 64, 64};                   // four independent select chains (e mod 4), merged by min
+        for (int k = 0; k < 8; ++k) g8[k] = -INFINITY;
 #pragma unroll
-        for (int e = 63; e >= 0; --e) if (__uint_as_float(r[e]) == m) j4[e & 3] = e;
-        const int jj = min(min(j4[0], j4[1]), min(j4[2], j4[3]));
-        const unsigned long long key = ((unsigned long long)t4_ord(m) << 32) | (0xffffffffu - (uint32_t)(j * TC_BN + hf * 64 + jj));
-        if (hf == 1) mrg[row_in_tile] = key;
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
-        if (hf == 0) {
-          const unsigned long long o = mrg[row_in_tile];
-          rp[t * TC_BM + row_in_tile] = o > key ? o : key;       // equal values: the larger key is the smaller column
+        for (int half = 0; half < 2; ++half) {
+          uint32_t r1[32], r2[32];
+          RR_TMEM_LD32(r1, taddr + half * 32);
+          RR_TMEM_LD32(r2, taddr + 128 + half * 32);
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (half == 1) {
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            mbar_arrive(BAR(14 + acc));                 // accumulators free: the MMAs of tile t+2 may start
+            if (threadIdx.x == 64) T4_TRACE(it_t, 5);
+          }
+          // column direction: running maximum of -d^2/2 over the rows this lane sees; strict '>' + increasing t = first row wins ties.
+          // FSETP and PRMT issue on the half-rate ALU pipe, the predicated move is an FADD with -0 so that it goes to the FMA pipe:
+          // 2.5 ALU instructions per element in total (with the FMNMX3 of the row direction).
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const int e = half * 32 + u;
+            const float v = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
+            t4_col_update(cmax[e], ctile[e >> 2], v, (uint32_t)t, e & 3);
+            g8[e >> 3] = fmaxf(g8[e >> 3], v);
+          }
         }
-        asm volatile("bar.sync %0, 64;" ::"r"(2 + q) : "memory");
+        if (threadIdx.x == 64) T4_TRACE(it_t, 6);
+        // row direction: only the chunk maximum and the first 8-column group attaining it; the index is resolved by nn_tc4_resolve_kernel
+        const float m = fmaxf(fmaxf(fmaxf(g8[0], g8[1]), fmaxf(g8[2], g8[3])), fmaxf(fmaxf(g8[4], g8[5]), fmaxf(g8[6], g8[7])));
+        int gid = 7;
+#pragma unroll
+        for (int k = 6; k >= 0; --k) if (g8[k] == m) gid = k;
+        rv[t * TC_BM + row_in_tile] = m;
+        rg[t * TC_BM + row_in_tile] = (uint8_t)gid;
+        if (threadIdx.x == 64) T4_TRACE(it_t, 7);
       }
       // ---- end of the sweep: reduce the column candidates over the 128 lanes -------------------------------
       // lexicographic (largest value, smallest row); row = tile * 128 + row_in_tile
@@ -249,48 +331,112 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
-// ---- finish: nn01[p][row] = column of the best key over the NT column blocks ---------------------------------
-__global__ void __launch_bounds__(256) nn_tc4_finish_kernel(const unsigned long long* __restrict__ rowpart, int S, int NT, int B,
-                                                            int32_t* __restrict__ nn01) {
+// ---- finish A: best 64-column chunk of every row (first chunk on equal values) -> its first maximal 8-column group ------
+__global__ void __launch_bounds__(256) nn_tc4_best_group_kernel(const float* __restrict__ rowval, const uint8_t* __restrict__ rowgid,
+                                                                int S, int NT, int B, int32_t* __restrict__ best_group) {
   const long long i = blockIdx.x * 256LL + threadIdx.x;
   if (i >= (long long)B * S) return;
   const int p = (int)(i / S), row = (int)(i % S);
   const long long Sp = (long long)NT * TC_BM;
-  const unsigned long long* rp = rowpart + (long long)p * NT * Sp + row;
-  unsigned long long best = 0;
-  for (int j = 0; j < NT; ++j) { const unsigned long long c = rp[j * Sp]; best = c > best ? c : best; }
-  nn01[i] = (int32_t)(0xffffffffu - (uint32_t)(best & 0xffffffffull));
+  const float* rv = rowval + (long long)p * 2 * NT * Sp + row;
+  float best = -INFINITY; int bc = 0;
+  for (int c = 0; c < 2 * NT; ++c) { const float v = rv[c * Sp]; if (v > best) { best = v; bc = c; } }
+  best_group[i] = bc * 8 + rowgid[(long long)p * 2 * NT * Sp + bc * Sp + row];
+}
+
+// ---- finish B: exact index inside the winning 8-column group, in the reference's arithmetic ------------------------
+// d = sqrt(sum_f (a_f - b_f)^2 + 1e-7) accumulated f = 0..31 with FMA, lexicographic (d, index) minimum = torch's
+// dist.min(dim) on utils/knn_search.py:33-38's values (the same arithmetic as nn mode 0 / nn_diff_kernel).
+// One thread per (row, candidate column): 8 consecutive lanes resolve one row.
+__global__ void __launch_bounds__(256) nn_tc4_resolve_kernel(const float* __restrict__ inv, const int32_t* __restrict__ best_group,
+                                                             int S, int B, int32_t* __restrict__ nn01) {
+  const long long gt = blockIdx.x * 256LL + threadIdx.x;
+  const long long i = gt >> 3; const int cnd = (int)(gt & 7);
+  const bool live = i < (long long)B * S;                 // B * S is not always a multiple of 32: keep the shuffles warp-uniform
+  float s = INFINITY; int col = 0x7fffffff;
+  if (live) {
+    const int p = (int)(i / S), row = (int)(i % S);
+    col = best_group[i] * 8 + cnd;
+    if (col < S) {
+      const float4* a4 = reinterpret_cast<const float4*>(inv + ((long long)(p * 2) * S + row) * 32);
+      const float4* b4 = reinterpret_cast<const float4*>(inv + ((long long)(p * 2 + 1) * S + col) * 32);
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float4 av = __ldg(a4 + k), bv = __ldg(b4 + k);
+        float d;
+        d = av.x - bv.x; acc = fmaf(d, d, acc);
+        d = av.y - bv.y; acc = fmaf(d, d, acc);
+        d = av.z - bv.z; acc = fmaf(d, d, acc);
+        d = av.w - bv.w; acc = fmaf(d, d, acc);
+      }
+      s = sqrtf(acc + 1e-7f);
+    }
+  }
+#pragma unroll
+  for (int o = 4; o > 0; o >>= 1) {
+    const float so = __shfl_xor_sync(0xffffffffu, s, o);
+    const int co = __shfl_xor_sync(0xffffffffu, col, o);
+    if (so < s || (so == s && co < col)) { s = so; col = co; }
+  }
+  if (live && cnd == 0) nn01[i] = col;
 }
 
 static inline size_t nn_tc4_workspace_bytes(int B, int S) {
   const size_t NT = (size_t)(S + TC_BM - 1) / TC_BM;
-  return rr_align((size_t)B * 2 * NT * T4_TILE_BYTES) + rr_align(sizeof(unsigned long long) * (size_t)B * NT * NT * TC_BM) + 2048;
+  return rr_align((size_t)B * 2 * NT * T4_TILE_BYTES) + rr_align(sizeof(float) * (size_t)B * 2 * NT * NT * TC_BM) +
+         rr_align((size_t)B * 2 * NT * NT * TC_BM) + rr_align(sizeof(int32_t) * (size_t)B * S) + 4096;
 }
 
-// inv: [B][2][S][32] pooled features; img / rowpart: workspace of nn_tc4_workspace_bytes(B, S)
-static inline int nn_tc4_launch_both(roreg_ctx* c, const float* inv, int S, int B, uint8_t* img, unsigned long long* rowpart,
+// inv: [B][2][S][32] pooled features; img / rowval / rowgid / best_group: workspace of nn_tc4_workspace_bytes(B, S)
+static inline int nn_tc4_launch_both(roreg_ctx* c, const float* inv, int S, int B, uint8_t* img, float* rowval, uint8_t* rowgid, int32_t* best_group,
                                      int32_t* nn01, int32_t* nn10, cudaStream_t st) {
   const int NT = (S + TC_BM - 1) / TC_BM;
   RR_ARG(c, NT <= 256);                                  // tile indices of the column direction are kept as bytes
   RR_ARG(c, (reinterpret_cast<uintptr_t>(img) & 1023) == 0);
   const long long total_rows = (long long)B * 2 * NT * TC_BM;
-  nn_tc4_prep_kernel<<<(unsigned)((total_rows + 7) / 8), 256, 0, st>>>(inv, S, NT, total_rows, img);
+  nn_tc4_prep_kernel<<<(unsigned)((total_rows / 4 + 7) / 8), 256, 0, st>>>(inv, S, NT, total_rows, img);
   RR_LAUNCH_CHECK(c);
-  static int passes = 0;
-  if (!passes) {
-    RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
-    passes = 3;
-    if (const char* e = getenv("ROREG_DEBUG_NN_PASSES")) if (atoi(e) == 1) passes = 1;      // bottleneck experiments only
+  static bool attr_set = false;
+  if (!attr_set) {
+    RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
+    attr_set = true;
   }
   const int items = B * NT;
   const int grid = items < c->sm_count ? items : c->sm_count;
-  NNTc4Args a{img, S, NT, B, rowpart, nn10};
-  if (passes == 1) nn_tc4_kernel<1><<<grid, T4_THREADS, T4_SMEM_BYTES, st>>>(a);
-  else nn_tc4_kernel<3><<<grid, T4_THREADS, T4_SMEM_BYTES, st>>>(a);
-  RR_LAUNCH_CHECK(c);
+  NNTc4Args a{img, S, NT, B, rowval, rowgid, nn10, nullptr};
+  const char* trace_fn = getenv("ROREG_DEBUG_NN_TRACE");
+  static bool traced = false;
+  if (trace_fn && !traced && items >= 1000) {            // one-off timeline dump of CTA 0 (debug only; synchronises)
+    traced = true;
+    const size_t nb = (size_t)grid * 256 * 8 * sizeof(long long);
+    RR_CUDA(c, cudaMalloc(&a.trace, nb));
+    RR_CUDA(c, cudaMemsetAsync(a.trace, 0, nb, st));
+    nn_tc4_kernel<true><<<grid, T4_THREADS, T4_SMEM_BYTES, st>>>(a);
+    RR_LAUNCH_CHECK(c);
+    RR_CUDA(c, cudaStreamSynchronize(st));
+    long long* h = (long long*)malloc(256 * 8 * sizeof(long long));
+    RR_CUDA(c, cudaMemcpy(h, a.trace, 256 * 8 * sizeof(long long), cudaMemcpyDeviceToHost));
+    if (FILE* f = fopen(trace_fn, "w")) {
+      fprintf(f, "# tile P_issue M_afull M_accfree M_committed E_full E_loaded E_math E_end (clock64 - first)\n");
+      const long long t0 = h[0];
+      for (int i = 0; i < 255; ++i) {
+        fprintf(f, "%d", i);
+        for (int e = 0; e < 8; ++e) fprintf(f, " %lld", h[i * 8 + e] ? h[i * 8 + e] - t0 : -1);
+        fprintf(f, "\n");
+      }
+      fclose(f);
+    }
+    free(h); cudaFree(a.trace);
+  } else {
+    nn_tc4_kernel<false><<<grid, T4_THREADS, T4_SMEM_BYTES, st>>>(a);
+    RR_LAUNCH_CHECK(c);
+  }
   const long long n = (long long)B * S;
-  nn_tc4_finish_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowpart, S, NT, B, nn01);
+  nn_tc4_best_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(rowval, rowgid, S, NT, B, best_group);
+  RR_LAUNCH_CHECK(c);
+  nn_tc4_resolve_kernel<<<(unsigned)((n * 8 + 255) / 256), 256, 0, st>>>(inv, best_group, S, B, nn01);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

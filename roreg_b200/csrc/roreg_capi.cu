@@ -7,6 +7,7 @@
 #include "kernels_corr_tc.cuh"
 #include "kernels_corr_tc2.cuh"
 #include "kernels_nn_tc4.cuh"
+#include "kernels_corr_tc3.cuh"
 #include "kernels_gemm_tc.cuh"
 #include "kernels_gconv.cuh"
 #include "kernels_matchot.cuh"
@@ -69,7 +70,7 @@ int roreg_ctx_destroy(roreg_ctx* c) {
 }
 
 int roreg_set_corr_mode(roreg_ctx* c, int mode) {
-  RR_ARG(c, mode >= 0 && mode <= 2);
+  RR_ARG(c, mode >= 0 && mode <= 3);
   c->corr_mode = mode;
   return ROREG_OK;
 }
@@ -148,10 +149,12 @@ int roreg_mutual_match(roreg_ctx* c, const float* f0, int n0, const float* f1, i
     const size_t NT = (size_t)(n0 + TC_BM - 1) / TC_BM;
     ar.off = (ar.off + 1023) & ~size_t(1023);
     uint8_t* img = ar.take<uint8_t>(2 * NT * T4_TILE_BYTES);
-    unsigned long long* rowpart = ar.take<unsigned long long>(NT * NT * TC_BM);
+    float* rowval = ar.take<float>(2 * NT * NT * TC_BM);
+    uint8_t* rowgid = ar.take<uint8_t>(2 * NT * NT * TC_BM);
+    int32_t* bchunk = ar.take<int32_t>((size_t)n0);
     RR_CUDA(c, cudaMemcpyAsync(inv2, f0, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
     RR_CUDA(c, cudaMemcpyAsync(inv2 + (size_t)n0 * RR_F, f1, sizeof(float) * (size_t)n0 * RR_F, cudaMemcpyDeviceToDevice, st));
-    if ((rc = nn_tc4_launch_both(c, inv2, n0, 1, img, rowpart, w01, w10, st))) return rc;
+    if ((rc = nn_tc4_launch_both(c, inv2, n0, 1, img, rowval, rowgid, bchunk, w01, w10, st))) return rc;
   } else if (mode >= 1) {
     float* inv2 = ar.take<float>(2 * (size_t)n0 * RR_F);
     float* Ahat = ar.take<float>(2 * (size_t)n0 * TC_KEXT);
@@ -179,7 +182,8 @@ int roreg_group_corr(roreg_ctx* c, const float* X, const int32_t* idxX, const fl
   if (K == 0) return ROREG_OK;
   if (c->corr_mode >= 1) {
     CorrTcArgs t{nullptr, nullptr, idxX, idxY, 1, nullptr, 0, nullptr, K, 1, (variant == 1) ? c->d_perm8 : c->d_permT8, cor_out, argmax_out, 3, 0, nullptr};
-    return c->corr_mode == 2 ? group_corr_tc2_launch(c, X, Y, t, (cudaStream_t)stream)
+    return c->corr_mode == 3 ? group_corr_tc3_launch(c, X, Y, t, (cudaStream_t)stream)
+         : c->corr_mode == 2 ? group_corr_tc2_launch(c, X, Y, t, (cudaStream_t)stream)
                              : group_corr_tc_launch(c, X, Y, t, (cudaStream_t)stream);   // indices are trusted
   }
   CorrArgs a{};
@@ -540,8 +544,10 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     const size_t NT = (size_t)(S + TC_BM - 1) / TC_BM;
     ar.off = (ar.off + 1023) & ~size_t(1023);
     uint8_t* img = ar.take<uint8_t>((size_t)B * 2 * NT * T4_TILE_BYTES);
-    unsigned long long* rowpart = ar.take<unsigned long long>((size_t)B * NT * NT * TC_BM);
-    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowpart, nn01, nn10, st))) return rc;
+    float* rowval = ar.take<float>((size_t)B * 2 * NT * NT * TC_BM);
+    uint8_t* rowgid = ar.take<uint8_t>((size_t)B * 2 * NT * NT * TC_BM);
+    int32_t* bchunk = ar.take<int32_t>((size_t)B * S);
+    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowval, rowgid, bchunk, nn01, nn10, st))) return rc;
   } else if (b->nn_mode >= 1) {
     float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
@@ -569,7 +575,7 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     CorrTcArgs t{nullptr, nullptr, b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index, 3, 0, nullptr};
     if (const char* e = getenv("ROREG_DEBUG_CORR_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) t.dbg_passes = v; }
     if (const char* e = getenv("ROREG_DEBUG_CORR_SKIP")) t.dbg_skip = atoi(e);
-    if ((rc = (c->corr_mode == 2 ? group_corr_tc2_launch(c, b->desc, b->desc, t, st) : group_corr_tc_launch(c, b->desc, b->desc, t, st)))) return rc;
+    if ((rc = (c->corr_mode == 3 ? group_corr_tc3_launch(c, b->desc, b->desc, t, st) : c->corr_mode == 2 ? group_corr_tc2_launch(c, b->desc, b->desc, t, st) : group_corr_tc_launch(c, b->desc, b->desc, t, st)))) return rc;
   } else {
     const long long total = (long long)B * S;
     const int grid = (int)(total < (long long)c->sm_count * 8 ? total : (long long)c->sm_count * 8);

@@ -83,7 +83,67 @@ __global__ void __launch_bounds__(192, 1) gather_kernel(const float* __restrict_
   }
 }
 
-int main() {
+// L2-resident tile stream (the nn mode-4 pattern): groups of `share` CTAs stream the same 40 x tile_bytes image again and again.
+__global__ void __launch_bounds__(64, 1) stream_kernel(const uint8_t* __restrict__ img, int tile_bytes, int n_tiles, int reps, int share, int stages, int split) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ __align__(8) uint64_t bars[16];
+  const uint32_t bar0 = smem_u32(bars);
+  auto FULL = [&](int s) { return bar0 + 8u * s; };
+  auto FREE = [&](int s) { return bar0 + 8u * (8 + s); };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 8; ++s) { mbar_init(FULL(s), 1); mbar_init(FREE(s), 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const uint8_t* base = img + (size_t)(blockIdx.x / share) * n_tiles * tile_bytes;
+  const int total = n_tiles * reps;
+  if (threadIdx.x == 0) {
+    for (int it = 0; it < total; ++it) {
+      const int st = it % stages; const uint32_t ph = (it / stages) & 1;
+      mbar_wait(FREE(st), ph ^ 1);
+      mbar_expect_tx(FULL(st), tile_bytes);
+      const uint8_t* src = base + (size_t)(it % n_tiles) * tile_bytes;
+      const int piece = tile_bytes / split;
+      for (int k = 0; k < split; ++k) bulk_load_1d(smem_u32(smem + st * tile_bytes + k * piece), src + k * piece, piece, FULL(st));
+    }
+  } else if (threadIdx.x == 32) {
+    for (int it = 0; it < total; ++it) {
+      const int st = it % stages; const uint32_t ph = (it / stages) & 1;
+      mbar_wait(FULL(st), ph);
+      mbar_arrive(FREE(st));
+    }
+  }
+}
+
+static void run_stream(int sms) {
+  const int n_tiles = 40, reps = 20;
+  uint8_t* img; cudaMalloc(&img, (size_t)148 * n_tiles * 49152); cudaMemset(img, 1, (size_t)148 * n_tiles * 49152);
+  cudaFuncSetAttribute(stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  const int tbs[2] = {32768, 16384};
+  for (int tb : tbs)
+    for (int share : {1, 8, 40, 148})
+      for (int stages : {3, 5})
+        for (int split : {1, 4}) {
+          if (stages * tb > 196608) continue;
+          cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+          const size_t sm = (size_t)stages * tb + 1024;
+          stream_kernel<<<sms, 64, sm>>>(img, tb, n_tiles, 2, share, stages, split);
+          cudaEventRecord(e0);
+          stream_kernel<<<sms, 64, sm>>>(img, tb, n_tiles, reps, share, stages, split);
+          cudaEventRecord(e1);
+          cudaError_t e = cudaDeviceSynchronize();
+          if (e != cudaSuccess) { printf("FAILED: %s\n", cudaGetErrorString(e)); exit(1); }
+          float ms; cudaEventElapsedTime(&ms, e0, e1);
+          const double bytes = (double)sms * n_tiles * reps * tb;
+          printf("stream tile %5d B  share %3d CTAs/image  stages %d  copies/tile %d : %.3f ms  %.0f GB/s  %.1f B/clk/SM (at 1.965 GHz)\n", tb, share, stages,
+                 split, ms, bytes / ms / 1e6, bytes / ms / 1e6 / sms / 1.965);
+        }
+  cudaFree(img);
+}
+
+int main(int argc, char** argv) {
+  if (argc > 1 && argv[1][0] == 's') { cudaDeviceProp p; cudaGetDeviceProperties(&p, 0); run_stream(p.multiProcessorCount); return 0; }
   cudaDeviceProp p; cudaGetDeviceProperties(&p, 0);
   const int sms = p.multiProcessorCount;
   const int B = 32, n = 5000, K = 3400;

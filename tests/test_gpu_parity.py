@@ -375,7 +375,7 @@ def test_register_batch_tensor_core_nn(ctx, tables, mode):
 
 
 # ---------------------------------------------------------------------------------------- corr modes 1, 2 (tcgen05)
-@pytest.fixture(scope="module", params=[1, 2], ids=["corr1", "corr2"])
+@pytest.fixture(scope="module", params=[1, 2, 3], ids=["corr1", "corr2", "corr3"])
 def ctx_tc(request):
     from roreg_b200 import ops
     c = ops.Context(0)
@@ -384,10 +384,10 @@ def ctx_tc(request):
     c.close()
 
 
-@pytest.mark.parametrize("variant,K", [(1, 500), (2, 501), (1, 1), (1, 2), (2, 3)])
+@pytest.mark.parametrize("variant,K", [(1, 500), (2, 501), (1, 1), (1, 2), (2, 3), (1, 4001)])
 def test_group_corr_tensor_core_mode(ctx_tc, pair, tables, variant, K):
     """tcgen05 Gram (MN-major operands straight from HBM, 3xTF32 split in shared memory): values to 1e-5 of the
-    float64 restatement, argmax equal wherever the float64 top-2 gap is clear; odd / tiny K exercise the tail slot."""
+    float64 restatement, argmax equal wherever the float64 top-2 gap is clear; odd / tiny K exercise the tail slot, K = 4001 gives every persistent CTA a dozen pipeline items (buffer re-use, barrier phases)."""
     rng = np.random.default_rng(40 + K)
     ix = rng.integers(0, 1200, K).astype(np.int32); iy = rng.integers(0, 1200, K).astype(np.int32)
     X = pair["feats1"]; Y = pair["feats0"]
