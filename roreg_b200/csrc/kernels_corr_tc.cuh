@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(CtThreads<CW>::value, 1) group_corr_tc_kernel(
   constexpr int CT_THREADS = CtThreads<CW>::value;
   constexpr int CONV_THREADS = 32 * CW;
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles0 = smem + CT_STAGES * CT_RAW_BYTES;                                       // 2 x (Xhi | Xlo | Yhi | Ylo)
   float* Gs = reinterpret_cast<float*>(tiles0 + CT_TILES_BYTES);                           // [2][60 g][64 h]
   uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + CT_GS_BYTES;                            // 3600 B

@@ -35,7 +35,7 @@ constexpr uint32_t C2_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(6
 template <bool TRACE, int PASSES>
 __global__ void __launch_bounds__(C2_THREADS, 2) group_corr_tc2_kernel(CorrTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* tiles = smem + C2_STAGES * C2_RAW_BYTES;                                        // 45 KB: 1024-aligned
   float* Gs = reinterpret_cast<float*>(tiles + C2_TILES_BYTES);                            // [60 g][64 h]
   uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + C2_GS_BYTES;                            // 3600 B

@@ -5,8 +5,8 @@
 // landed rows are written (15 KB) and re-read (15 KB) by the convert stage, the 3xTF32 operand tiles are written
 // (32 KB) and read by 12 tf32 MMAs (48 KB), and the 60x60 Gram goes through shared memory once more (30 KB) for the
 // generalised-diagonal sums: ~140-165 KB per match against 128 B/clk.  Mode 3 removes what can be removed:
-//   * no landing buffers: loader warps LDG a descriptor row straight into registers (15 x 16 B per lane, 12 warps =
-//     90 KB in flight per SM) and write the operands from there;
+//   * no landing buffers: loader warps LDG a descriptor row straight into registers (15 x 16 B per lane, 11 warps =
+//     82 KB in flight per SM) and write the operands from there;
 //   * float16 two-accumulator arithmetic (see kernels_nn_tc4.cuh): x = hi + 2^-11 lo', D1 = Xhi.Yhi,
 //     D2 = Xlo'.Yhi + Xhi.Ylo', G = D1 + 2^-11 D2 - float32-class products, but the operand tiles are half the bytes
 //     (16 KB per match) and the contraction is 6 kind::f16 MMAs per TWO matches (24 KB of operand reads per match);
@@ -17,9 +17,9 @@
 //     matches stacked along M (resp. N).
 // Shared-memory traffic per match: 16 KB (operand writes) + 24 KB (MMA reads) + 30 KB (Gram transpose) = 70 KB.
 //
-//   warps 0-11   loaders    3 groups (one tile set each) x {X m0, X m1, Y m0, Y m1}: LDG row -> regs -> fp16 hi / lo' -> STS.64
-//   warps 12-15  epilogue   tcgen05.ld D1, D2 -> FFMA combine -> smem transpose -> 60 generalised-diagonal sums -> argmax
-//   warp 16      MMA        6 x tcgen05.mma kind::f16 (M = N = 128, K = 16, A/B MN-major), 2 x (D1 | D2) in TMEM
+//   warps 0-10   loaders    a pool over the row tasks {X m0, X m1, Y m0, Y m1} of every item: LDG row -> regs -> fp16 hi / lo' -> STS.64
+//   warp 11      MMA        6 x tcgen05.mma kind::f16 (M = N = 128, K = 16, A/B MN-major), 2 x (D1 | D2) in TMEM
+//   warps 12-19  epilogue   (two sets of 4 warps alternating over the items)  tcgen05.ld D1, D2 -> FFMA combine -> smem transpose -> 60 generalised-diagonal sums -> argmax
 #pragma once
 #include <cuda_fp16.h>
 #include "kernels_corr_tc.cuh"
@@ -27,12 +27,13 @@
 
 namespace roreg {
 
-constexpr int C3_GROUPS = 3;
-constexpr int C3_THREADS = (4 * C3_GROUPS + 4 + 1) * 32;  // 544
+constexpr int C3_GROUPS = 3;                              // operand-tile sets (items in flight between the loaders and the tensor pipe)
+constexpr int C3_LOADERS = 11;                            // loader warps: a pool that takes the (item, row) tasks round-robin
+constexpr int C3_THREADS = (C3_LOADERS + 1 + 8) * 32;     // 640: 11 loader warps, the MMA warp, two epilogue sets of 4 warps
 constexpr int C3_OP_BYTES = 32 * 128;                     // one match's operand tile: 32 f-rows x 64 h fp16 = 4 KB
 constexpr int C3_BUF_BYTES = 8 * C3_OP_BYTES;             // Xhi m0|m1, Xlo m0|m1, Yhi m0|m1, Ylo m0|m1 = 32 KB
-constexpr int C3_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h]
-constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + C3_GS_BYTES + 3600 + 16 + 256 + 1024;   // 134 KB
+constexpr int C3_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h], one per epilogue set
+constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + 2 * C3_GS_BYTES + 3600 + 32 + 256 + 1024;   // 165 KB
 // kind::f16, A and B MN-major, D = f32, M = N = 128
 constexpr uint32_t C3_IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // MN-major SWIZZLE_128B descriptor: LBO = 4096 B, SBO = 1024 B, version 1, layout type 2
@@ -64,15 +65,15 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 template <bool TRACE>
 __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                                    // one 32 KB operand-tile set per loader group
-  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                           // [2][60 g][64 h]
-  uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + C3_GS_BYTES;                            // 3600 B
-  float* red_v = reinterpret_cast<float*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_v + 2);   // [2] each
-  uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(tabs + 3600 + 16) + 7) & ~uintptr_t(7));
-  // barriers: 0..2 conv_done[grp], 3..5 tiles_free[grp], 6..7 mma_done[acc], 8..9 acc_free[acc].
-  // A loader group owns one tile set: every waiter then only ever distinguishes ADJACENT phases of a barrier (run 34: with
-  // three groups sharing two tile sets a group could run two phases ahead of tiles_free and pass the parity test early).
+  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [2 epilogue sets][2 matches][60 g][64 h]
+  uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + 2 * C3_GS_BYTES;                        // 3600 B
+  uint32_t* red_k = reinterpret_cast<uint32_t*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_k + 4);   // [2 sets][2 matches] each
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_i + 4);                                 // 8-byte aligned: every size above is a multiple of 8
+  // barriers: 0..2 conv_done[set], 3..5 tiles_free[set], 6..7 mma_done[acc], 8..9 acc_free[acc].
+  // Every waiter must only ever have to distinguish ADJACENT phases of a barrier (run 34: with three loader groups sharing
+  // two tile sets a group ran two phases ahead of tiles_free and passed the parity test early -> deadlock).
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(6 + s), 1); mbar_init(BAR(8 + s), 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 16) {
+  if (warp == C3_LOADERS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -99,63 +100,69 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   // timeline instrumentation (TRACE instantiation only, unpredicated stores - see kernels_corr_tc2.cuh): event e of this CTA's i-th live item
 #define C3_TRACE(i, e) do { if (TRACE) a.trace[((size_t)blockIdx.x * 256 + ((i) < 255u ? (i) : 255u)) * 12 + (e)] = clock64(); } while (0)
   const int items_per_pair = (a.K + 1) / 2;
-  const long long n_items = (long long)a.B * items_per_pair;
-  // every role walks the same item sequence and skips the same items (device-side match counts)
-  auto item_count = [&](long long item, int& p, int& k0) -> int {
-    p = (int)(item / items_per_pair); k0 = (int)(item % items_per_pair) * 2;
-    const int cnt = a.n_matches ? a.n_matches[p] : a.K;
-    return cnt - k0;                                   // <= 0: nothing, 1: one match, >= 2: two matches
+  const int n_items = a.B * items_per_pair;            // < 2^31 (checked by the launcher): 32-bit divisions only
+  // every role walks the same item sequence (item = blockIdx.x + i * gridDim.x -> pair p, first match k0 = 2 j) and skips the
+  // same items (device-side match counts); the walk carries (p, j) along so that the loops contain no division
+  const int step_p = (int)gridDim.x / items_per_pair, step_j = (int)gridDim.x % items_per_pair;
+  struct Walk { int item, p, j; };
+  auto walk_begin = [&]() -> Walk { return Walk{(int)blockIdx.x, (int)blockIdx.x / items_per_pair, (int)blockIdx.x % items_per_pair}; };
+  auto walk_next = [&](Walk& w) { w.item += gridDim.x; w.p += step_p; w.j += step_j; if (w.j >= items_per_pair) { w.j -= items_per_pair; ++w.p; } };
+  auto walk_avail = [&](const Walk& w) -> int {        // <= 0: nothing, 1: one match, >= 2: two matches
+    return (a.n_matches ? a.n_matches[w.p] : a.K) - 2 * w.j;
   };
 
-  if (warp < 4 * C3_GROUPS) {
+  if (warp < C3_LOADERS) {
     // ===================== loaders =====================
-    const int grp = warp >> 2, role = warp & 3;        // role: 0 X m0, 1 X m1, 2 Y m0, 3 Y m1
-    const int isY = role >> 1, m = role & 1;
-    // byte offset of this lane's j-th float4 (flat element e = (32 j + lane) * 4 -> f = e / 60, h = e % 60) inside a tile
-    int off[15];
-#pragma unroll
-    for (int j = 0; j < 15; ++j) {
-      const int e = (j * 32 + lane) * 4, f = e / 60, h = e % 60;
-      off[j] = (f >> 3) * 1024 + (f & 7) * 128 + ((((h * 2) >> 4) ^ (f & 7)) << 4) + ((h * 2) & 15);
-    }
-    const float* base = isY ? a.Y : a.X;
-    const int32_t* idx = isY ? a.idxY : a.idxX;
-    // row of this warp's (side, slot) for an item; the odd tail's second slot re-reads the first match
-    auto row_ptr = [&](int p, int k0, int avail) -> const float4* {
+    // Row task T = 4 * (live item index) + role, role: 0 X m0, 1 X m1, 2 Y m0, 3 Y m1; warp w takes the tasks T = w (mod 11).
+    // A warp's successive items are 2-3 apart and the MMAs retire in item order, so when it waits for tiles_free of item L
+    // (the MMAs of item L-3) the barrier is at most one phase behind - the parity test stays unambiguous.
+    // row of a (side, slot) for an item; the odd tail's second slot re-reads the first match
+    auto row_ptr = [&](int p, int k0, int avail, int role) -> const float4* {
+      const int isY = role >> 1, m = role & 1;
       const int k = k0 + ((m < avail) ? m : 0);
       const long long w = (long long)p * a.K + k;
+      const int32_t* idx = isY ? a.idxY : a.idxX;
       long long r = idx ? idx[w * a.idx_stride] : k;
       if (a.pair_cloud) r += (long long)a.pair_cloud[2 * p + (isY ? 0 : 1)] * a.n;
-      return reinterpret_cast<const float4*>(base + r * RR_ROW);
+      return reinterpret_cast<const float4*>((isY ? a.Y : a.X) + r * RR_ROW);
     };
-    // walk to this group's next live item
-    long long item = blockIdx.x; uint32_t live = 0;    // `live` = index of the next live item of this CTA
-    const float4* next = nullptr; uint32_t next_it = 0;
+    Walk wk = walk_begin(); uint32_t live = 0;         // `live` = index of the next live item of this CTA
+    int role_next = warp;                              // (warp - 4 * live) mod 11, kept incrementally
+    const float4* next = nullptr; uint32_t next_it = 0; int next_role = 0;
     auto advance = [&]() {
       next = nullptr;
-      for (; item < n_items; item += gridDim.x) {
-        int p, k0; const int avail = item_count(item, p, k0);
+      for (; wk.item < n_items; walk_next(wk)) {
+        const int avail = walk_avail(wk);
         if (avail <= 0) continue;
         const uint32_t my = live++;
-        if ((int)(my % C3_GROUPS) == grp) { next = row_ptr(p, k0, avail); next_it = my; item += gridDim.x; return; }
+        const int role = role_next;
+        role_next = role_next >= 4 ? role_next - 4 : role_next + C3_LOADERS - 4;
+        if (role < 4) { next = row_ptr(wk.p, 2 * wk.j, avail, role); next_it = my; next_role = role; walk_next(wk); return; }
       }
     };
     advance();
     while (next) {
-      const float4* src = next; const uint32_t it = next_it;
-      float4 v[15];
+      const float4* src = next; const uint32_t it = next_it; const int role = next_role;
+      // lanes 0..14 take the 15 float4 of descriptor row f = 2 j, lanes 16..30 those of row f = 2 j + 1 (lanes 15, 31 idle): a
+      // half-warp then stores into ONE 128-byte f-row of the tile - conflict-free - where the flat mapping (32 consecutive
+      // float4 per instruction) straddled two or three f-rows and doubled the store wavefronts (run 42: LSU data pipe 81 % busy)
+      const int hw = lane >> 4, ql = lane & 15;
+      const bool act = ql < 15;
+      float4 v[16];
 #pragma unroll
-      for (int j = 0; j < 15; ++j) v[j] = ldg_stream4(src + j * 32 + lane);
+      for (int j = 0; j < 16; ++j) v[j] = act ? ldg_stream4(src + 30 * j + 15 * hw + ql) : make_float4(0.f, 0.f, 0.f, 0.f);
       if (role == 0 && lane == 0) C3_TRACE(it, 0);
       advance();                                       // resolve the next row while this one is in flight
-      const uint32_t use = it / C3_GROUPS;             // how often this group's tile set has been filled before
+      const int set = it % C3_GROUPS; const uint32_t use = it / C3_GROUPS;
       if (role == 0 && lane == 0) C3_TRACE(it, 1);
-      mbar_wait_lean(BAR(3 + grp), (use & 1) ^ 1);     // the MMAs of this group's previous item no longer read the tile set
+      mbar_wait_lean(BAR(3 + set), (use & 1) ^ 1);     // the MMAs of the set's previous item no longer read it
       if (role == 0 && lane == 0) C3_TRACE(it, 2);
-      uint8_t* thi = bufs + grp * C3_BUF_BYTES + (isY * 4 + m) * C3_OP_BYTES;
+      uint8_t* thi = bufs + set * C3_BUF_BYTES + ((role >> 1) * 4 + (role & 1)) * C3_OP_BYTES;
       uint8_t* tlo = thi + 2 * C3_OP_BYTES;
+      const int qh = ql >> 1, qb = (ql & 1) * 8;       // h = 4 ql: 16-byte chunk h / 8 and the 8-byte half inside it
+      if (act)
 #pragma unroll
-      for (int j = 0; j < 15; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const __half2 h01 = __floats2half2_rn(v[j].x, v[j].y), h23 = __floats2half2_rn(v[j].z, v[j].w);
         const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
         const __half2 l01 = __floats2half2_rn((v[j].x - f01.x) * T4_LO_SCALE, (v[j].y - f01.y) * T4_LO_SCALE);
@@ -163,19 +170,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
         uint2 hv, lv;
         hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
         lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-        *reinterpret_cast<uint2*>(thi + off[j]) = hv;
-        *reinterpret_cast<uint2*>(tlo + off[j]) = lv;
+        const int fr = ((2 * j) & 7) | hw;               // f % 8 with f = 2 j + hw;  f / 8 = j / 4
+        const int off = (j >> 2) * 1024 + fr * 128 + ((qh ^ fr) << 4) + qb;
+        *reinterpret_cast<uint2*>(thi + off) = hv;
+        *reinterpret_cast<uint2*>(tlo + off) = lv;
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to tcgen05
       __syncwarp();
-      if (lane == 0) mbar_arrive(BAR(0 + grp));        // conv_done: 4 warps per item
+      if (lane == 0) mbar_arrive(BAR(0 + set));        // conv_done: 4 row tasks per item
       if (role == 0 && lane == 0) C3_TRACE(it, 3);
     }
-  } else if (warp == 16) {
+  } else if (warp == C3_LOADERS) {
     // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues =====================
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int p, k0; if (item_count(item, p, k0) <= 0) continue;
+    for (Walk wk = walk_begin(); wk.item < n_items; walk_next(wk)) {
+      if (walk_avail(wk) <= 0) continue;
       const int g = it % C3_GROUPS, acc = it & 1; const uint32_t gph = (it / C3_GROUPS) & 1, aph = (it >> 1) & 1;
       mbar_wait_lean(BAR(0 + g), gph);                 // operand tiles written and visible to the async proxy
       if (lane == 0) C3_TRACE(it, 4);
@@ -198,24 +207,32 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     }
   } else {
     // ===================== epilogue =====================
-    const int q = warp & 3;                            // TMEM lane quadrant of this warp (warps 12..15 -> 0..3)
+    // two sets of 4 warps (12..15, 16..19): set s takes the items with it % 2 == s, i.e. accumulator buffer s - a warp is alone on
+    // its latency chain (run 39/40: 2100 clk per item), so two items are drained side by side
+    const int eset = (warp - 12) >> 2;
+    const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
     const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
-    float* G = Gs + m * 60 * 64;
+    float* G = Gs + (eset * 2 + m) * 60 * 64;
+    const int nbar = 2 + eset * 2 + m;                 // named barrier of this (set, match) warp pair
+    uint32_t* rk = red_k + eset * 2; int* ri = red_i + eset * 2;
     // this thread always sums the generalised diagonal a = h: keep its 60 table bytes in registers
     uint32_t trow[15];
 #pragma unroll
     for (int w4 = 0; w4 < 15; ++w4) {
       const uint8_t* t = tabs + (h < RR_G ? h : 0) * 60 + 4 * w4;
-      trow[w4] = (uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24);
+      trow[w4] = 4u * ((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24));   // bytes = 4 * P < 240: byte offsets
     }
+    const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
     uint32_t it = 0;
-    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-      int p, k0; const int avail = item_count(item, p, k0);
+    for (Walk wk = walk_begin(); wk.item < n_items; walk_next(wk)) {
+      const int avail = walk_avail(wk);
       if (avail <= 0) continue;
+      if ((int)(it & 1) != eset) { ++it; continue; }
+      const int p = wk.p, k0 = 2 * wk.j;
       const int buf = it & 1; const uint32_t ph = (it >> 1) & 1;
       mbar_wait_lean(BAR(6 + buf), ph);
-      if (warp == 12 && lane == 0) C3_TRACE(it, 7);
+      if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 7);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + m * 64;
 #pragma unroll
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
           if (lane == 0) mbar_arrive(BAR(8 + buf));    // accumulators free as soon as they sit in registers
-          if (warp == 12 && lane == 0) C3_TRACE(it, 8);
+          if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 8);
         }
         // transposed store: Gs[m][g][h]; a warp writes 32 consecutive h -> conflict-free
 #pragma unroll
@@ -237,44 +254,53 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
           if (g < 60) G[g * 64 + h] = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
         }
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");
+      asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");
+      if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 10);
       float c = -INFINITY;
       if (h < RR_G) {
-        float c4[4] = {0.f, 0.f, 0.f, 0.f};            // four independent chains (the sum order differs from g = 0..59 only in rounding)
+        // all 60 loads first (independent addresses straight from the table bytes), then a fixed-shape tree: the warp is alone on
+        // its latency chain, so the shared-memory latency must be paid once, not 15 times (the sum order differs from
+        // g = 0..59 only in rounding)
+        float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-        for (int w4 = 0; w4 < 15; ++w4) {
-          const uint32_t tw = trow[w4];
-          c4[0] += G[(4 * w4 + 0) * 64 + (tw & 0xff)];
-          c4[1] += G[(4 * w4 + 1) * 64 + ((tw >> 8) & 0xff)];
-          c4[2] += G[(4 * w4 + 2) * 64 + ((tw >> 16) & 0xff)];
-          c4[3] += G[(4 * w4 + 3) * 64 + (tw >> 24)];
+        for (int part = 0; part < 3; ++part) {           // 20 loads in flight at a time (register budget: 96 per thread)
+          float gv[20];
+#pragma unroll
+          for (int w = 0; w < 5; ++w) {
+            const int w4 = part * 5 + w;
+            const uint32_t tw = trow[w4];
+            gv[4 * w + 0] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 0) * 256 + __byte_perm(tw, 0, 0x4440));
+            gv[4 * w + 1] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 1) * 256 + __byte_perm(tw, 0, 0x4441));
+            gv[4 * w + 2] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 2) * 256 + __byte_perm(tw, 0, 0x4442));
+            gv[4 * w + 3] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 3) * 256 + __byte_perm(tw, 0, 0x4443));
+          }
+#pragma unroll
+          for (int k = 0; k < 20; ++k) c8[(part * 20 + k) & 7] += gv[k];
         }
-        c = (c4[0] + c4[1]) + (c4[2] + c4[3]);
+        c = ((c8[0] + c8[1]) + (c8[2] + c8[3])) + ((c8[4] + c8[5]) + (c8[6] + c8[7]));
       }
+      if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 11);
       const bool valid = m < avail;
       const long long w = (long long)p * a.K + k0 + m;
       if (valid && h < RR_G && a.cor_out) a.cor_out[w * RR_G + h] = c;
-      float v = c; int ix = (h < RR_G) ? h : 0x7fffffff;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float vo = __shfl_xor_sync(0xffffffffu, v, o);
-        const int io = __shfl_xor_sync(0xffffffffu, ix, o);
-        if (vo > v || (vo == v && io < ix)) { v = vo; ix = io; }
-      }
-      if ((q & 1) == 1 && lane == 0) { red_v[m] = v; red_i[m] = ix; }       // upper half-row warp (h 32..63) publishes
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");
+      // first maximal index (torch.argmax): warp-wide integer max of the order-preserving key, then the smallest h attaining it
+      const uint32_t key = (h < RR_G) ? t4_ord(c + 0.f) : 0u;              // + 0.f: -0 and +0 compare equal, as in float arithmetic
+      const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+      const int ix = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)h : 0x7fffffffu);
+      if ((q & 1) == 1 && lane == 0) { rk[m] = kmax; ri[m] = ix; }          // upper half-row warp (h 32..63) publishes
+      asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");
       if ((q & 1) == 0 && lane == 0 && valid && a.argmax_out) {
         int best = ix;                                                      // lower warp holds the smaller indices
-        if (red_v[m] > v) best = red_i[m];
+        if (rk[m] > kmax) best = ri[m];
         a.argmax_out[w] = best;
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(2 + m) : "memory");             // Gs / red reusable
-      if (warp == 12 && lane == 0) C3_TRACE(it, 9);
+      asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");             // Gs / red reusable
+      if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 9);
       ++it;
     }
   }
   __syncthreads();
-  if (warp == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  if (warp == C3_LOADERS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 // X, Y: descriptor arrays [rows][32][60] float32, 16-byte aligned (a row is 7680 B)
@@ -288,6 +314,7 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
     attr_set = true;
   }
   const long long items = (long long)a.B * ((a.K + 1) / 2);
+  RR_ARG(c, items < (1LL << 31));
   const int grid = (int)(items < c->sm_count ? items : c->sm_count);
   const char* trace_fn = getenv("ROREG_DEBUG_CORR_TRACE");
   static bool traced = false;
@@ -302,11 +329,11 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
     long long* h = (long long*)malloc(256 * 12 * sizeof(long long));
     RR_CUDA(c, cudaMemcpy(h, a.trace, 256 * 12 * sizeof(long long), cudaMemcpyDeviceToHost));
     if (FILE* f = fopen(trace_fn, "w")) {
-      fprintf(f, "# it L_issued L_advanced L_tilesfree L_done M_convdone M_accfree M_committed E_mmadone E_loaded E_end (clock64 - first; loader stamps: the X-m0 warp of the group that owns the item)\n");
+      fprintf(f, "# it L_issued L_advanced L_tilesfree L_done M_convdone M_accfree M_committed E_mmadone E_loaded E_end E_stored E_summed (clock64 - first; loader stamps: the X-m0 warp of the group that owns the item)\n");
       const long long t0 = h[0];
       for (int i = 0; i < 255; ++i) {
         fprintf(f, "%d", i);
-        for (int e = 0; e < 10; ++e) fprintf(f, " %lld", h[i * 12 + e] ? h[i * 12 + e] - t0 : -1);
+        for (int e = 0; e < 12; ++e) fprintf(f, " %lld", h[i * 12 + e] ? h[i * 12 + e] - t0 : -1);
         fprintf(f, "\n");
       }
       fclose(f);

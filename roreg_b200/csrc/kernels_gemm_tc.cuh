@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
   // barriers: 0..3 full, 4..7 empty, 8..9 tmem_full, 10..11 tmem_empty
   __shared__ uint32_t tmem_base_s;

@@ -95,7 +95,7 @@ struct NNTcArgs {
 __global__ void __launch_bounds__(192, 1) nn_tc_kernel(const __grid_constant__ CUtensorMap mapA,
                                                        const __grid_constant__ CUtensorMap mapB, NNTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // 48 KB
   uint8_t* sB = smem + TC_TILE_BYTES;                   // TC_STAGES x 48 KB
   float* sNb = reinterpret_cast<float*>(smem + TC_TILE_BYTES * (1 + TC_STAGES));   // [2][128]
@@ -322,7 +322,7 @@ __global__ void __launch_bounds__(256) nn_tc2_prep_kernel(const float* __restric
 
 __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc2_kernel(const __grid_constant__ CUtensorMap mapH, NNTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;                                   // 32 KB
   uint8_t* sB = smem + T2_TILE_BYTES;                   // T2_STAGES x 32 KB
   float* sNb = reinterpret_cast<float*>(smem + T2_TILE_BYTES * (1 + T2_STAGES));   // [2][128]
@@ -527,7 +527,7 @@ __global__ void nn_tc3_unpack_kernel(const unsigned long long* __restrict__ col_
 
 __global__ void __launch_bounds__(T2_THREADS, 1) nn_tc3_kernel(const __grid_constant__ CUtensorMap mapH, NNTc3Args a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + T2_TILE_BYTES;
   float* sNb = reinterpret_cast<float*>(smem + T2_TILE_BYTES * (1 + T2_STAGES));   // [2][128]

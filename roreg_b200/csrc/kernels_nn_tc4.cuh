@@ -58,6 +58,38 @@ __device__ __forceinline__ int t4_sw128_h(int r, int k) { return r * 128 + ((((k
 //   16..31 column-role, for D1    [ 1, -n1, 0...]
 //   32..47 column-role, for D2    [ 0, 0, 1, 1, -n2, -n3, 0...]
 // so that  ext_row . ext_col1 = -na1 - nb1  and  ext_row . ext_col2 = -(na2 + na3) - (nb2 + nb3).
+// one warp emits one padded row rr of (pair, side) ps; lane holds x = feature[lane] (0 for a padding row rr >= S)
+__device__ __forceinline__ void t4_emit_row(uint8_t* __restrict__ img, long long ps, int rr, int S, int NT, int lane, float x) {
+  const int t = rr >> 7, r = rr & 127;
+  uint8_t* tile = img + (ps * NT + t) * (long long)T4_TILE_BYTES;
+  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
+  const __half hi = __float2half_rn(x);
+  const __half lo = __float2half_rn((x - __half2float(hi)) * T4_LO_SCALE);
+  const float nh = (rr < S) ? 0.5f * warp_sum(x * x) : T4_PAD_NORM;
+  const __half n1 = __float2half_rn(nh);
+  const float r1 = (nh - __half2float(n1)) * T4_LO_SCALE;
+  const __half n2 = __float2half_rn(r1);
+  const __half n3 = __float2half_rn(r1 - __half2float(n2));
+  // lane L stores 32-bit word L of the 128-byte row: words 0..15 = hi pairs, 16..31 = lo' pairs (one coalesced row per warp)
+  {
+    const uint32_t hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
+    const int s0 = (2 * lane) & 31;
+    const uint32_t h0 = __shfl_sync(0xffffffffu, hb, s0), h1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
+    const uint32_t l0 = __shfl_sync(0xffffffffu, lb, s0), l1 = __shfl_sync(0xffffffffu, lb, s0 + 1);
+    const uint32_t word = lane < 16 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
+    *reinterpret_cast<uint32_t*>(tile + t4_sw128_h(r, 2 * lane)) = word;
+  }
+  // extension box: lane writes columns 2*lane, 2*lane+1
+  __half e0 = zero, e1 = zero;
+  if (lane == 0) { e0 = __hneg(n1); e1 = one; }              // cols 0,1
+  else if (lane == 1) { e0 = __hneg(n2); e1 = __hneg(n3); }   // cols 2,3
+  else if (lane == 2) { e0 = one; e1 = one; }                // cols 4,5
+  else if (lane == 8) { e0 = one; e1 = __hneg(n1); }         // cols 16,17
+  else if (lane == 17) { e0 = one; e1 = one; }               // cols 34,35
+  else if (lane == 18) { e0 = __hneg(n2); e1 = __hneg(n3); }  // cols 36,37
+  *reinterpret_cast<__half2*>(tile + TC_BOX_BYTES + t4_sw128_h(r, 2 * lane)) = __halves2half2(e0, e1);
+}
+
 __global__ void __launch_bounds__(256) nn_tc4_prep_kernel(const float* __restrict__ inv, int S, int NT, long long total_rows,
                                                           uint8_t* __restrict__ img) {
   // a warp converts 4 consecutive padded rows: the 4 loads are issued before anything is used (the kernel is latency-bound)
@@ -69,38 +101,47 @@ __global__ void __launch_bounds__(256) nn_tc4_prep_kernel(const float* __restric
   float xs[4];
 #pragma unroll
   for (int u = 0; u < 4; ++u) xs[u] = (rr0 + u < S) ? inv[(ps * S + rr0 + u) * 32 + lane] : 0.f;
-  const __half one = __float2half_rn(1.f), zero = __float2half_rn(0.f);
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    const int rr = rr0 + u, t = rr >> 7, r = rr & 127;
-    uint8_t* tile = img + (ps * NT + t) * (long long)T4_TILE_BYTES;
-    const float x = xs[u];
-    const __half hi = __float2half_rn(x);
-    const __half lo = __float2half_rn((x - __half2float(hi)) * T4_LO_SCALE);
-    const float nh = (rr < S) ? 0.5f * warp_sum(x * x) : T4_PAD_NORM;
-    const __half n1 = __float2half_rn(nh);
-    const float r1 = (nh - __half2float(n1)) * T4_LO_SCALE;
-    const __half n2 = __float2half_rn(r1);
-    const __half n3 = __float2half_rn(r1 - __half2float(n2));
-    // lane L stores 32-bit word L of the 128-byte row: words 0..15 = hi pairs, 16..31 = lo' pairs (one coalesced row per warp)
-    {
-      const uint32_t hb = __half_as_ushort(hi), lb = __half_as_ushort(lo);
-      const int s0 = (2 * lane) & 31;
-      const uint32_t h0 = __shfl_sync(0xffffffffu, hb, s0), h1 = __shfl_sync(0xffffffffu, hb, s0 + 1);
-      const uint32_t l0 = __shfl_sync(0xffffffffu, lb, s0), l1 = __shfl_sync(0xffffffffu, lb, s0 + 1);
-      const uint32_t word = lane < 16 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
-      *reinterpret_cast<uint32_t*>(tile + t4_sw128_h(r, 2 * lane)) = word;
-    }
-    // extension box: lane writes columns 2*lane, 2*lane+1
-    __half e0 = zero, e1 = zero;
-    if (lane == 0) { e0 = __hneg(n1); e1 = one; }              // cols 0,1
-    else if (lane == 1) { e0 = __hneg(n2); e1 = __hneg(n3); }   // cols 2,3
-    else if (lane == 2) { e0 = one; e1 = one; }                // cols 4,5
-    else if (lane == 8) { e0 = one; e1 = __hneg(n1); }         // cols 16,17
-    else if (lane == 17) { e0 = one; e1 = one; }               // cols 34,35
-    else if (lane == 18) { e0 = __hneg(n2); e1 = __hneg(n3); }  // cols 36,37
-    *reinterpret_cast<__half2*>(tile + TC_BOX_BYTES + t4_sw128_h(r, 2 * lane)) = __halves2half2(e0, e1);
+  for (int u = 0; u < 4; ++u) t4_emit_row(img, ps, rr0 + u, S, NT, lane, xs[u]);
+}
+
+// the padding rows S .. NT*128-1 of every (pair, side) only (the fused pooling kernel writes the real rows)
+__global__ void __launch_bounds__(256) nn_tc4_pad_kernel(int S, int NT, int n_ps, uint8_t* __restrict__ img) {
+  const int pad = NT * TC_BM - S;
+  const long long w = blockIdx.x * 8LL + (threadIdx.x >> 5);
+  if (w >= (long long)n_ps * pad) return;
+  t4_emit_row(img, w / pad, S + (int)(w % pad), S, NT, threadIdx.x & 31, 0.f);
+}
+
+// invariant pooling (kernels_match.cuh: inv_pool_kernel, same arithmetic) fused with the operand-image row: the pooled,
+// normalised feature is written once as float32 (the resolve kernel and the reference-arithmetic paths read it) and once as
+// the fp16 hi / lo' / extension row of its tile - saves the prep kernel's pass over the features.
+__global__ void __launch_bounds__(256) inv_pool_t4_kernel(PoolArgs a, int NT, uint8_t* __restrict__ img) {
+  __shared__ float part[8][480];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + warp;
+  if (r >= a.rows) return;
+  const int ps = r / a.S, i = r - ps * a.S;
+  long long cloud = 0;
+  if (a.pair_cloud) cloud = a.pair_cloud[ps];
+  const int srcrow = a.sample ? a.sample[r] : i;
+  const float4* src = reinterpret_cast<const float4*>(a.desc + (cloud * a.n + srcrow) * (long long)RR_ROW);
+  float4 v[15];
+#pragma unroll
+  for (int k = 0; k < 15; ++k) v[k] = ldg_stream4(src + k * 32 + lane);
+#pragma unroll
+  for (int k = 0; k < 15; ++k) part[warp][k * 32 + lane] = (v[k].x + v[k].y) + (v[k].z + v[k].w);
+  __syncwarp();
+  float s = 0.f;
+#pragma unroll
+  for (int j = 0; j < 15; ++j) s += part[warp][lane * 15 + j];
+  float m = s / 60.0f;
+  if (a.normalise) {
+    const float ss = warp_sum(m * m);
+    m = m / (sqrtf(ss) + 1e-5f);
   }
+  a.out[(long long)r * RR_F + lane] = m;
+  t4_emit_row(img, ps, i, a.S, NT, lane, m);
 }
 
 struct NNTc4Args {
@@ -140,7 +181,9 @@ __device__ __forceinline__ void t4_commit(uint32_t bar) {
   asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
 }
 
-// if (v > cmax) { cmax = v; byte `slot` of ctile = t; }   as FSETP + @p FADD (FMA pipe) + @p PRMT
+// if (v > cmax) { cmax = v; byte `slot` of ctile = t; }   as FSETP + @p FADD (an FMA-pipe move: v + -0) + @p PRMT.
+// (Run 43 tried the tile index as an fp16 pair updated by a predicated HFMA2 to take the PRMT off the half-rate ALU pipe:
+//  the kernel got 16 % slower - fp16 FMAs issue on the "heavy" half of the FMA pipe only - so the byte-packed form stays.)
 __device__ __forceinline__ void t4_col_update(float& cmax, uint32_t& ctile, float v, uint32_t t, int slot) {
 #define T4_CU(SEL) asm("{\n.reg .pred p;\nsetp.gt.f32 p, %2, %0;\n@p add.f32 %0, %2, 0f80000000;\n@p prmt.b32 %1, %1, %3, " #SEL ";\n}" \
                        : "+f"(cmax), "+r"(ctile) : "f"(v), "r"(t))
@@ -156,7 +199,7 @@ __device__ __forceinline__ void t4_col_update(float& cmax, uint32_t& ctile, floa
 template <bool TRACE>
 __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* sB = smem;                                   // stationary tile (cloud 1 block), 32 KB
   uint8_t* sA = smem + T4_TILE_BYTES;                   // T4_STAGES x 32 KB streaming tiles (cloud 0)
   unsigned long long* cmg = reinterpret_cast<unsigned long long*>(smem + T4_TILE_BYTES * (1 + T4_STAGES));   // [2 halves][4 quadrants][64 columns]
@@ -250,7 +293,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
     uint32_t it_t = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int j = item % NT, p = item / NT;
-      float cmax[64]; uint32_t ctile[16];
+      float cmax[64]; uint32_t ctile[16];             // running column maxima; tile index of each as a byte, four per register
 #pragma unroll
       for (int e = 0; e < 64; ++e) cmax[e] = -INFINITY;
 #pragma unroll
@@ -278,14 +321,15 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
             if (threadIdx.x == 64) T4_TRACE(it_t, 5);
           }
           // column direction: running maximum of -d^2/2 over the rows this lane sees; strict '>' + increasing t = first row wins ties.
-          // FSETP and PRMT issue on the half-rate ALU pipe, the predicated move is an FADD with -0 so that it goes to the FMA pipe:
-          // 2.5 ALU instructions per element in total (with the FMNMX3 of the row direction).
+          // Per element: FFMA (combine) + FSETP + @p FADD + @p PRMT, and half an FMNMX3 for the row direction.
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
+          for (int u = 0; u < 32; u += 2) {
             const int e = half * 32 + u;
-            const float v = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
-            t4_col_update(cmax[e], ctile[e >> 2], v, (uint32_t)t, e & 3);
-            g8[e >> 3] = fmaxf(g8[e >> 3], v);
+            const float v0 = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
+            const float v1 = fmaf(__uint_as_float(r2[u + 1]), T4_LO_UNSCALE, __uint_as_float(r1[u + 1]));
+            t4_col_update(cmax[e], ctile[e >> 2], v0, (uint32_t)t, e & 3);
+            t4_col_update(cmax[e + 1], ctile[e >> 2], v1, (uint32_t)t, (e + 1) & 3);
+            g8[e >> 3] = fmaxf(fmaxf(g8[e >> 3], v0), v1);
           }
         }
         if (threadIdx.x == 64) T4_TRACE(it_t, 6);
@@ -389,14 +433,23 @@ static inline size_t nn_tc4_workspace_bytes(int B, int S) {
 }
 
 // inv: [B][2][S][32] pooled features; img / rowval / rowgid / best_group: workspace of nn_tc4_workspace_bytes(B, S)
+// img_ready: the real rows of the image were already written by inv_pool_t4_kernel (only the padding rows are missing)
 static inline int nn_tc4_launch_both(roreg_ctx* c, const float* inv, int S, int B, uint8_t* img, float* rowval, uint8_t* rowgid, int32_t* best_group,
-                                     int32_t* nn01, int32_t* nn10, cudaStream_t st) {
+                                     int32_t* nn01, int32_t* nn10, cudaStream_t st, bool img_ready = false) {
   const int NT = (S + TC_BM - 1) / TC_BM;
   RR_ARG(c, NT <= 256);                                  // tile indices of the column direction are kept as bytes
   RR_ARG(c, (reinterpret_cast<uintptr_t>(img) & 1023) == 0);
   const long long total_rows = (long long)B * 2 * NT * TC_BM;
-  nn_tc4_prep_kernel<<<(unsigned)((total_rows / 4 + 7) / 8), 256, 0, st>>>(inv, S, NT, total_rows, img);
-  RR_LAUNCH_CHECK(c);
+  if (img_ready) {
+    const long long pad_rows = (long long)B * 2 * (NT * TC_BM - S);
+    if (pad_rows > 0) {
+      nn_tc4_pad_kernel<<<(unsigned)((pad_rows + 7) / 8), 256, 0, st>>>(S, NT, B * 2, img);
+      RR_LAUNCH_CHECK(c);
+    }
+  } else {
+    nn_tc4_prep_kernel<<<(unsigned)((total_rows / 4 + 7) / 8), 256, 0, st>>>(inv, S, NT, total_rows, img);
+    RR_LAUNCH_CHECK(c);
+  }
   static bool attr_set = false;
   if (!attr_set) {
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));

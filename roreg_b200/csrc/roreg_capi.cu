@@ -535,9 +535,6 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   RR_MARK(0);
   // 1. invariant pooling + normalisation of both sides of every pair  (test/matcher.py:69-72)
   PoolArgs pa{b->desc, b->pair_cloud, b->sample, b->n, S, B * 2 * S, 1, inv};
-  inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
-  RR_LAUNCH_CHECK(c);
-  RR_MARK(1);
   // 2. 1-NN both ways  (test/matcher.py:94-97)
   const long long ps = 2LL * S * RR_F;
   if (b->nn_mode == 4) {
@@ -547,8 +544,14 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     float* rowval = ar.take<float>((size_t)B * 2 * NT * NT * TC_BM);
     uint8_t* rowgid = ar.take<uint8_t>((size_t)B * 2 * NT * NT * TC_BM);
     int32_t* bchunk = ar.take<int32_t>((size_t)B * S);
-    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowval, rowgid, bchunk, nn01, nn10, st))) return rc;
+    inv_pool_t4_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa, (int)NT, img);   // pooling fused with the fp16 operand image
+    RR_LAUNCH_CHECK(c);
+    RR_MARK(1);
+    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowval, rowgid, bchunk, nn01, nn10, st, true))) return rc;
   } else if (b->nn_mode >= 1) {
+    inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
+    RR_LAUNCH_CHECK(c);
+    RR_MARK(1);
     float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
     float* nh = ar.take<float>((size_t)B * 2 * S);
@@ -557,6 +560,9 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
     else if (b->nn_mode == 2) { if ((rc = nn_tc2_launch_both(c, inv, S, B, Ahat, nh, nn01, nn10, st))) return rc; }
     else if ((rc = nn_tc_launch_both(c, inv, S, B, Ahat, Bhat, nh, nn01, nn10, st))) return rc;
   } else {
+    inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
+    RR_LAUNCH_CHECK(c);
+    RR_MARK(1);
     if ((rc = launch_nn(c, 0, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;
     if ((rc = launch_nn(c, 0, inv + (size_t)S * RR_F, inv, ps, ps, S, S, nn10, nullptr, S, B, st))) return rc;
   }
