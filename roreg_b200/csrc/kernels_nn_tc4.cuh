@@ -438,7 +438,7 @@ static inline int nn_tc4_launch_both(roreg_ctx* c, const float* inv, int S, int 
                                      int32_t* nn01, int32_t* nn10, cudaStream_t st, bool img_ready = false) {
   const int NT = (S + TC_BM - 1) / TC_BM;
   RR_ARG(c, NT <= 256);                                  // tile indices of the column direction are kept as bytes
-  RR_ARG(c, (reinterpret_cast<uintptr_t>(img) & 1023) == 0);
+  RR_ARG(c, (reinterpret_cast<uintptr_t>(img) & 15) == 0);    // cp.async.bulk source: 16-byte aligned (the swizzle only constrains the shared-memory side)
   const long long total_rows = (long long)B * 2 * NT * TC_BM;
   if (img_ready) {
     const long long pad_rows = (long long)B * 2 * (NT * TC_BM - S);
