@@ -60,7 +60,12 @@ int roreg_knn(roreg_ctx* ctx, const float* target, int n, const float* source, i
 /* ---- a13  test/matcher.py:94-106: 1-NN both ways on [n0,32] / [n1,32] invariant features + the mutual
  * check; matches come out in increasing row of f0 as (row in f0, row in f1).  n_matches: device int32[1].
  * nn01 [n0] / nn10 [n1] optional outputs (may be NULL).  mode 0 = float32 difference form (reference
- * arithmetic), mode 1 / 2 / 3 = tensor-core Gram form (tcgen05, 3xTF32; 2 = 8 epilogue warps, 3 = one Gram serves both directions).                                               */
+ * arithmetic), mode 1 / 2 / 3 = tensor-core Gram form (tcgen05, 3xTF32; 2 = 8 epilogue warps, 3 = one Gram serves
+ * both directions), mode 4 = one tcgen05 Gram per pair in the fp16 two-accumulator split (x = hi + 2^-11 lo',
+ * float32-class products), norms folded into the contraction, column direction reduced in registers, row direction
+ * finished by an exact float32 re-evaluation of the 8 best candidates in the reference's arithmetic - the fast one.
+ * Modes >= 1 need n0 == n1 here (the batched engine has no such restriction on its arena) and |x| <= ~1e4 (fp16 range;
+ * the matcher's inputs are L2-normalised).                                                                          */
 int roreg_mutual_match(roreg_ctx* ctx, const float* f0, int n0, const float* f1, int n1, int mode,
                        int32_t* matches, int32_t* n_matches, int32_t* nn01, int32_t* nn10, void* stream);
 

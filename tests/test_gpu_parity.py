@@ -374,7 +374,36 @@ def test_register_batch_tensor_core_nn(ctx, tables, mode):
         assert len(a ^ b) <= 4          # the two NN arithmetics may differ on a handful of near ties only
 
 
-# ---------------------------------------------------------------------------------------- corr modes 1, 2 (tcgen05)
+def test_fast_path_full_size_against_reference_arithmetic(ctx, tables):
+    """BASELINE configs[1] size (5000 keypoints, 40 x 40 tiles, every persistent CTA sweeps many items): the default fast path
+    (nn mode 4 + corr mode 3) against the reference-arithmetic kernels (nn mode 0 + corr mode 0) on the same two pairs:
+    same matches up to near ties, same coarse-rotation index on (nearly) every common match, same pose."""
+    from roreg_b200 import ops
+    prs = [synth.make_pair(s, n=5000) for s in (301, 302)]
+    outs = []
+    for nn_mode, corr_mode in ((0, 0), (4, 3)):
+        c = ctx if corr_mode == 0 else ops.Context(0)
+        c.set_corr_mode(corr_mode)
+        desc = c.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+        keys = c.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+        pc = c.dev(np.array([[0, 1], [2, 3]], np.int32))
+        o = c.register_batch(desc, keys, pc, max_iter=500, seed=3, nn_mode=nn_mode)
+        torch.cuda.synchronize()
+        outs.append({k: _np(v).copy() for k, v in o.items()})
+        if c is not ctx:
+            c.close()
+    o0, o1 = outs
+    for i, pr in enumerate(prs):
+        k0 = int(o0["n_matches"][i]); k1 = int(o1["n_matches"][i])
+        m0 = {tuple(r): d for r, d in zip(o0["matches"][i, :k0].tolist(), o0["dr_index"][i, :k0].tolist())}
+        m1 = {tuple(r): d for r, d in zip(o1["matches"][i, :k1].tolist(), o1["dr_index"][i, :k1].tolist())}
+        assert len(set(m0) ^ set(m1)) <= 8                 # near ties of the two NN arithmetics only (k ~ 3400)
+        common = set(m0) & set(m1)
+        assert np.mean([m0[r] == m1[r] for r in common]) > 0.995
+        assert np.abs(o1["poses"][i][:3] - pr["gt"]).max() < 5e-3 and np.abs(o0["poses"][i][:3] - pr["gt"]).max() < 5e-3
+
+
+# ---------------------------------------------------------------------------------------- corr modes 1, 2, 3 (tcgen05)
 @pytest.fixture(scope="module", params=[1, 2, 3], ids=["corr1", "corr2", "corr3"])
 def ctx_tc(request):
     from roreg_b200 import ops
