@@ -220,6 +220,13 @@ int roreg_estimate_batch(roreg_ctx* ctx, const roreg_batch* batch, const double*
  * roreg_get_stage_ms synchronises on the last event and writes ROREG_N_STAGES floats (milliseconds). */
 #define ROREG_N_STAGES 7
 int roreg_set_timing(roreg_ctx* ctx, int enable);
+
+/* Schedule of roreg_register_batch.  0 (default): every stage on the caller's stream.  1: a batch of >= 8 pairs is split in two halves whose stages overlap on two
+ * internal streams (pooling of the second half beside the NN of the first, RANSAC tail of the first beside the NN of the
+ * second); the call still only returns work ordered after / before the caller's stream.  Per-stage timing
+ * (roreg_set_timing) and estimator == 2 always use the serial schedule.  Results are identical; on a B200 the serial
+ * schedule measured faster, hence the default.                                                          */
+int roreg_set_overlap(roreg_ctx* ctx, int enable);
 int roreg_get_stage_ms(roreg_ctx* ctx, float* ms_host);
 
 #ifdef __cplusplus

@@ -26,6 +26,10 @@ struct roreg_ctx {
   int timing;                     // roreg_set_timing: record an event after every stage of roreg_register_batch
   cudaEvent_t ev[ROREG_N_STAGES + 1];
   int ev_valid;
+  // two-stream schedule of roreg_register_batch (roreg_set_overlap): tensor-core chain vs pooling / RANSAC tail
+  int overlap;                    // 1 (default): split a batch in two halves and overlap their stages on s_tc / s_light
+  cudaStream_t s_tc, s_light;     // created on first use: s_tc high priority, s_light low priority
+  cudaEvent_t ev_fork, ev_pool[2], ev_corr[2], ev_join[2];
   char err[512];
 };
 

@@ -84,6 +84,7 @@ struct CoarseArgs {
   const int32_t* dr_index; long long dr_pair_stride;
   const int32_t* triplets;       // [B][H][3] or NULL
   int H; uint64_t seed;
+  int pair_base;                 // index of this launch's first pair in the caller's batch (keeps the draws independent of how a batch is split)
   double* hyps;                  // [B][H][12]
   int32_t* n_hyp;                // [B]
   int32_t* scratch;              // [B][cap] bucket-sorted match ids
@@ -118,7 +119,25 @@ __global__ void __launch_bounds__(256) coarse_bucket_kernel(CoarseArgs a) {
   __syncthreads();
   if (tid < 60) a.bucket[p * 128 + tid] = cnt[tid];
   if (tid < 61) a.bucket[p * 128 + 60 + tid] = start[tid];
-  for (int k = tid; k < K; k += 256) { const int r = dr[k]; sorted[start[r] + atomicAdd(&fill[r], 1)] = k; }
+  // stable counting sort by one warp, 32 matches per step: a match's slot = start[bucket] + matches of the same bucket seen before
+  // (fill) + its rank among the same-bucket lanes of this step (match_any).  Deterministic - ascending k inside a bucket - so the
+  // device-side draws pick the same triplets on every run (an atomicAdd scatter made them depend on the arrival order).
+  if (tid < 32) {
+    for (int base = 0; base < K; base += 32) {
+      const int k = base + tid;
+      const bool valid = k < K;
+      const int r = valid ? dr[k] : 64 + tid;                          // invalid lanes get unique keys
+      const unsigned m = __match_any_sync(0xffffffffu, r);
+      const int rank = __popc(m & ((1u << tid) - 1u));
+      const int before = valid ? fill[r] : 0;
+      __syncwarp();
+      if (valid) {
+        sorted[start[r] + before + rank] = k;
+        if ((m >> tid) == 1u) fill[r] = before + __popc(m);           // the highest lane of the group publishes the new count
+      }
+      __syncwarp();
+    }
+  }
 }
 
 // stage 2: one thread per hypothesis, grid = (ceil(H/64), B)
@@ -140,14 +159,14 @@ __global__ void __launch_bounds__(64) coarse_hyp_kernel(CoarseArgs a) {
     const int32_t* t = a.triplets + ((long long)p * a.H + it) * 3;
     idx[0] = t[0]; idx[1] = t[1]; idx[2] = t[2];
   } else {
-    const double u = rr_u01(a.seed, p, it, 0);
+    const double u = rr_u01(a.seed, p + a.pair_base, it, 0);
     int r = 0;
     while (r < 59 && !(u < cdf[r])) ++r;
     while (r > 0 && cnt[r] < 2) --r;                // guard against cdf round-off landing on an empty bucket
     if (cnt[r] < 2) { for (r = 0; r < 59 && cnt[r] < 2; ++r) {} }
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      int o = (int)(rr_u01(a.seed, p, it, 1 + j) * cnt[r]);
+      int o = (int)(rr_u01(a.seed, p + a.pair_base, it, 1 + j) * cnt[r]);
       o = min(o, cnt[r] - 1);
       idx[j] = sorted[start[r] + o];
     }

@@ -29,6 +29,7 @@ int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const 
   roreg_ctx* c = new roreg_ctx();
   memset(c, 0, sizeof(*c));
   c->device = device;
+  c->overlap = 0;
   *out = c;
   RR_CUDA(c, cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -63,6 +64,10 @@ int roreg_ctx_destroy(roreg_ctx* c) {
   cudaSetDevice(c->device);
   cudaDeviceSynchronize();
   if (c->ev[0]) for (int i = 0; i <= ROREG_N_STAGES; ++i) cudaEventDestroy(c->ev[i]);
+  if (c->s_tc) {
+    cudaStreamDestroy(c->s_tc); cudaStreamDestroy(c->s_light); cudaEventDestroy(c->ev_fork);
+    for (int h = 0; h < 2; ++h) { cudaEventDestroy(c->ev_pool[h]); cudaEventDestroy(c->ev_corr[h]); cudaEventDestroy(c->ev_join[h]); }
+  }
   cudaFree(c->d_perm8); cudaFree(c->d_permT8); cudaFree(c->d_nei); cudaFree(c->d_rot32); cudaFree(c->d_rot64);
   if (c->ws) cudaFree(c->ws);
   delete c;
@@ -502,14 +507,24 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
 // ------------------------------------------------------------------------------------------------
 // batched engine
 // ------------------------------------------------------------------------------------------------
-int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
-  RR_ARG(c, b && b->desc && b->keys && b->pair_cloud && b->matches && b->n_matches && b->dr_index && b->poses &&
-                b->recall && b->best_overlap);
-  RR_ARG(c, b->B >= 1 && b->n >= 1 && b->keynum >= 1 && b->keynum <= b->n && b->max_iter >= 1 && b->ird > 0);
-  RR_ARG(c, b->sample || b->keynum == b->n);
-  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd) || b->estimator == 2);
-  cudaStream_t st = (cudaStream_t)stream;
-  const int B = b->B, S = b->keynum, H = b->max_iter;
+// ---- the batched engine in three phases per (sub-)batch -----------------------------------------------------------
+// P  pooling (HBM-bound, SMs mostly idle)            TC  NN + mutual check + Des2R (tensor-core kernels, one CTA per SM)
+// T  hypotheses + scoring + refinement (FP64 / latency-bound small kernels)
+// Serial schedule (default): P, TC, T on the caller's stream.  Overlapped schedule (roreg_set_overlap(1)): the batch is split in
+// two halves; the TC chains of both halves run back to back on a high-priority stream while P of the second half runs beside
+// the NN of the first and T of the first beside the NN of the second on a low-priority stream - the kernels' bottlenecks
+// are complementary and one pooling / scoring CTA fits on an SM next to the persistent NN CTA.  Measured (run 47, 64 pairs): 19.9 k
+// pairs/s overlapped against 21.5 k serial - the co-resident kernels slow each other more than the overlap hides - so it is off by default.
+struct BatchPlan {            // one (sub-)batch: views into the caller's arrays + its slice of the workspace
+  roreg_batch b;              // pointers already offset to the first pair of the slice, b.B = pairs in the slice
+  int pair_base;
+  float* inv; int32_t *nn01, *nn10; double *hyps, *partial; int32_t *scratch, *n_hyp, *bucket; double* cdf;
+  uint8_t* img; float* rowval; uint8_t* rowgid; int32_t* bgroup;          // nn mode 4
+  float *Ahat, *Bhat, *nh; unsigned long long* cb;                        // nn modes 1-3
+};
+
+static size_t batch_ws_bytes(const roreg_batch* b, int B) {
+  const int S = b->keynum, H = b->max_iter;
   const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
   size_t need = rr_align(sizeof(float) * (size_t)B * 2 * S * RR_F) + 2 * rr_align(sizeof(int32_t) * (size_t)B * S) +
                 rr_align(sizeof(double) * (size_t)B * H * 12) + rr_align(sizeof(double) * (size_t)B * tiles * H) +
@@ -517,113 +532,221 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
                 rr_align(sizeof(int32_t) * (size_t)B * 128) + rr_align(sizeof(double) * (size_t)B * 60) + 8192;
   if (b->nn_mode == 4) need += nn_tc4_workspace_bytes(B, S) + 2048;
   else if (b->nn_mode >= 1) need += nn_tc_workspace_bytes((long long)B * 2 * S);
-  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 4);
-  int rc = rr_ws_reserve(c, need);
-  if (rc) return rc;
-  rr_arena ar{(char*)c->ws, 0};
-  float* inv = ar.take<float>((size_t)B * 2 * S * RR_F);
-  int32_t* nn01 = ar.take<int32_t>((size_t)B * S);
-  int32_t* nn10 = ar.take<int32_t>((size_t)B * S);
-  double* hyps = ar.take<double>((size_t)B * H * 12);
-  double* partial = ar.take<double>((size_t)B * tiles * H);
-  int32_t* scratch = ar.take<int32_t>((size_t)B * S);
-  int32_t* n_hyp = ar.take<int32_t>(B);
-  int32_t* bucket = ar.take<int32_t>((size_t)B * 128);
-  double* cdf = ar.take<double>((size_t)B * 60);
+  return rr_align(need);
+}
 
-#define RR_MARK(i) do { if (c->timing) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); } while (0)
-  RR_MARK(0);
-  // 1. invariant pooling + normalisation of both sides of every pair  (test/matcher.py:69-72)
-  PoolArgs pa{b->desc, b->pair_cloud, b->sample, b->n, S, B * 2 * S, 1, inv};
-  // 2. 1-NN both ways  (test/matcher.py:94-97)
-  const long long ps = 2LL * S * RR_F;
+static void batch_plan(const roreg_batch* b, int p0, int B, char* ws, BatchPlan* pl) {
+  const int S = b->keynum, H = b->max_iter;
+  const int tiles = (S + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
+  pl->b = *b; pl->b.B = B; pl->pair_base = p0;
+  pl->b.pair_cloud = b->pair_cloud + 2 * (size_t)p0;
+  if (b->sample) pl->b.sample = b->sample + (size_t)p0 * 2 * S;
+  if (b->triplets) pl->b.triplets = b->triplets + (size_t)p0 * H * 3;
+  if (b->hyp_host_svd) pl->b.hyp_host_svd = b->hyp_host_svd + (size_t)p0 * H * 12;
+  pl->b.matches = b->matches + (size_t)p0 * S * 2; pl->b.n_matches = b->n_matches + p0; pl->b.dr_index = b->dr_index + (size_t)p0 * S;
+  pl->b.poses = b->poses + (size_t)p0 * 16; pl->b.recall = b->recall + p0; pl->b.best_overlap = b->best_overlap + p0;
+  rr_arena ar{ws, 0};
+  pl->inv = ar.take<float>((size_t)B * 2 * S * RR_F);
+  pl->nn01 = ar.take<int32_t>((size_t)B * S);
+  pl->nn10 = ar.take<int32_t>((size_t)B * S);
+  pl->hyps = ar.take<double>((size_t)B * H * 12);
+  pl->partial = ar.take<double>((size_t)B * tiles * H);
+  pl->scratch = ar.take<int32_t>((size_t)B * S);
+  pl->n_hyp = ar.take<int32_t>(B);
+  pl->bucket = ar.take<int32_t>((size_t)B * 128);
+  pl->cdf = ar.take<double>((size_t)B * 60);
+  pl->img = nullptr; pl->rowval = nullptr; pl->rowgid = nullptr; pl->bgroup = nullptr;
+  pl->Ahat = pl->Bhat = pl->nh = nullptr; pl->cb = nullptr;
   if (b->nn_mode == 4) {
     const size_t NT = (size_t)(S + TC_BM - 1) / TC_BM;
     ar.off = (ar.off + 1023) & ~size_t(1023);
-    uint8_t* img = ar.take<uint8_t>((size_t)B * 2 * NT * T4_TILE_BYTES);
-    float* rowval = ar.take<float>((size_t)B * 2 * NT * NT * TC_BM);
-    uint8_t* rowgid = ar.take<uint8_t>((size_t)B * 2 * NT * NT * TC_BM);
-    int32_t* bchunk = ar.take<int32_t>((size_t)B * S);
-    inv_pool_t4_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa, (int)NT, img);   // pooling fused with the fp16 operand image
-    RR_LAUNCH_CHECK(c);
-    RR_MARK(1);
-    if ((rc = nn_tc4_launch_both(c, inv, S, B, img, rowval, rowgid, bchunk, nn01, nn10, st, true))) return rc;
+    pl->img = ar.take<uint8_t>((size_t)B * 2 * NT * T4_TILE_BYTES);
+    pl->rowval = ar.take<float>((size_t)B * 2 * NT * NT * TC_BM);
+    pl->rowgid = ar.take<uint8_t>((size_t)B * 2 * NT * NT * TC_BM);
+    pl->bgroup = ar.take<int32_t>((size_t)B * S);
   } else if (b->nn_mode >= 1) {
-    inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
-    RR_LAUNCH_CHECK(c);
-    RR_MARK(1);
-    float* Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
-    float* Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
-    float* nh = ar.take<float>((size_t)B * 2 * S);
-    unsigned long long* cb = ar.take<unsigned long long>((size_t)B * S);
-    if (b->nn_mode == 3) { if ((rc = nn_tc3_launch_both(c, inv, S, B, Ahat, nh, cb, nn01, nn10, st))) return rc; }
-    else if (b->nn_mode == 2) { if ((rc = nn_tc2_launch_both(c, inv, S, B, Ahat, nh, nn01, nn10, st))) return rc; }
-    else if ((rc = nn_tc_launch_both(c, inv, S, B, Ahat, Bhat, nh, nn01, nn10, st))) return rc;
+    pl->Ahat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
+    pl->Bhat = ar.take<float>((size_t)B * 2 * S * TC_KEXT);
+    pl->nh = ar.take<float>((size_t)B * 2 * S);
+    pl->cb = ar.take<unsigned long long>((size_t)B * S);
+  }
+}
+
+#define RR_MARK(i) do { if (mark) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); } while (0)
+
+// P: invariant pooling + normalisation of both sides of every pair  (test/matcher.py:69-72)
+static int batch_phase_pool(roreg_ctx* c, const BatchPlan& pl, cudaStream_t st, bool mark) {
+  const roreg_batch* b = &pl.b;
+  const int B = b->B, S = b->keynum;
+  RR_MARK(0);
+  PoolArgs pa{b->desc, b->pair_cloud, b->sample, b->n, S, B * 2 * S, 1, pl.inv};
+  if (b->nn_mode == 4) {
+    const int NT = (S + TC_BM - 1) / TC_BM;
+    inv_pool_t4_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa, NT, pl.img);      // pooling fused with the fp16 operand image
   } else {
     inv_pool_kernel<<<(pa.rows + 7) / 8, 256, 0, st>>>(pa);
-    RR_LAUNCH_CHECK(c);
-    RR_MARK(1);
-    if ((rc = launch_nn(c, 0, inv, inv + (size_t)S * RR_F, ps, ps, S, S, nn01, nullptr, S, B, st))) return rc;
-    if ((rc = launch_nn(c, 0, inv + (size_t)S * RR_F, inv, ps, ps, S, S, nn10, nullptr, S, B, st))) return rc;
+  }
+  RR_LAUNCH_CHECK(c);
+  RR_MARK(1);
+  return ROREG_OK;
+}
+
+// TC: 1-NN both ways (test/matcher.py:94-97), mutual check (:98-107), coarse rotation of every match (test/estimator.py:105-111)
+static int batch_phase_tc(roreg_ctx* c, const BatchPlan& pl, cudaStream_t st, bool mark) {
+  const roreg_batch* b = &pl.b;
+  const int B = b->B, S = b->keynum;
+  int rc;
+  const long long ps = 2LL * S * RR_F;
+  if (b->nn_mode == 4) {
+    if ((rc = nn_tc4_launch_both(c, pl.inv, S, B, pl.img, pl.rowval, pl.rowgid, pl.bgroup, pl.nn01, pl.nn10, st, true))) return rc;
+  } else if (b->nn_mode == 3) {
+    if ((rc = nn_tc3_launch_both(c, pl.inv, S, B, pl.Ahat, pl.nh, pl.cb, pl.nn01, pl.nn10, st))) return rc;
+  } else if (b->nn_mode == 2) {
+    if ((rc = nn_tc2_launch_both(c, pl.inv, S, B, pl.Ahat, pl.nh, pl.nn01, pl.nn10, st))) return rc;
+  } else if (b->nn_mode == 1) {
+    if ((rc = nn_tc_launch_both(c, pl.inv, S, B, pl.Ahat, pl.Bhat, pl.nh, pl.nn01, pl.nn10, st))) return rc;
+  } else {
+    if ((rc = launch_nn(c, 0, pl.inv, pl.inv + (size_t)S * RR_F, ps, ps, S, S, pl.nn01, nullptr, S, B, st))) return rc;
+    if ((rc = launch_nn(c, 0, pl.inv + (size_t)S * RR_F, pl.inv, ps, ps, S, S, pl.nn10, nullptr, S, B, st))) return rc;
   }
   RR_MARK(2);
-  // 3. mutual check, ordered compaction  (test/matcher.py:98-107)
-  CompactArgs ca{nn01, nn10, S, S, S, b->sample, S, b->matches, S, b->n_matches};
+  CompactArgs ca{pl.nn01, pl.nn10, S, S, S, b->sample, S, b->matches, S, b->n_matches};
   mutual_compact_kernel<<<B, 1024, 0, st>>>(ca);
   RR_LAUNCH_CHECK(c);
   RR_MARK(3);
-  // 4. coarse rotation of every match  (test/estimator.py:105-111: X = cloud id1, Y = cloud id0)
-  CorrArgs co{};
-  co.X = b->desc; co.Y = b->desc; co.idxX = b->matches + 1; co.idxY = b->matches; co.idx_stride = 2;
-  co.pair_cloud = b->pair_cloud; co.n = b->n; co.n_matches = b->n_matches; co.K = S; co.B = B;
-  co.tab = c->d_perm8; co.cor_out = nullptr; co.argmax_out = b->dr_index;
+  // X = cloud id1, Y = cloud id0
   if (c->corr_mode >= 1) {
     CorrTcArgs t{nullptr, nullptr, b->matches + 1, b->matches, 2, b->pair_cloud, b->n, b->n_matches, S, B, c->d_perm8, nullptr, b->dr_index, 3, 0, nullptr};
     if (const char* e = getenv("ROREG_DEBUG_CORR_PASSES")) { const int v = atoi(e); if (v >= 1 && v <= 3) t.dbg_passes = v; }
     if (const char* e = getenv("ROREG_DEBUG_CORR_SKIP")) t.dbg_skip = atoi(e);
     if ((rc = (c->corr_mode == 3 ? group_corr_tc3_launch(c, b->desc, b->desc, t, st) : c->corr_mode == 2 ? group_corr_tc2_launch(c, b->desc, b->desc, t, st) : group_corr_tc_launch(c, b->desc, b->desc, t, st)))) return rc;
   } else {
+    CorrArgs co{};
+    co.X = b->desc; co.Y = b->desc; co.idxX = b->matches + 1; co.idxY = b->matches; co.idx_stride = 2;
+    co.pair_cloud = b->pair_cloud; co.n = b->n; co.n_matches = b->n_matches; co.K = S; co.B = B;
+    co.tab = c->d_perm8; co.cor_out = nullptr; co.argmax_out = b->dr_index;
     const long long total = (long long)B * S;
     const int grid = (int)(total < (long long)c->sm_count * 8 ? total : (long long)c->sm_count * 8);
     group_corr_kernel<<<grid, 128, 0, st>>>(co);
     RR_LAUNCH_CHECK(c);
   }
   RR_MARK(4);
-  if (b->estimator == 2) {                 // matcher + Des2R only: the caller generates hypotheses (ET network) and calls roreg_estimate_batch
-    if (c->timing) { for (int i = 5; i <= ROREG_N_STAGES; ++i) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); c->ev_valid = 1; }
-    return ROREG_OK;
-  }
-  // 5. hypotheses
+  return ROREG_OK;
+}
+
+// T: hypotheses, one-shot scoring (test/estimator.py:149-154,232-238 / :426-436), two refinements (:240-241 / :438-439)
+static int batch_phase_tail(roreg_ctx* c, const BatchPlan& pl, cudaStream_t st, bool mark) {
+  const roreg_batch* b = &pl.b;
+  const int B = b->B, S = b->keynum, H = b->max_iter;
+  int rc;
   MatchView mv{};
   mv.keys0 = b->keys; mv.keys1 = b->keys; mv.pair_cloud = b->pair_cloud; mv.n = b->n; mv.matches = b->matches;
   mv.cap = S; mv.n_matches = b->n_matches; mv.K = S; mv.scores = nullptr; mv.scores_f64 = 0; mv.scores_pair_stride = 0;
-  const double* hyp_src = hyps;
-  const int32_t* n_hyp_src = n_hyp;
+  const double* hyp_src = pl.hyps;
+  const int32_t* n_hyp_src = pl.n_hyp;
   if (b->hyp_host_svd) { hyp_src = b->hyp_host_svd; n_hyp_src = nullptr; }
   else {
-    CoarseArgs cg{mv, b->dr_index, S, b->triplets, H, b->seed, hyps, n_hyp, scratch, bucket, cdf};
+    CoarseArgs cg{mv, b->dr_index, S, b->triplets, H, b->seed, pl.pair_base, pl.hyps, pl.n_hyp, pl.scratch, pl.bucket, pl.cdf};
     if (!b->triplets) {
       coarse_bucket_kernel<<<B, 256, 0, st>>>(cg);
       RR_LAUNCH_CHECK(c);
     } else {
-      RR_CUDA(c, cudaMemsetAsync(n_hyp, 0x7f, sizeof(int32_t) * B, st));     // "all H hypotheses valid"
+      RR_CUDA(c, cudaMemsetAsync(pl.n_hyp, 0x7f, sizeof(int32_t) * B, st));     // "all H hypotheses valid"
     }
     coarse_hyp_kernel<<<dim3((H + 63) / 64, B), 64, 0, st>>>(cg);
     RR_LAUNCH_CHECK(c);
   }
   RR_MARK(5);
-  // 6. score every hypothesis on all matches, keep the first best  (test/estimator.py:149-154,232-238 / :426-436)
-  if ((rc = score_and_select(c, mv, S, hyp_src, (long long)H * 12, nullptr, n_hyp_src, H, b->ird, partial, nullptr,
+  if ((rc = score_and_select(c, mv, S, hyp_src, (long long)H * 12, nullptr, n_hyp_src, H, b->ird, pl.partial, nullptr,
                              b->recall, b->best_overlap, B, st))) return rc;
   RR_MARK(6);
-  // 7. refine twice  (test/estimator.py:240-241 / :438-439)
   RefineArgs ra{};
   ra.mv = mv; ra.T_in = nullptr; ra.hyps = hyp_src; ra.hyp_pair_stride = (long long)H * 12; ra.order = nullptr;
   ra.best_id = b->recall; ra.rad0 = b->ird * 2.0; ra.rad1 = b->ird; ra.rounds = 2; ra.T_out = b->poses; ra.inlier_mask = nullptr; ra.mask_stride = S;
   refine_kernel<<<B, 512, 0, st>>>(ra);
   RR_LAUNCH_CHECK(c);
   RR_MARK(7);
-  if (c->timing) c->ev_valid = 1;
+  return ROREG_OK;
+}
+#undef RR_MARK
+
+int roreg_set_overlap(roreg_ctx* c, int enable) {
+  if (!c) return ROREG_ERR_ARG;
+  c->overlap = enable ? 1 : 0;
+  return ROREG_OK;
+}
+
+static int overlap_streams(roreg_ctx* c) {
+  if (c->s_tc) return ROREG_OK;
+  int lo = 0, hi = 0;
+  RR_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));          // lo = numerically largest = lowest priority
+  RR_CUDA(c, cudaStreamCreateWithPriority(&c->s_tc, cudaStreamNonBlocking, hi));
+  RR_CUDA(c, cudaStreamCreateWithPriority(&c->s_light, cudaStreamNonBlocking, lo));
+  RR_CUDA(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  for (int h = 0; h < 2; ++h) {
+    RR_CUDA(c, cudaEventCreateWithFlags(&c->ev_pool[h], cudaEventDisableTiming));
+    RR_CUDA(c, cudaEventCreateWithFlags(&c->ev_corr[h], cudaEventDisableTiming));
+    RR_CUDA(c, cudaEventCreateWithFlags(&c->ev_join[h], cudaEventDisableTiming));
+  }
+  return ROREG_OK;
+}
+
+int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
+  RR_ARG(c, b && b->desc && b->keys && b->pair_cloud && b->matches && b->n_matches && b->dr_index && b->poses &&
+                b->recall && b->best_overlap);
+  RR_ARG(c, b->B >= 1 && b->n >= 1 && b->keynum >= 1 && b->keynum <= b->n && b->max_iter >= 1 && b->ird > 0);
+  RR_ARG(c, b->sample || b->keynum == b->n);
+  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd) || b->estimator == 2);
+  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  // the two-stream schedule needs two sub-batches worth the launch overhead, no per-stage timing and the full pipeline
+  const bool overlapped = c->overlap && !c->timing && b->estimator != 2 && b->B >= 8 && !getenv("ROREG_NO_OVERLAP");
+  if (!overlapped) {
+    if ((rc = rr_ws_reserve(c, batch_ws_bytes(b, b->B)))) return rc;
+    BatchPlan pl;
+    batch_plan(b, 0, b->B, (char*)c->ws, &pl);
+    const bool mark = c->timing != 0;
+    if ((rc = batch_phase_pool(c, pl, st, mark))) return rc;
+    if ((rc = batch_phase_tc(c, pl, st, mark))) return rc;
+    if (b->estimator == 2) {                 // matcher + Des2R only: the caller generates hypotheses (ET network) and calls roreg_estimate_batch
+      if (mark) { for (int i = 5; i <= ROREG_N_STAGES; ++i) RR_CUDA(c, cudaEventRecord(c->ev[i], st)); c->ev_valid = 1; }
+      return ROREG_OK;
+    }
+    if ((rc = batch_phase_tail(c, pl, st, mark))) return rc;
+    if (mark) c->ev_valid = 1;
+    return ROREG_OK;
+  }
+  const int B0 = (b->B + 1) / 2, B1 = b->B - B0;
+  const size_t w0 = batch_ws_bytes(b, B0), w1 = batch_ws_bytes(b, B1);
+  if ((rc = rr_ws_reserve(c, w0 + w1 + 4096))) return rc;
+  if ((rc = overlap_streams(c))) return rc;
+  BatchPlan pl[2];
+  batch_plan(b, 0, B0, (char*)c->ws, &pl[0]);
+  batch_plan(b, B0, B1, (char*)c->ws + w0, &pl[1]);
+  // fork: both internal streams start after everything already enqueued on the caller's stream
+  RR_CUDA(c, cudaEventRecord(c->ev_fork, st));
+  RR_CUDA(c, cudaStreamWaitEvent(c->s_light, c->ev_fork, 0));
+  RR_CUDA(c, cudaStreamWaitEvent(c->s_tc, c->ev_fork, 0));
+  // s_light: P0 P1 ... ; s_tc: (P0) TC0 (P1) TC1 ; s_light: ... (TC0) T0 (TC1) T1
+  for (int h = 0; h < 2; ++h) {
+    if ((rc = batch_phase_pool(c, pl[h], c->s_light, false))) return rc;
+    RR_CUDA(c, cudaEventRecord(c->ev_pool[h], c->s_light));
+  }
+  for (int h = 0; h < 2; ++h) {
+    RR_CUDA(c, cudaStreamWaitEvent(c->s_tc, c->ev_pool[h], 0));
+    if ((rc = batch_phase_tc(c, pl[h], c->s_tc, false))) return rc;
+    RR_CUDA(c, cudaEventRecord(c->ev_corr[h], c->s_tc));
+  }
+  for (int h = 0; h < 2; ++h) {
+    RR_CUDA(c, cudaStreamWaitEvent(c->s_light, c->ev_corr[h], 0));
+    if ((rc = batch_phase_tail(c, pl[h], c->s_light, false))) return rc;
+  }
+  // join: later work on the caller's stream sees every result
+  RR_CUDA(c, cudaEventRecord(c->ev_join[0], c->s_tc));
+  RR_CUDA(c, cudaEventRecord(c->ev_join[1], c->s_light));
+  RR_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
+  RR_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
   return ROREG_OK;
 }
 

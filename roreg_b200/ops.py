@@ -50,6 +50,10 @@ class Context:
 
     STAGES = ("inv_pool", "nn", "compact", "group_corr", "hypotheses", "score_select", "refine")
 
+    def set_overlap(self, on):
+        """Two-stream schedule of register_batch (default off: it measured slower on a B200); results are identical either way."""
+        _lib.check(self.h, self.lib.roreg_set_overlap(self.h, int(on)), "roreg_set_overlap")
+
     def set_corr_mode(self, mode):
         _lib.check(self.h, self.lib.roreg_set_corr_mode(self.h, int(mode)), "roreg_set_corr_mode")
 

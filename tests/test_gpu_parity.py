@@ -374,6 +374,35 @@ def test_register_batch_tensor_core_nn(ctx, tables, mode):
         assert len(a ^ b) <= 4          # the two NN arithmetics may differ on a handful of near ties only
 
 
+@pytest.mark.parametrize("nn_mode,corr_mode", [(0, 0), (4, 3)])
+def test_register_batch_overlapped_schedule_equals_serial(tables, nn_mode, corr_mode):
+    """roreg_set_overlap: the two-stream schedule (two half-batches, stages overlapped) must return exactly what the serial
+    schedule returns - same kernels on the same pairs, device draws keyed by the pair's index in the whole batch."""
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    c.set_corr_mode(corr_mode)
+    prs = [synth.make_pair(400 + i, n=700) for i in range(9)]             # odd count: halves of 5 and 4 pairs
+    desc = c.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+    keys = c.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+    pc = c.dev(np.array([[2 * i, 2 * i + 1] for i in range(9)], np.int32))
+    res = []
+    for on in (False, True, True):
+        c.set_overlap(on)
+        o = c.register_batch(desc, keys, pc, max_iter=300, seed=11, nn_mode=nn_mode)
+        torch.cuda.synchronize()
+        res.append({k: _np(v).copy() for k, v in o.items()})
+    c.close()
+    for o in res[1:]:
+        assert np.array_equal(o["n_matches"], res[0]["n_matches"]) and np.array_equal(o["recall"], res[0]["recall"])
+        for i in range(9):
+            k = int(res[0]["n_matches"][i])
+            assert np.array_equal(o["matches"][i, :k], res[0]["matches"][i, :k])
+            assert np.array_equal(o["dr_index"][i, :k], res[0]["dr_index"][i, :k])
+        assert np.array_equal(o["poses"], res[0]["poses"])
+    for i, pr in enumerate(prs):
+        assert np.abs(res[1]["poses"][i][:3] - pr["gt"]).max() < 1e-2
+
+
 def test_fast_path_full_size_against_reference_arithmetic(ctx, tables):
     """BASELINE configs[1] size (5000 keypoints, 40 x 40 tiles, every persistent CTA sweeps many items): the default fast path
     (nn mode 4 + corr mode 3) against the reference-arithmetic kernels (nn mode 0 + corr mode 0) on the same two pairs:
