@@ -23,9 +23,11 @@
 //     - 0.8 instruction per element - and two small kernels finish it: best chunk per row, then the exact index
 //     among that group's 8 columns in the REFERENCE's float32 difference-form arithmetic (utils/knn_search.py:33-38);
 //   * reads operands from a tile-major, pre-swizzled image written by the prep kernel (exactly the bytes of the
-//     SWIZZLE_128B K-major shared-memory layout), so a tile is ONE contiguous cp.async.bulk - no tensor maps.
+//     K-major shared-memory layouts: a SWIZZLE_128B box + un-swizzled extension blocks), so a tile is ONE contiguous
+//     cp.async.bulk - no tensor maps; a streamed tile only moves the 20 KB its role needs, which leaves room for 9 stages
+//     (run 40: with 5 stages of 32 KB the 6300-clock copy latency under load bounded the tile rate at ~1300 clk).
 //
-//   warp 0      producer   32 KB bulk copies: stationary tile once per item, streaming tiles through 5 stages
+//   warp 0      producer   bulk copies: stationary tile (28 KB) once per item, streaming tiles (20 KB prefix) through 9 stages
 //   warp 1      MMA        8 x tcgen05.mma kind::f16 (M = N = 128, K = 16) per tile, 2 x (D1 | D2) in TMEM
 //   warps 2-9   epilogue   tcgen05.ld 32x32b.x32 -> FFMA combine -> column running max / chunk-row max
 #pragma once
@@ -34,10 +36,12 @@
 
 namespace roreg {
 
-constexpr int T4_TILE_BYTES = 2 * TC_BOX_BYTES;                  // [hi | lo'] box + extension box = 32 KB per 128-row tile
-constexpr int T4_STAGES = 5;
+constexpr int T4_EXT_BYTES = 128 * 32;                           // one extension block: 128 rows x 16 fp16 (K = 16), un-swizzled K-major
+constexpr int T4_TILE_BYTES = TC_BOX_BYTES + 3 * T4_EXT_BYTES;   // [hi | lo'] box (16 KB) + XA | XB1 | XB2 (4 KB each) = 28 KB per 128-row tile
+constexpr int T4_STREAM_BYTES = TC_BOX_BYTES + T4_EXT_BYTES;     // a streamed (row-role) tile needs only the prefix [hi | lo'] + XA = 20 KB
+constexpr int T4_STAGES = 9;
 constexpr int T4_THREADS = 64 + 256;
-constexpr int T4_SMEM_BYTES = T4_TILE_BYTES * (1 + T4_STAGES) + 2 * 4 * 64 * 8 /*column merge*/ + 1024 + 256;
+constexpr int T4_SMEM_BYTES = T4_TILE_BYTES + T4_STREAM_BYTES * T4_STAGES + 2 * 4 * 64 * 8 /*column merge*/ + 1024 + 256;   // 213 KB
 constexpr float T4_PAD_NORM = 30000.f;                           // half-norm of a padding row (fp16-representable): loses every comparison
 constexpr float T4_LO_SCALE = 2048.f, T4_LO_UNSCALE = 1.f / 2048.f;
 // kind::f16 (A, B = F16, K-major), D = f32, M = 128, N = 128
@@ -48,16 +52,26 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
                ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum) : "memory");
 }
 
+// K-major, no swizzle (CUTLASS cute/atom/mma_traits_sm100.hpp: Major-K INTERLEAVE = ((8,m),(T,2)):((1T,SBO),(1,LBO))): a K = 16 fp16
+// slice of an extension block is two 16-byte chunks per row; 8-row core matrices of 128 B, chunk 1 at +LBO = 128 B, the next 8
+// rows at +SBO = 256 B.  Descriptor: start >> 4 | LBO >> 4 << 16 | SBO >> 4 << 32 | version 1 | layout type 0.
+__device__ __forceinline__ uint64_t t4_desc_ext(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(128 >> 4) << 16) | ((uint64_t)(256 >> 4) << 32) | (1ull << 46);
+}
+// byte offset of 32-bit word w (fp16 columns 2w, 2w+1; w < 8) of row r inside an extension block
+__device__ __forceinline__ int t4_ext_off(int r, int w) { return (r >> 3) * 256 + (w >> 2) * 128 + (r & 7) * 16 + (w & 3) * 4; }
+
 // byte offset of fp16 element (r, k), k < 64, in a [128 x 128 B] K-major SWIZZLE_128B box:
 // 16-byte chunk (2k / 16) of row r sits at chunk position (2k / 16) ^ (r % 8)
 __device__ __forceinline__ int t4_sw128_h(int r, int k) { return r * 128 + ((((k >> 3) ^ (r & 7))) << 4) + ((k & 7) << 1); }
 
 // ---- prep: pooled features [B*2][S][32] -> tile images [B*2][NT][32 KB] ---------------------------------------
-// box 0, row r: hi[0..31] | lo'[0..31];  box 1, row r (64 fp16 columns):
-//   0..15  row-role extension     [-n1, 1, -n2, -n3, 1, 1, 0...]
-//   16..31 column-role, for D1    [ 1, -n1, 0...]
-//   32..47 column-role, for D2    [ 0, 0, 1, 1, -n2, -n3, 0...]
-// so that  ext_row . ext_col1 = -na1 - nb1  and  ext_row . ext_col2 = -(na2 + na3) - (nb2 + nb3).
+// tile = box 0 (SWIZZLE_128B, row r: hi[0..31] | lo'[0..31]) + three un-swizzled extension blocks of 16 fp16 columns:
+//   XA   row-role extension     [-n1, 1, -n2, -n3, 1, 1, 0...]
+//   XB1  column-role, for D1    [ 1, -n1, 0...]
+//   XB2  column-role, for D2    [ 0, 0, 1, 1, -n2, -n3, 0...]
+// so that  XA . XB1 = -na1 - nb1  and  XA . XB2 = -(na2 + na3) - (nb2 + nb3).  A streamed (row-role) tile is the 20 KB prefix
+// box 0 + XA; only the stationary (column-role) tile needs all 28 KB.
 // one warp emits one padded row rr of (pair, side) ps; lane holds x = feature[lane] (0 for a padding row rr >= S)
 __device__ __forceinline__ void t4_emit_row(uint8_t* __restrict__ img, long long ps, int rr, int S, int NT, int lane, float x) {
   const int t = rr >> 7, r = rr & 127;
@@ -79,15 +93,22 @@ __device__ __forceinline__ void t4_emit_row(uint8_t* __restrict__ img, long long
     const uint32_t word = lane < 16 ? (h0 | (h1 << 16)) : (l0 | (l1 << 16));
     *reinterpret_cast<uint32_t*>(tile + t4_sw128_h(r, 2 * lane)) = word;
   }
-  // extension box: lane writes columns 2*lane, 2*lane+1
-  __half e0 = zero, e1 = zero;
-  if (lane == 0) { e0 = __hneg(n1); e1 = one; }              // cols 0,1
-  else if (lane == 1) { e0 = __hneg(n2); e1 = __hneg(n3); }   // cols 2,3
-  else if (lane == 2) { e0 = one; e1 = one; }                // cols 4,5
-  else if (lane == 8) { e0 = one; e1 = __hneg(n1); }         // cols 16,17
-  else if (lane == 17) { e0 = one; e1 = one; }               // cols 34,35
-  else if (lane == 18) { e0 = __hneg(n2); e1 = __hneg(n3); }  // cols 36,37
-  *reinterpret_cast<__half2*>(tile + TC_BOX_BYTES + t4_sw128_h(r, 2 * lane)) = __halves2half2(e0, e1);
+  // extension blocks (un-swizzled): lanes 0..23 write word (lane & 7) of block lane >> 3:
+  //   XA  (row role)            [-n1, 1 | -n2, -n3 | 1, 1 | 0 ...]
+  //   XB1 (column role, for D1) [ 1, -n1 | 0 ...]
+  //   XB2 (column role, for D2) [ 0, 0 | 1, 1 | -n2, -n3 | 0 ...]
+  if (lane < 24) {
+    const int blk = lane >> 3, w = lane & 7;
+    __half e0 = zero, e1 = zero;
+    if (blk == 0) {
+      if (w == 0) { e0 = __hneg(n1); e1 = one; } else if (w == 1) { e0 = __hneg(n2); e1 = __hneg(n3); } else if (w == 2) { e0 = one; e1 = one; }
+    } else if (blk == 1) {
+      if (w == 0) { e0 = one; e1 = __hneg(n1); }
+    } else {
+      if (w == 1) { e0 = one; e1 = one; } else if (w == 2) { e0 = __hneg(n2); e1 = __hneg(n3); }
+    }
+    *reinterpret_cast<__half2*>(tile + TC_BOX_BYTES + blk * T4_EXT_BYTES + t4_ext_off(r, w)) = __halves2half2(e0, e1);
+  }
 }
 
 __global__ void __launch_bounds__(256) nn_tc4_prep_kernel(const float* __restrict__ inv, int S, int NT, long long total_rows,
@@ -200,19 +221,19 @@ template <bool TRACE>
 __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sB = smem;                                   // stationary tile (cloud 1 block), 32 KB
-  uint8_t* sA = smem + T4_TILE_BYTES;                   // T4_STAGES x 32 KB streaming tiles (cloud 0)
-  unsigned long long* cmg = reinterpret_cast<unsigned long long*>(smem + T4_TILE_BYTES * (1 + T4_STAGES));   // [2 halves][4 quadrants][64 columns]
+  uint8_t* sB = smem;                                   // stationary tile (cloud 1 block), 28 KB
+  uint8_t* sA = smem + T4_TILE_BYTES;                   // T4_STAGES x 20 KB streaming tiles (cloud 0)
+  unsigned long long* cmg = reinterpret_cast<unsigned long long*>(smem + T4_TILE_BYTES + T4_STREAM_BYTES * T4_STAGES);   // [2 halves][4 quadrants][64 columns]
   uint64_t* bars = reinterpret_cast<uint64_t*>(cmg + 2 * 4 * 64);
-  // barriers: 0 b_full, 1 b_empty, 2..6 a_full, 7..11 a_empty, 12..13 tmem_full, 14..15 tmem_empty
+  // barriers: 0 b_full, 1 b_empty, 2..10 a_full, 11..19 a_empty, 20..21 tmem_full, 22..23 tmem_empty
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
     mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
-    for (int s = 0; s < T4_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(7 + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR(12 + s), 1); mbar_init(BAR(14 + s), 256); }
+    for (int s = 0; s < T4_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(2 + T4_STAGES + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(2 + 2 * T4_STAGES + s), 1); mbar_init(BAR(4 + 2 * T4_STAGES + s), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -242,21 +263,22 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
         b_phase ^= 1;
         for (int t = 0; t < NT; ++t, ++it_a) {
           const int st = it_a % T4_STAGES; const uint32_t ph = (it_a / T4_STAGES) & 1;
-          t4_wait(BAR(7 + st), ph ^ 1);
+          t4_wait(BAR(2 + T4_STAGES + st), ph ^ 1);
           T4_TRACE(it_a, 0);
-          mbar_expect_tx(BAR(2 + st), T4_TILE_BYTES);
-          t4_bulk(smem_u32(sA + st * T4_TILE_BYTES), imgA + (long long)t * T4_TILE_BYTES, T4_TILE_BYTES, BAR(2 + st));
+          mbar_expect_tx(BAR(2 + st), T4_STREAM_BYTES);
+          t4_bulk(smem_u32(sA + st * T4_STREAM_BYTES), imgA + (long long)t * T4_TILE_BYTES, T4_STREAM_BYTES, BAR(2 + st));
         }
       }
     }
   } else if (warp == 1) {
     // the whole warp walks the loop (no divergent region around the tcgen05 instructions), one elected lane issues
     uint32_t it_a = 0, it_t = 0, b_phase = 0;
-    // descriptor low words (start address >> 4 | LBO field); the high word (SBO = 1024 B, version 1, SWIZZLE_128B) is a constant.
-    // column-role operands (stationary): hi at +0/+32, lo' at +64/+96 of box 0; extension vectors at +32 (D1) / +64 (D2) of box 1
+    // box-0 descriptors: low word (start address >> 4 | LBO field) + a constant high word (SBO = 1024 B, version 1, SWIZZLE_128B);
+    // hi at +0/+32 B, lo' at +64/+96 B of a row.  Extension blocks: un-swizzled descriptors (t4_desc_ext).
     constexpr uint64_t DHI = ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
     const uint32_t b0 = ((smem_u32(sB) >> 4) & 0x3FFF) | (1u << 16);
     const uint32_t a00 = ((smem_u32(sA) >> 4) & 0x3FFF) | (1u << 16);
+    const uint64_t bx1 = t4_desc_ext(smem_u32(sB) + TC_BOX_BYTES + T4_EXT_BYTES), bx2 = t4_desc_ext(smem_u32(sB) + TC_BOX_BYTES + 2 * T4_EXT_BYTES);
     auto D = [&](uint32_t lo) -> uint64_t { return DHI | lo; };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       t4_wait(BAR(0), b_phase); b_phase ^= 1;
@@ -265,21 +287,22 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
         const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
         t4_wait(BAR(2 + st), ph);
         if (lane == 0) T4_TRACE(it_t, 1);
-        t4_wait(BAR(14 + acc), tph ^ 1);
+        t4_wait(BAR(4 + 2 * T4_STAGES + acc), tph ^ 1);
         if (lane == 0) T4_TRACE(it_t, 2);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a0 = a00 + st * (T4_TILE_BYTES >> 4);            // 16-byte units: hi +0/+2, lo' +4/+6, extension box +1024
+        const uint32_t a0 = a00 + st * (T4_STREAM_BYTES >> 4);          // 16-byte units: hi +0/+2, lo' +4/+6
+        const uint64_t ax = t4_desc_ext(smem_u32(sA) + st * T4_STREAM_BYTES + TC_BOX_BYTES);
         const uint32_t d1 = tmem_base + acc * 256, d2 = d1 + 128;
-        t4_umma(d1, D(a0 + 1024), D(b0 + 1024 + 2), 0u);                // -na1 - nb1
+        t4_umma(d1, ax, bx1, 0u);                                       // -na1 - nb1
         t4_umma(d1, D(a0), D(b0), 1u);                                  // hi.hi
         t4_umma(d1, D(a0 + 2), D(b0 + 2), 1u);
-        t4_umma(d2, D(a0 + 1024), D(b0 + 1024 + 4), 0u);                // -(na2 + na3) - (nb2 + nb3)
+        t4_umma(d2, ax, bx2, 0u);                                       // -(na2 + na3) - (nb2 + nb3)
         t4_umma(d2, D(a0 + 4), D(b0), 1u);                              // lo'.hi
         t4_umma(d2, D(a0 + 6), D(b0 + 2), 1u);
         t4_umma(d2, D(a0), D(b0 + 4), 1u);                              // hi.lo'
         t4_umma(d2, D(a0 + 2), D(b0 + 6), 1u);
-        t4_commit(BAR(7 + st));
-        t4_commit(BAR(12 + acc));
+        t4_commit(BAR(2 + T4_STAGES + st));
+        t4_commit(BAR(2 + 2 * T4_STAGES + acc));
         if (lane == 0) T4_TRACE(it_t, 3);
       }
       t4_commit(BAR(1));
@@ -302,7 +325,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
       uint8_t* rg = a.rowgid + ((long long)p * 2 * NT + 2 * j + hf) * Sp;
       for (int t = 0; t < NT; ++t, ++it_t) {
         const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
-        t4_wait(BAR(12 + acc), tph);
+        t4_wait(BAR(2 + 2 * T4_STAGES + acc), tph);
         if (threadIdx.x == 64) T4_TRACE(it_t, 4);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256 + hf * 64;
@@ -317,7 +340,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
           asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
           if (half == 1) {
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(BAR(14 + acc));                 // accumulators free: the MMAs of tile t+2 may start
+            mbar_arrive(BAR(4 + 2 * T4_STAGES + acc));  // accumulators free: the MMAs of tile t+2 may start
             if (threadIdx.x == 64) T4_TRACE(it_t, 5);
           }
           // column direction: running maximum of -d^2/2 over the rows this lane sees; strict '>' + increasing t = first row wins ties.
