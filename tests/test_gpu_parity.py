@@ -516,6 +516,38 @@ def test_empty_and_tiny_inputs(ctx, tables):
     assert int(best.item()) == 0 and float(ov.item()) == 1.0
 
 
+def test_fast_modes_tiny_and_degenerate_inputs(tables):
+    """nn mode 4 / corr mode 3 on inputs smaller than one tile, on a batch where one pair has nothing in common (few, random
+    matches: a short Des2R item list that every warp role must walk identically) and on a single-pair batch."""
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    c.set_corr_mode(3)
+    rng = np.random.default_rng(21)
+    # tiny clouds: 5 and 130 keypoints (less than / just more than one 128-row tile)
+    for n in (5, 130):
+        f0 = rng.standard_normal((n, 32)).astype(np.float32); f0 /= np.linalg.norm(f0, axis=1, keepdims=True)
+        f1 = f0[rng.permutation(n)] + 0.01 * rng.standard_normal((n, 32)).astype(np.float32)
+        f1 = (f1 / np.linalg.norm(f1, axis=1, keepdims=True)).astype(np.float32)
+        m, cnt, nn01, nn10 = c.mutual_match(c.dev(f0), c.dev(f1), 4)
+        torch.cuda.synchronize()
+        _check_nn_tc(_np(nn01), f1, f0); _check_nn_tc(_np(nn10), f0, f1)
+        assert int(cnt.item()) >= n - 2
+    # a pair whose clouds have nothing in common next to a normal pair
+    good = synth.make_pair(77, n=600)
+    junk0 = rng.standard_normal((600, 32, 60)).astype(np.float32); junk0 /= np.linalg.norm(junk0, axis=1, keepdims=True)
+    junk1 = rng.standard_normal((600, 32, 60)).astype(np.float32); junk1 /= np.linalg.norm(junk1, axis=1, keepdims=True)
+    desc = c.dev(np.stack([good["feats0"], good["feats1"], junk0, junk1]))
+    keys = c.dev(np.stack([good["keys0"], good["keys1"], good["keys0"], good["keys1"]]), torch.float64)
+    for pcs in ([[0, 1], [2, 3]], [[0, 1]]):
+        o = c.register_batch(desc, keys, c.dev(np.array(pcs, np.int32)), max_iter=200, seed=2, nn_mode=4)
+        torch.cuda.synchronize()
+        assert np.abs(_np(o["poses"][0])[:3] - good["gt"]).max() < 1e-2
+        k = int(o["n_matches"][0])
+        pps, _ = O.mutual_run(good["feats0"], good["feats1"])
+        assert abs(k - pps.shape[0]) <= 2
+    c.close()
+
+
 def test_mutual_plugin_raises_like_reference_on_no_matches(tmp_path):
     """np.concatenate([]) -> ValueError in the reference when no mutual pair exists (test/matcher.py:106)."""
     import types

@@ -118,3 +118,17 @@ def test_match_ot_against_reference_outputs(tables):
     for (id0, id1), (m, s) in zip(ds.pair_ids, out):
         assert np.array_equal(m, z[f"match_{id0}-{id1}"])
         assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-4          # stated tolerance; matches are bit-exact
+
+
+def test_torch_mirror_equals_numpy_oracle():
+    """oracle/torch_mirror.py (the reference's tensor operations on CPU, used only for bench.py's `reference_ops` timing) returns
+    what the NumPy restatement returns: same matches, same coarse-rotation indices, a pose at the planted ground truth."""
+    from oracle import torch_mirror as TM
+    from roreg_b200 import group, synth
+    t = group.load()
+    pr = synth.make_pair(5, n=500)
+    T, pps, dr = TM.register_pair(pr, t.perm, 200, 0.1, 0)
+    p2, _ = O.mutual_run(pr["feats0"], pr["feats1"])
+    assert np.array_equal(pps, p2)
+    assert np.array_equal(dr, O.rindex(pr["feats0"], pr["feats1"], p2, t.perm))
+    assert np.abs(T[:3] - pr["gt"]).max() < 1e-2
