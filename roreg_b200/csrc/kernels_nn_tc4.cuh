@@ -366,18 +366,16 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
         if (threadIdx.x == 64) T4_TRACE(it_t, 7);
       }
       // ---- end of the sweep: reduce the column candidates over the 128 lanes -------------------------------
-      // lexicographic (largest value, smallest row); row = tile * 128 + row_in_tile
+      // lexicographic (largest value, smallest row); row = tile * 128 + row_in_tile.  Two warp-wide integer reductions per column
+      // (redux.sync on the order-preserving key, then on the rows attaining it): the shuffle butterfly this replaces cost
+      // 18-33 k clocks per item - a third of the sweep itself (profiles/r01_run40_nn4_timeline.txt, tiles 39 -> 40).
 #pragma unroll
       for (int e = 0; e < 64; ++e) {
-        float v = cmax[e];
-        uint32_t row = ((ctile[e >> 2] >> (8 * (e & 3))) & 0xff) * TC_BM + row_in_tile;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          const float vo = __shfl_xor_sync(0xffffffffu, v, o);
-          const uint32_t ro = __shfl_xor_sync(0xffffffffu, row, o);
-          if (vo > v || (vo == v && ro < row)) { v = vo; row = ro; }
-        }
-        if (lane == (e & 31)) cmg[(hf * 4 + q) * 64 + e] = ((unsigned long long)t4_ord(v) << 32) | (0xffffffffu - row);
+        const uint32_t key = t4_ord(cmax[e] + 0.f);     // + 0.f: -0 and +0 compare equal, as in float arithmetic
+        const uint32_t row = ((ctile[e >> 2] >> (8 * (e & 3))) & 0xff) * TC_BM + row_in_tile;
+        const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
+        const uint32_t rmin = __reduce_min_sync(0xffffffffu, key == kmax ? row : 0xffffffffu);
+        if (lane == (e & 31)) cmg[(hf * 4 + q) * 64 + e] = ((unsigned long long)kmax << 32) | (0xffffffffu - rmin);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       {
