@@ -28,7 +28,7 @@
 //     (run 40: with 5 stages of 32 KB the 6300-clock copy latency under load bounded the tile rate at ~1300 clk).
 //
 //   warp 0      producer   bulk copies: stationary tile (28 KB) once per item, streaming tiles (20 KB prefix) through 9 stages
-//   warp 1      MMA        8 x tcgen05.mma kind::f16 (M = N = 128, K = 16) per tile, 2 x (D1 | D2) in TMEM
+//   warps 1,10  MMA        8 x tcgen05.mma kind::f16 (M = N = 128, K = 16) per tile, 2 x (D1 | D2) in TMEM; one issuing warp per accumulator pair
 //   warps 2-9   epilogue   tcgen05.ld 32x32b.x32 -> FFMA combine -> column running max / chunk-row max
 #pragma once
 #include <cuda_fp16.h>
@@ -40,7 +40,7 @@ constexpr int T4_EXT_BYTES = 128 * 32;                           // one extensio
 constexpr int T4_TILE_BYTES = TC_BOX_BYTES + 3 * T4_EXT_BYTES;   // [hi | lo'] box (16 KB) + XA | XB1 | XB2 (4 KB each) = 28 KB per 128-row tile
 constexpr int T4_STREAM_BYTES = TC_BOX_BYTES + T4_EXT_BYTES;     // a streamed (row-role) tile needs only the prefix [hi | lo'] + XA = 20 KB
 constexpr int T4_STAGES = 9;
-constexpr int T4_THREADS = 64 + 256;
+constexpr int T4_THREADS = 64 + 256 + 32;                        // producer, MMA issuer A, 8 epilogue warps, MMA issuer B
 constexpr int T4_SMEM_BYTES = T4_TILE_BYTES + T4_STREAM_BYTES * T4_STAGES + 2 * 4 * 64 * 8 /*column merge*/ + 1024 + 256;   // 213 KB
 constexpr float T4_PAD_NORM = 30000.f;                           // half-norm of a padding row (fp16-representable): loses every comparison
 constexpr float T4_LO_SCALE = 2048.f, T4_LO_UNSCALE = 1.f / 2048.f;
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   if (threadIdx.x == 0) {
-    mbar_init(BAR(0), 1); mbar_init(BAR(1), 1);
+    mbar_init(BAR(0), 1); mbar_init(BAR(1), 2);         // b_empty: one commit per MMA-issuing warp
     for (int s = 0; s < T4_STAGES; ++s) { mbar_init(BAR(2 + s), 1); mbar_init(BAR(2 + T4_STAGES + s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(2 + 2 * T4_STAGES + s), 1); mbar_init(BAR(4 + 2 * T4_STAGES + s), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -270,8 +270,13 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
         }
       }
     }
-  } else if (warp == 1) {
-    // the whole warp walks the loop (no divergent region around the tcgen05 instructions), one elected lane issues
+  } else if (warp == 1 || warp == 10) {
+    // Two MMA-issuing warps, one per accumulator pair: warp 1 takes the even tiles of the CTA's tile sequence, warp 10 the odd
+    // ones.  The serial per-tile loop of a single issuer (waits, descriptor set-up, 8 issues that each block for the 64
+    // tensor clocks of the previous one, 2 commits) paced the kernel at ~1300 clk per tile (run 40 timeline) while the tensor
+    // pipe needs 512; with two issuers the loops overlap.  The whole warp walks the loop (no divergent region around the
+    // tcgen05 instructions), one elected lane issues.
+    const uint32_t mine = (warp == 1) ? 0u : 1u;
     uint32_t it_a = 0, it_t = 0, b_phase = 0;
     // box-0 descriptors: low word (start address >> 4 | LBO field) + a constant high word (SBO = 1024 B, version 1, SWIZZLE_128B);
     // hi at +0/+32 B, lo' at +64/+96 B of a row.  Extension blocks: un-swizzled descriptors (t4_desc_ext).
@@ -283,6 +288,7 @@ __global__ void __launch_bounds__(T4_THREADS, 1) nn_tc4_kernel(NNTc4Args a) {
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       t4_wait(BAR(0), b_phase); b_phase ^= 1;
       for (int t = 0; t < NT; ++t, ++it_a, ++it_t) {
+        if ((it_t & 1u) != mine) continue;
         const int st = it_a % T4_STAGES; const uint32_t ph = (it_a / T4_STAGES) & 1;
         const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
         t4_wait(BAR(2 + st), ph);
