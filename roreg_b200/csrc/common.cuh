@@ -87,6 +87,15 @@ struct rr_arena {
 };
 static inline size_t rr_align(size_t b) { return (b + 255) & ~size_t(255); }
 
+// cudaFuncSetAttribute applies to the CURRENT device only: remember per device (bit d of a process-wide mask), not per process
+static inline bool rr_first_use_on_device(unsigned long long* mask, int device) {
+  const unsigned long long bit = 1ull << (device & 63);
+  if (*mask & bit) return false;
+  *mask |= bit;
+  return true;
+}
+
+
 #ifdef __CUDACC__
 __device__ __forceinline__ float4 ldg_stream4(const float4* p) {
   float4 r;

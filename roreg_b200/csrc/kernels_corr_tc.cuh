@@ -285,10 +285,9 @@ __global__ void __launch_bounds__(CtThreads<CW>::value, 1) group_corr_tc_kernel(
 
 template <int CW>
 static inline int group_corr_tc_launch_cw(roreg_ctx* c, const CorrTcArgs& a, int grid, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc_kernel<CW>, cudaFuncAttributeMaxDynamicSharedMemorySize, CT_SMEM_BYTES));
-    attr_set = true;
   }
   group_corr_tc_kernel<CW><<<grid, CtThreads<CW>::value, CT_SMEM_BYTES, st>>>(a);
   RR_LAUNCH_CHECK(c);

@@ -243,12 +243,11 @@ __global__ void __launch_bounds__(C2_THREADS, 2) group_corr_tc2_kernel(CorrTcArg
 static inline int group_corr_tc2_launch(roreg_ctx* c, const float* X, const float* Y, CorrTcArgs a, cudaStream_t st) {
   RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   a.X = X; a.Y = Y;
-  static bool attr_set = false;
+  static unsigned long long attr_mask = 0;
   static int ctas_per_sm = 2;
-  if (!attr_set) {
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc2_kernel<false, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, C2_SMEM_BYTES));
     if (const char* e = getenv("ROREG_DEBUG_CORR_CTAS")) { const int v = atoi(e); if (v >= 1 && v <= 2) ctas_per_sm = v; }
-    attr_set = true;
   }
   const long long items = (long long)a.B * a.K;
   const long long cap = (long long)c->sm_count * ctas_per_sm;

@@ -307,11 +307,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
 static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const float* Y, CorrTcArgs a, cudaStream_t st) {
   RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   a.X = X; a.Y = Y; a.trace = nullptr;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
-    attr_set = true;
   }
   const long long items = (long long)a.B * ((a.K + 1) / 2);
   RR_ARG(c, items < (1LL << 31));

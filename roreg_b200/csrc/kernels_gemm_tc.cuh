@@ -216,10 +216,9 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   if ((rc = gemm_make_map(c, &mAl, A_lo ? A_lo : A_hi, a.R, a.Kdim, GM_BM))) return rc;
   if ((rc = gemm_make_map(c, &mWh, W_hi, w_rows, a.Kdim, a.NT))) return rc;
   if ((rc = gemm_make_map(c, &mWl, W_lo ? W_lo : W_hi, w_rows, a.Kdim, a.NT))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
-    attr_set = true;
   }
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const long long tiles = (long long)n_mt * a.n_ntiles;

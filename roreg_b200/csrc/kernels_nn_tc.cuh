@@ -265,10 +265,9 @@ static inline int nn_tc_launch_both(roreg_ctx* c, const float* inv, int S, int B
   int rc;
   if ((rc = nn_tc_make_map(c, &mA, Ahat, rows))) return rc;
   if ((rc = nn_tc_make_map(c, &mB, Bhat, rows))) return rc;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES));
-    attr_set = true;
   }
   const int nrb = (S + TC_BM - 1) / TC_BM;
   const int items = B * 2 * nrb;
@@ -487,10 +486,9 @@ static inline int nn_tc2_launch_both(roreg_ctx* c, const float* inv, int S, int 
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(H) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    attr_set = true;
   }
   const int nrb = (S + TC_BM - 1) / TC_BM;
   const int items = B * 2 * nrb;
@@ -708,10 +706,9 @@ static inline int nn_tc3_launch_both(roreg_ctx* c, const float* inv, int S, int 
                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(c->err, sizeof(c->err), "cuTensorMapEncodeTiled(H) failed (%d)", (int)r); return ROREG_ERR_CUDA; }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES));
-    attr_set = true;
   }
   const int nrb = (S + TC_BM - 1) / TC_BM;
   const int items = B * nrb;

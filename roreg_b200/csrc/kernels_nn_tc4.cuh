@@ -477,11 +477,10 @@ static inline int nn_tc4_launch_both(roreg_ctx* c, const float* inv, int S, int 
     nn_tc4_prep_kernel<<<(unsigned)((total_rows / 4 + 7) / 8), 256, 0, st>>>(inv, S, NT, total_rows, img);
     RR_LAUNCH_CHECK(c);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  static unsigned long long attr_mask = 0;
+  if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
     RR_CUDA(c, cudaFuncSetAttribute(nn_tc4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T4_SMEM_BYTES));
-    attr_set = true;
   }
   const int items = B * NT;
   const int grid = items < c->sm_count ? items : c->sm_count;
