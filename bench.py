@@ -82,6 +82,38 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local):
+    """Multi-rank runs only: keep this rank's threads - hence the first touch of its pinned host buffers - on the NUMA node of its
+    GPU (sysfs numa_node of the GPU's PCI device), so that 8 ranks do not pull 8 x 55 GB/s across the socket interconnect.
+    Returns the previous affinity mask (restored before the CPU baseline) or None when anything is unavailable."""
+    if os.environ.get("ROREG_BENCH_NUMA", "1") == "0":
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:                       # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        old = os.sched_getaffinity(0)
+        cpus &= old
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return old
+    except Exception:
+        return None
+
+
 def make_inputs(B, n, rank):
     from roreg_b200 import synth
     prs = [synth.make_pair(1000 * (rank + 1) + p, n=n) for p in range(B)]
@@ -211,6 +243,7 @@ def main():
     ctx.set_corr_mode(args.corr_mode)
     B, n, H = args.pairs_per_step, args.n, args.max_iter
     prs, desc_h, keys_h, pc_h = make_inputs(B, n, rank)
+    old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
     desc_pin = torch.from_numpy(desc_h).pin_memory(); keys_pin = torch.from_numpy(keys_h).pin_memory()
     pc = ctx.dev(pc_h)
     dev = ctx.device
@@ -406,6 +439,11 @@ def main():
                         "launch stream in a serial replay of the timed steps (the timed region itself overlaps the stages of two "
                         "half-batches on two streams: value / n_gpus vs serial_schedule_pairs_per_s is what the overlap buys)"}
 
+    if old_affinity is not None:
+        try:
+            os.sched_setaffinity(0, old_affinity)
+        except Exception:
+            pass
     if rank == 0:
         cb = cpu_baseline(prs, min(args.cpu_sample_pairs, B), H, 0.1, args.cpu_seconds) if (world == 1 and args.cpu_sample_pairs > 0) else None
         line = {"metric": "pair registrations/sec (5000 kpt, 60-rot)", "value": value, "unit": "pairs/s", "n_gpus": world,
