@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "4")),
                     help="0 = float32 difference form (reference arithmetic), 1-3 = tcgen05 3xTF32 Gram variants, 4 = one fp16 two-accumulator Gram per pair (default)")
+    ap.add_argument("--score-mode", type=int, default=int(os.environ.get("ROREG_SCORE_MODE", "0")),
+                    help="one-shot scoring arithmetic: 0 float64 (default), 1 float32 pre-filter + exact float64 re-check")
     ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "3")),
                     help="0 = FP32 CUDA-core Gram, 1-2 = tcgen05 3xTF32 Gram, 3 = fp16 two-accumulator Gram, operands from registers (default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
@@ -241,6 +243,8 @@ def main():
     torch.cuda.set_device(local)
     ctx = ops.Context(local)
     ctx.set_corr_mode(args.corr_mode)
+    if args.score_mode:
+        ctx.set_score_mode(args.score_mode)
     B, n, H = args.pairs_per_step, args.n, args.max_iter
     prs, desc_h, keys_h, pc_h = make_inputs(B, n, rank)
     old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
@@ -458,7 +462,7 @@ def main():
                                       "access pattern of the reference's test sets; the plugin's CloudCache); the headline e2e above uploads "
                                       "both clouds for every single pair"},
                 "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
-                "nn_mode": args.nn_mode, "corr_mode": args.corr_mode}
+                "nn_mode": args.nn_mode, "corr_mode": args.corr_mode, "score_mode": args.score_mode}
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

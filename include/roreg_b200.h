@@ -227,6 +227,11 @@ int roreg_set_timing(roreg_ctx* ctx, int enable);
  * (roreg_set_timing) and estimator == 2 always use the serial schedule.  Results are identical; on a B200 the serial
  * schedule measured faster, hence the default.                                                          */
 int roreg_set_overlap(roreg_ctx* ctx, int enable);
+/* Arithmetic of the one-shot scoring inside roreg_ransac_oneshot / roreg_register_batch (test/estimator.py:377-382).
+ * 0 (default): every point test in float64, as the reference.  1: float32 pre-filter - a test is decided in float32 when its
+ * squared distance is outside [ird^2 - m, ird^2 + m] (m = a rigorous bound of the float32 evaluation error, kernels_ransac.cuh)
+ * and repeated in float64 otherwise; decisions and sums are identical to mode 0 by construction.                      */
+int roreg_set_score_mode(roreg_ctx* ctx, int mode);
 int roreg_get_stage_ms(roreg_ctx* ctx, float* ms_host);
 
 #ifdef __cplusplus

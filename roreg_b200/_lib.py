@@ -61,6 +61,7 @@ SIGNATURES = {
     "roreg_estimate_batch": (_i, [_p, C.POINTER(RoregBatch), _p, _p, _p]),
     "roreg_set_timing": (_i, [_p, _i]),
     "roreg_set_overlap": (_i, [_p, _i]),
+    "roreg_set_score_mode": (_i, [_p, _i]),
     "roreg_get_stage_ms": (_i, [_p, C.POINTER(C.c_float)]),
 }
 

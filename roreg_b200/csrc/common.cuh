@@ -23,6 +23,7 @@ struct roreg_ctx {
   size_t ws_bytes;
   int64_t launches;
   int corr_mode;                  // 0 = FP32 CUDA-core Gram, 1 / 2 = tcgen05 3xTF32 Gram, 2-match / 1-match items (roreg_set_corr_mode)
+  int score_mode;                 // 0 = float64 one-shot scoring, 1 = float32 pre-filter + exact float64 re-check (roreg_set_score_mode)
   int timing;                     // roreg_set_timing: record an event after every stage of roreg_register_batch
   cudaEvent_t ev[ROREG_N_STAGES + 1];
   int ev_valid;

@@ -205,6 +205,7 @@ struct ScoreArgs {
   int H; double r2;
   double* partial;                                 // [B][tiles][H]
   int tiles;
+  double r;                                        // sqrt(r2), score mode 1 only
 };
 
 __global__ void __launch_bounds__(256) ransac_score_kernel(ScoreArgs a) {
@@ -239,6 +240,117 @@ __global__ void __launch_bounds__(256) ransac_score_kernel(ScoreArgs a) {
       const bool in = is_inlier(T, &sk[k][0], &sk[k][3], a.r2);
       acc += in ? sk[k][6] : 0.0;
     }
+  }
+  a.partial[((long long)p * a.tiles + tile) * a.H + h] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// score mode 1 (roreg_set_score_mode, opt-in): float32 pre-filter with an exact float64 re-check.  Same grid, same partial sums,
+// same decisions as ransac_score_kernel: every point test is first evaluated in float32 (15 FP32-pipe operations instead of 20
+// FP64-pipe ones) and compared against [r2 - m, r2 + m]; only a test that lands inside the band is repeated in float64 with
+// is_inlier().  m bounds |s32 - d2| for every d2 on the wrong side of r2 (u = 2^-24, T = [R|t], a = k0_i, b = k1_i):
+//   x32_c = fma(R_c0,b_0, fma(R_c1,b_1, fma(R_c2,b_2,t_c)))  =>  |x32_c - x_c| <= 6u (rowsum|R| * max|b| + max|t|)   (3 roundings + 3 input
+//   d32_c = a_c - x32_c                                       =>  |d32_c - d_c| <= E + u|d_c|,  E = u (max|a| + 6 (...))    conversions)
+//   s32   = fma(d_z,d_z, fma(d_y,d_y, d_x*d_x))               =>  |s32 - d2|    <= 2 sqrt(3) E d + 4 E^2 + 6 u d2
+// The right-hand side grows more slowly than d2 itself, so evaluated at d = r it covers both directions (a true inlier cannot
+// read above r2 + m, a true outlier cannot read below r2 - m); the kernel uses 2 m.  NaN / inf hypotheses fail both float
+// comparisons and take the float64 path.  max|a|, max|b| are per tile (block reduction while staging), the T terms per thread.
+// ---------------------------------------------------------------------------------------------
+__device__ __noinline__ bool is_inlier_recheck(const double* __restrict__ Tp, const double* pt, double r2) {
+  double T[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) T[j] = Tp[j];
+  return is_inlier(T, pt, pt + 3, r2);
+}
+
+__global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a) {
+  __shared__ double sk[RR_SCORE_TILE][7];
+  __shared__ float4 sa[RR_SCORE_TILE], sb[RR_SCORE_TILE];
+  __shared__ uint32_t smax[2][8];
+  const int p = blockIdx.z, tile = blockIdx.y, tid = threadIdx.x;
+  const int K = mv_count(a.mv, p);
+  const int k_begin = tile * RR_SCORE_TILE;
+  const int h = blockIdx.x * 256 + tid;
+  const int H = a.n_hyp ? min(a.H, a.n_hyp[p]) : a.H;
+  if (k_begin >= K) {
+    if (h < a.H) a.partial[((long long)p * a.tiles + tile) * a.H + h] = 0.0;
+    return;
+  }
+  const int cnt = min(RR_SCORE_TILE, K - k_begin);
+  float am = 0.f, bm = 0.f;
+  if (tid < cnt) {
+    double x[3], y[3], s;
+    mv_load(a.mv, p, k_begin + tid, x, y, s);
+    sk[tid][0] = x[0]; sk[tid][1] = x[1]; sk[tid][2] = x[2];
+    sk[tid][3] = y[0]; sk[tid][4] = y[1]; sk[tid][5] = y[2]; sk[tid][6] = s;
+    sa[tid] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
+    sb[tid] = make_float4((float)y[0], (float)y[1], (float)y[2], 0.f);
+    am = __double2float_ru(fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2]))));
+    bm = __double2float_ru(fmax(fabs(y[0]), fmax(fabs(y[1]), fabs(y[2]))));
+    if (!(am == am)) am = __int_as_float(0x7f800000);          // NaN coordinates: widen the band to everything
+    if (!(bm == bm)) bm = __int_as_float(0x7f800000);
+  }
+  // non-negative floats order like their bit patterns
+  const uint32_t wa = __reduce_max_sync(0xffffffffu, __float_as_uint(am)), wb = __reduce_max_sync(0xffffffffu, __float_as_uint(bm));
+  if ((tid & 31) == 0) { smax[0][tid >> 5] = wa; smax[1][tid >> 5] = wb; }
+  __syncthreads();
+  if (h >= a.H) return;
+  double acc = 0.0;
+  if (h < H) {
+    uint32_t ua = 0, ub = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { ua = max(ua, smax[0][w]); ub = max(ub, smax[1][w]); }
+    const double Amax = (double)__uint_as_float(ua), Bmax = (double)__uint_as_float(ub);
+    const long long src = a.order ? a.order[h] : h;
+    const double* Tp = a.hyps + p * a.hyp_pair_stride + src * 12;
+    float T[12];
+    double rrow = 0.0, tmax = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < 3; ++cc) {
+      const double r0 = Tp[4 * cc], r1 = Tp[4 * cc + 1], r2_ = Tp[4 * cc + 2], t = Tp[4 * cc + 3];
+      T[4 * cc] = (float)r0; T[4 * cc + 1] = (float)r1; T[4 * cc + 2] = (float)r2_; T[4 * cc + 3] = (float)t;
+      rrow = fmax(rrow, fabs(r0) + fabs(r1) + fabs(r2_));
+      tmax = fmax(tmax, fabs(t));
+    }
+    const double u = 5.9604644775390625e-8;                                    // 2^-24
+    const double E = u * (Amax + 6.0 * (rrow * Bmax + tmax));
+    const double m = 2.0 * (3.4641016151377549 * E * a.r + 4.0 * E * E + 6.0 * u * a.r2);
+    // NaN in T (fmax drops NaN operands) must reach the float64 path: the float products below are NaN then, both comparisons false
+    const float lo = __double2float_rd(a.r2 - m), hi = __double2float_ru(a.r2 + m);
+    const bool weighted = a.mv.scores != nullptr;
+    int n_in = 0;
+    auto dist2 = [&](int k) -> float {
+      const float4 pa = sa[k], pb = sb[k];
+      const float x = fmaf(T[0], pb.x, fmaf(T[1], pb.y, fmaf(T[2], pb.z, T[3])));
+      const float y = fmaf(T[4], pb.x, fmaf(T[5], pb.y, fmaf(T[6], pb.z, T[7])));
+      const float z = fmaf(T[8], pb.x, fmaf(T[9], pb.y, fmaf(T[10], pb.z, T[11])));
+      const float dx = pa.x - x, dy = pa.y - y, dz = pa.z - z;
+      return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+    };
+    auto count = [&](int k, bool in) {
+      if (weighted) { if (in) acc += sk[k][6]; }      // same order of float64 additions as ransac_score_kernel
+      else n_in += in ? 1 : 0;
+    };
+    int k = 0;
+    for (; k + 4 <= cnt; k += 4) {                    // four tests per branch: the band is hit by ~1e-4 of the tests
+      float s2[4]; bool in[4]; bool amb = false;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { s2[j] = dist2(k + j); in[j] = s2[j] < lo; amb |= !in[j] && !(s2[j] > hi); }
+      if (amb) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (!in[j] && !(s2[j] > hi)) in[j] = is_inlier_recheck(Tp, &sk[k + j][0], a.r2);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) count(k + j, in[j]);
+    }
+    for (; k < cnt; ++k) {
+      const float s2 = dist2(k);
+      bool in = s2 < lo;
+      if (!in && !(s2 > hi)) in = is_inlier_recheck(Tp, &sk[k][0], a.r2);
+      count(k, in);
+    }
+    if (!weighted) acc = (double)n_in;            // scores == NULL: every weight is 1.0, the float64 running sum is this integer
   }
   a.partial[((long long)p * a.tiles + tile) * a.H + h] = acc;
 }

@@ -30,6 +30,7 @@ int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const 
   memset(c, 0, sizeof(*c));
   c->device = device;
   c->overlap = 0;
+  c->score_mode = 0;
   *out = c;
   RR_CUDA(c, cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -77,6 +78,13 @@ int roreg_ctx_destroy(roreg_ctx* c) {
 int roreg_set_corr_mode(roreg_ctx* c, int mode) {
   RR_ARG(c, mode >= 0 && mode <= 3);
   c->corr_mode = mode;
+  return ROREG_OK;
+}
+
+int roreg_set_score_mode(roreg_ctx* c, int mode) {
+  if (!c) return ROREG_ERR_ARG;
+  RR_ARG(c, mode == 0 || mode == 1);
+  c->score_mode = mode;
   return ROREG_OK;
 }
 
@@ -221,8 +229,9 @@ static int score_and_select(roreg_ctx* c, const MatchView& mv, int cap, const do
                             const int32_t* order, const int32_t* n_hyp, int H, double ird, double* partial,
                             double* overlaps, int32_t* best_id, double* best_overlap, int B, cudaStream_t st) {
   const int tiles = (cap + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
-  ScoreArgs sa{mv, hyps, hyp_ps, order, n_hyp, H, ird * ird, partial, tiles};
-  ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
+  ScoreArgs sa{mv, hyps, hyp_ps, order, n_hyp, H, ird * ird, partial, tiles, ird};
+  if (c->score_mode == 1) ransac_score_pre_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
+  else ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
   RR_LAUNCH_CHECK(c);
   SelectArgs se{partial, tiles, H, mv.n_matches, mv.K, overlaps, best_id, best_overlap};
   ransac_select_kernel<<<B, 256, 0, st>>>(se);

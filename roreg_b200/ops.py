@@ -54,6 +54,10 @@ class Context:
         """Two-stream schedule of register_batch (default off: it measured slower on a B200); results are identical either way."""
         _lib.check(self.h, self.lib.roreg_set_overlap(self.h, int(on)), "roreg_set_overlap")
 
+    def set_score_mode(self, mode):
+        """0: float64 one-shot scoring (default); 1: float32 pre-filter with exact float64 re-check (same results)."""
+        _lib.check(self.h, self.lib.roreg_set_score_mode(self.h, int(mode)), "roreg_set_score_mode")
+
     def set_corr_mode(self, mode):
         _lib.check(self.h, self.lib.roreg_set_corr_mode(self.h, int(mode)), "roreg_set_corr_mode")
 

@@ -218,6 +218,40 @@ def test_ransac_no_positive_overlap_returns_minus_one(ctx, pair):
     assert int(best.item()) == -1 and float(bov.item()) == 0.0
 
 
+import os
+_experimental = pytest.mark.skipif(os.environ.get("ROREG_TEST_EXPERIMENTAL") != "1",
+                                   reason="opt-in paths not yet confirmed on a B200 (set ROREG_TEST_EXPERIMENTAL=1)")
+
+
+@_experimental
+@pytest.mark.parametrize("scores_kind", ["none", "f32"])
+def test_score_mode1_equals_float64_scoring(pair, scores_kind):
+    """roreg_set_score_mode(1): the float32 pre-filter + float64 re-check must reproduce the float64 scoring bit for bit -
+    on points planted ON the inlier sphere (the re-check path), on NaN / huge hypotheses and on ordinary ones."""
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    rng = np.random.default_rng(21)
+    k0, k1 = _matched(pair)
+    K = k0.shape[0]; H = 300
+    Hs = _hyps(pair, H, rng)
+    # plant a quarter of the k0 points at distance ird (1 + eps) from hypothesis 0's image of k1, eps from 0 to 1e-3
+    q = np.arange(0, K, 4)
+    d = rng.standard_normal((q.size, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    eps = np.where(np.arange(q.size) % 3 == 0, 0.0, rng.choice([-1, 1], q.size) * 10.0 ** rng.uniform(-12, -3, q.size))
+    k0 = k0.copy(); k0[q] = k1[q] @ Hs[0][:, :3].T + Hs[0][:, 3] + d * (0.1 * (1 + eps))[:, None]
+    Hs[5] = np.nan; Hs[6][:, 3] = 1e300; Hs[8][0, 0] = np.inf
+    sc = None if scores_kind == "none" else c.dev(rng.random(K).astype(np.float32), torch.float32)
+    d0 = c.dev(k0, torch.float64); d1 = c.dev(k1, torch.float64); dH = c.dev(Hs, torch.float64)
+    out = []
+    for mode in (0, 1):
+        c.set_score_mode(mode)
+        best, bov, ov = c.ransac_oneshot(d0, d1, sc, dH, None, 0.1, want_overlaps=True)
+        out.append((int(best.item()), float(bov.item()), _np(ov).copy()))
+    c.close()
+    assert out[0][0] == out[1][0] and out[0][1] == out[1][1]
+    assert np.array_equal(out[0][2], out[1][2], equal_nan=True)
+
+
 # ---------------------------------------------------------------------------------------- a20
 def test_kabsch3_proper_branch(ctx, pair):
     k0, k1 = _matched(pair)
