@@ -1,0 +1,47 @@
+"""The measurement contract of bench.py that can be exercised without a GPU: the `--impl reference` arm (the reference's
+CPU arithmetic through the oracle port, rank 0 only) prints ONE JSON line carrying the keys the driver reads, and the
+product arm refuses to run without the CUDA library / a GPU instead of falling back to the CPU."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(args, env=None, timeout=600):
+    e = dict(os.environ); e.update(env or {})
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py")] + args, cwd=ROOT, env=e, capture_output=True,
+                          text=True, timeout=timeout)
+
+
+def test_reference_arm_prints_the_contract_line():
+    r = _run(["--impl", "reference", "--steps", "2", "--warmup", "1", "--n", "400", "--max-iter", "100",
+              "--cpu-sample-pairs", "2", "--cpu-seconds", "1"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pairs/s" and d["higher_is_better"] is True and d["scaling"] == "weak"
+    assert d["steps"] == 2 and d["warmup"] == 1 and d["n_gpus"] == 1 and d["vs_baseline"] is None and d["data"] == "synthetic"
+    assert d["value"] > 0 and abs(d["e2e"]["value"] - d["value"]) < 1e-12
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    cb = d["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_arm_other_ranks_exit_without_work():
+    r = _run(["--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "0"], env={"RANK": "1", "WORLD_SIZE": "2", "LOCAL_RANK": "1"},
+             timeout=120)
+    assert r.returncode == 0 and not [l for l in r.stdout.splitlines() if l.startswith("{")]
+
+
+def test_product_arm_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        import pytest
+        pytest.skip("a GPU is present")
+    r = _run(["--steps", "1", "--warmup", "0", "--pairs-per-step", "1", "--n", "256", "--cpu-sample-pairs", "0"], timeout=300)
+    assert r.returncode != 0
+    assert not [l for l in r.stdout.splitlines() if l.startswith("{")]      # no number without the CUDA path
