@@ -47,6 +47,8 @@ def parse():
                     help="0 = float32 difference form (reference arithmetic), 1-3 = tcgen05 3xTF32 Gram variants, 4 = one fp16 two-accumulator Gram per pair (default)")
     ap.add_argument("--score-mode", type=int, default=int(os.environ.get("ROREG_SCORE_MODE", "0")),
                     help="one-shot scoring arithmetic: 0 float64 (default), 1 float32 pre-filter + exact float64 re-check")
+    ap.add_argument("--pipelined", type=int, default=int(os.environ.get("ROREG_PIPELINED", "0")),
+                    help="1: the resident-input loop uses roreg_register_batch_pipelined (RANSAC tail of batch i-1 beside the pooling of batch i)")
     ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "3")),
                     help="0 = FP32 CUDA-core Gram, 1-2 = tcgen05 3xTF32 Gram, 3 = fp16 two-accumulator Gram, operands from registers (default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
@@ -267,10 +269,15 @@ def main():
             torch.cuda.synchronize()
 
     # ---------------- resident-input throughput ("value") ----------------
-    # The timed region runs the library's default schedule (two internal streams, stages of the two half-batches overlapped).
+    # The timed region runs the library's default (serial) schedule; --pipelined 1 switches to the pipelined entry point.
     ctx.set_timing(False)
     for w in range(max(3, args.warmup)):
         step_resident(0, w)
+    if args.pipelined:                                          # grows both workspace slots outside the timed region
+        wouts = [None, None]
+        for w in range(max(3, args.warmup)):
+            wouts[w & 1] = ctx.register_batch_pipelined(desc_d[0], keys_d[0], pc, max_iter=H, ird=0.1, seed=w, nn_mode=args.nn_mode, out=wouts[w & 1])
+        ctx.flush_batches()
     torch.cuda.synchronize()
     sampler = ClockSampler(local); sampler.start()
     poses_all = torch.empty((args.steps, B, 4, 4), dtype=torch.float64, device=dev)
@@ -278,9 +285,21 @@ def main():
     l0 = ctx.launches
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
-    for s in range(args.steps):
-        o = step_resident(0, 100 + s)
-        poses_all[s].copy_(o["poses"])
+    if args.pipelined:
+        # steady-state pipeline: batch s's poses are complete after call s+1 (or the flush); fill and drain are inside the timed region
+        pouts = [None, None]
+        for s in range(args.steps):
+            pouts[s & 1] = ctx.register_batch_pipelined(desc_d[0], keys_d[0], pc, max_iter=H, ird=0.1, seed=100 + s, nn_mode=args.nn_mode,
+                                                        out=pouts[s & 1])
+            if s:
+                poses_all[s - 1].copy_(pouts[(s - 1) & 1]["poses"])
+        ctx.flush_batches()
+        poses_all[args.steps - 1].copy_(pouts[(args.steps - 1) & 1]["poses"])
+        o = pouts[(args.steps - 1) & 1]
+    else:
+        for s in range(args.steps):
+            o = step_resident(0, 100 + s)
+            poses_all[s].copy_(o["poses"])
     if world > 1:
         gathered = torch.empty((world,) + tuple(poses_all.shape), dtype=torch.float64, device=dev)
         dist.all_gather_into_tensor(gathered, poses_all)       # the path's only collective: final gather of poses
@@ -462,7 +481,7 @@ def main():
                                       "access pattern of the reference's test sets; the plugin's CloudCache); the headline e2e above uploads "
                                       "both clouds for every single pair"},
                 "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
-                "nn_mode": args.nn_mode, "corr_mode": args.corr_mode, "score_mode": args.score_mode}
+                "nn_mode": args.nn_mode, "corr_mode": args.corr_mode, "score_mode": args.score_mode, "pipelined": args.pipelined}
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

@@ -209,6 +209,14 @@ typedef struct {
 } roreg_batch;
 
 int roreg_register_batch(roreg_ctx* ctx, const roreg_batch* batch, void* stream);
+/* Pipelined form of roreg_register_batch for back-to-back batches (same per-pair loops, test/matcher.py:64-109 +
+ * test/estimator.py:102-111,163-242): a call enqueues the pooling, NN and Des2R of `batch` and, beside the pooling, the RANSAC
+ * tail (hypotheses, scoring, refinement) of the batch given to the PREVIOUS call.  The outputs poses / recall / best_overlap
+ * of a batch are therefore complete only after the next roreg_register_batch_pipelined or roreg_register_batch_flush on the
+ * same stream; its keys, pair_cloud, matches, n_matches and dr_index arrays must stay untouched until then (use two sets of
+ * buffers).  estimator 0 or 1; per-stage timing is not recorded.  Results equal roreg_register_batch's.               */
+int roreg_register_batch_pipelined(roreg_ctx* ctx, const roreg_batch* batch, void* stream);
+int roreg_register_batch_flush(roreg_ctx* ctx, void* stream);
 /* one-shot RANSAC + refinement (test/estimator.py:426-439) of every pair of the batch on caller-provided
  * hypotheses [B][max_iter][3][4] float64 (n_hyp [B] valid per pair, NULL = all), after estimator = 2.               */
 int roreg_estimate_batch(roreg_ctx* ctx, const roreg_batch* batch, const double* hyps, const int32_t* n_hyp,

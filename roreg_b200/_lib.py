@@ -58,6 +58,8 @@ SIGNATURES = {
     "roreg_rind_rows": (_i, [_p, _p, _i, _p, _p]),
     "roreg_sinkhorn_match": (_i, [_p, _p, _i, _i, _i, C.c_float, _i, _p, _p, _p, _p, _p]),
     "roreg_register_batch": (_i, [_p, C.POINTER(RoregBatch), _p]),
+    "roreg_register_batch_pipelined": (_i, [_p, C.POINTER(RoregBatch), _p]),
+    "roreg_register_batch_flush": (_i, [_p, _p]),
     "roreg_estimate_batch": (_i, [_p, C.POINTER(RoregBatch), _p, _p, _p]),
     "roreg_set_timing": (_i, [_p, _i]),
     "roreg_set_overlap": (_i, [_p, _i]),

@@ -31,6 +31,7 @@ struct roreg_ctx {
   int overlap;                    // 1 (default): split a batch in two halves and overlap their stages on s_tc / s_light
   cudaStream_t s_tc, s_light;     // created on first use: s_tc high priority, s_light low priority
   cudaEvent_t ev_fork, ev_pool[2], ev_corr[2], ev_join[2];
+  void* pipe;                     // state of roreg_register_batch_pipelined (PipeState, roreg_capi.cu), created on first use
   char err[512];
 };
 

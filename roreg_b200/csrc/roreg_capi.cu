@@ -31,6 +31,7 @@ int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const 
   c->device = device;
   c->overlap = 0;
   c->score_mode = 0;
+  c->pipe = nullptr;
   *out = c;
   RR_CUDA(c, cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -60,6 +61,7 @@ int roreg_ctx_create(int device, const int32_t* perm, const int32_t* nei, const 
   return ROREG_OK;
 }
 
+static void pipe_destroy(roreg_ctx* c);
 int roreg_ctx_destroy(roreg_ctx* c) {
   if (!c) return ROREG_ERR_ARG;
   cudaSetDevice(c->device);
@@ -69,6 +71,7 @@ int roreg_ctx_destroy(roreg_ctx* c) {
     cudaStreamDestroy(c->s_tc); cudaStreamDestroy(c->s_light); cudaEventDestroy(c->ev_fork);
     for (int h = 0; h < 2; ++h) { cudaEventDestroy(c->ev_pool[h]); cudaEventDestroy(c->ev_corr[h]); cudaEventDestroy(c->ev_join[h]); }
   }
+  pipe_destroy(c);
   cudaFree(c->d_perm8); cudaFree(c->d_permT8); cudaFree(c->d_nei); cudaFree(c->d_rot32); cudaFree(c->d_rot64);
   if (c->ws) cudaFree(c->ws);
   delete c;
@@ -756,6 +759,106 @@ int roreg_register_batch(roreg_ctx* c, const roreg_batch* b, void* stream) {
   RR_CUDA(c, cudaEventRecord(c->ev_join[1], c->s_light));
   RR_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[0], 0));
   RR_CUDA(c, cudaStreamWaitEvent(st, c->ev_join[1], 0));
+  return ROREG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pipelined form for back-to-back batches (throughput runs): the RANSAC tail T of batch i-1 (FP64 / latency-bound kernels with
+// small footprints) runs on an internal high-priority stream BESIDE the pooling P of batch i (HBM-bound, SMs idle) - the only two
+// phases whose CTAs fit on one SM together; the tensor-core phase TC owns the SMs and runs alone.  Per call, on the caller's stream:
+//     [ T(i-1) on the internal stream  ||  P(i) ]  ->  TC(i)  ->  wait for T(i-1)
+// Every phase processes a WHOLE batch (no half-batches: run 47 showed their fixed costs eat the overlap).  Two workspace slots
+// alternate, so batch i+1 reuses the slot of batch i-1 only after its tail was joined.
+struct PipeState {
+  BatchPlan pl;                 // the batch whose P and TC are enqueued and whose T is still owed
+  bool pending;
+  int slot;                     // workspace slot of the NEXT batch
+  void* ws[2]; size_t ws_bytes[2];
+  cudaStream_t s_tail; cudaEvent_t ev_tc, ev_tail;
+};
+
+static void pipe_destroy(roreg_ctx* c) {
+  PipeState* ps = reinterpret_cast<PipeState*>(c->pipe);
+  if (!ps) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 2; ++i) if (ps->ws[i]) cudaFree(ps->ws[i]);
+  if (ps->s_tail) cudaStreamDestroy(ps->s_tail);
+  if (ps->ev_tc) cudaEventDestroy(ps->ev_tc);
+  if (ps->ev_tail) cudaEventDestroy(ps->ev_tail);
+  delete ps;
+  c->pipe = nullptr;
+}
+
+static int pipe_get(roreg_ctx* c, PipeState** out) {
+  if (!c->pipe) {
+    PipeState* ps = new PipeState();
+    ps->pending = false; ps->slot = 0; ps->ws[0] = ps->ws[1] = nullptr; ps->ws_bytes[0] = ps->ws_bytes[1] = 0;
+    ps->s_tail = nullptr; ps->ev_tc = nullptr; ps->ev_tail = nullptr;
+    c->pipe = ps;
+    int lo = 0, hi = 0;
+    RR_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RR_CUDA(c, cudaStreamCreateWithPriority(&ps->s_tail, cudaStreamNonBlocking, hi));   // small tail kernels get free slots first
+    RR_CUDA(c, cudaEventCreateWithFlags(&ps->ev_tc, cudaEventDisableTiming));
+    RR_CUDA(c, cudaEventCreateWithFlags(&ps->ev_tail, cudaEventDisableTiming));
+  }
+  *out = reinterpret_cast<PipeState*>(c->pipe);
+  return ROREG_OK;
+}
+
+// enqueue the owed tail on the internal stream, ordered after everything on `st` so far; the caller joins with ev_tail
+static int pipe_tail(roreg_ctx* c, PipeState* ps, cudaStream_t st) {
+  int rc;
+  RR_CUDA(c, cudaEventRecord(ps->ev_tc, st));
+  RR_CUDA(c, cudaStreamWaitEvent(ps->s_tail, ps->ev_tc, 0));
+  if ((rc = batch_phase_tail(c, ps->pl, ps->s_tail, false))) return rc;
+  RR_CUDA(c, cudaEventRecord(ps->ev_tail, ps->s_tail));
+  return ROREG_OK;
+}
+
+int roreg_register_batch_flush(roreg_ctx* c, void* stream) {
+  if (!c) return ROREG_ERR_ARG;
+  PipeState* ps = reinterpret_cast<PipeState*>(c->pipe);
+  if (!ps || !ps->pending) return ROREG_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if ((rc = pipe_tail(c, ps, st))) return rc;
+  RR_CUDA(c, cudaStreamWaitEvent(st, ps->ev_tail, 0));
+  ps->pending = false;
+  return ROREG_OK;
+}
+
+int roreg_register_batch_pipelined(roreg_ctx* c, const roreg_batch* b, void* stream) {
+  RR_ARG(c, b && b->desc && b->keys && b->pair_cloud && b->matches && b->n_matches && b->dr_index && b->poses &&
+                b->recall && b->best_overlap);
+  RR_ARG(c, b->B >= 1 && b->n >= 1 && b->keynum >= 1 && b->keynum <= b->n && b->max_iter >= 1 && b->ird > 0);
+  RR_ARG(c, b->sample || b->keynum == b->n);
+  RR_ARG(c, b->estimator == 0 || (b->estimator == 1 && b->hyp_host_svd));
+  RR_ARG(c, b->nn_mode >= 0 && b->nn_mode <= 4);
+  cudaStream_t st = (cudaStream_t)stream;
+  PipeState* ps;
+  int rc;
+  if ((rc = pipe_get(c, &ps))) return rc;
+  const int slot = ps->slot;
+  const size_t need = batch_ws_bytes(b, b->B);
+  if (ps->ws_bytes[slot] < need) {            // growth only: the slot's last user was joined into `st` one call ago, drain before freeing
+    RR_CUDA(c, cudaDeviceSynchronize());
+    if (ps->ws[slot]) { cudaFree(ps->ws[slot]); ps->ws[slot] = nullptr; ps->ws_bytes[slot] = 0; }
+    const size_t want = need + need / 8 + (1 << 20);
+    if (cudaMalloc(&ps->ws[slot], want) != cudaSuccess) {
+      cudaGetLastError();
+      snprintf(c->err, sizeof(c->err), "pipelined workspace cudaMalloc(%zu) failed", want);
+      return ROREG_ERR_NOMEM;
+    }
+    ps->ws_bytes[slot] = want;
+  }
+  const bool owed = ps->pending;
+  if (owed && (rc = pipe_tail(c, ps, st))) return rc;            // T(i-1) on the internal stream ...
+  BatchPlan pl;
+  batch_plan(b, 0, b->B, (char*)ps->ws[slot], &pl);
+  if ((rc = batch_phase_pool(c, pl, st, false))) return rc;      // ... beside P(i)
+  if ((rc = batch_phase_tc(c, pl, st, false))) return rc;
+  if (owed) RR_CUDA(c, cudaStreamWaitEvent(st, ps->ev_tail, 0)); // later work on `st` (and the slot's next user) sees T(i-1) done
+  ps->pl = pl; ps->pending = true; ps->slot = slot ^ 1;
   return ROREG_OK;
 }
 

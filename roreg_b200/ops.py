@@ -31,6 +31,7 @@ class Context:
         rot = np.ascontiguousarray(self.tables.rot, np.float64)
         rc = self.lib.roreg_ctx_create(device, perm.ctypes.data, nei.ctypes.data, rot.ctypes.data, C.byref(h))
         self.h = h
+        self._pipe_keep = []
         _lib.check(self.h, rc, "roreg_ctx_create")
 
     def close(self):
@@ -178,7 +179,7 @@ class Context:
 
     # ---- batched engine ------------------------------------------------------------------------
     def register_batch(self, desc, keys, pair_cloud, keynum=None, sample=None, nn_mode=0, estimator=0, max_iter=1000,
-                       ird=0.1, seed=0, triplets=None, hyps=None, out=None):
+                       ird=0.1, seed=0, triplets=None, hyps=None, out=None, pipelined=False):
         """desc [n_clouds,n,32,60] f32, keys [n_clouds,n,3] f64, pair_cloud [B,2] int32 (device tensors).
         Returns dict of device tensors: matches [B,keynum,2], n_matches [B], dr_index [B,keynum],
         poses [B,4,4], recall [B], best_overlap [B]."""
@@ -203,10 +204,26 @@ class Context:
         b.hyp_host_svd = hyps.data_ptr() if hyps is not None else None
         b.matches, b.n_matches, b.dr_index = out["matches"].data_ptr(), out["n_matches"].data_ptr(), out["dr_index"].data_ptr()
         b.poses, b.recall, b.best_overlap = out["poses"].data_ptr(), out["recall"].data_ptr(), out["best_overlap"].data_ptr()
+        if pipelined:
+            rc = self.lib.roreg_register_batch_pipelined(self.h, C.byref(b), _stream())
+            _lib.check(self.h, rc, "roreg_register_batch_pipelined")
+            self._pipe_keep = (self._pipe_keep + [(out, keys, pair_cloud, sample, triplets, hyps)])[-2:]   # inputs of the owed tail stay alive
+            return out
         rc = self.lib.roreg_register_batch(self.h, C.byref(b), _stream())
         _lib.check(self.h, rc, "roreg_register_batch")
         self._last_batch = b       # kept for estimate_batch (same buffers; `out` keeps the tensors alive)
         return out
+
+    def register_batch_pipelined(self, *args, **kw):
+        """Throughput form of register_batch for back-to-back batches (roreg_register_batch_pipelined): the RANSAC tail of the
+        previous batch runs beside this batch's pooling.  `poses`, `recall`, `best_overlap` of the returned dict are complete only
+        after the NEXT register_batch_pipelined / flush_batches on the same stream - pass a different `out` (and different keys /
+        pair_cloud tensors if they change) for consecutive calls."""
+        return self.register_batch(*args, pipelined=True, **kw)
+
+    def flush_batches(self):
+        """Enqueue the tail still owed by the last register_batch_pipelined call."""
+        _lib.check(self.h, self.lib.roreg_register_batch_flush(self.h, _stream()), "roreg_register_batch_flush")
 
     def estimate_batch(self, out, hyps, n_hyp=None):
         """One-shot RANSAC + refine on caller-provided hypotheses [B,max_iter,3,4] f64 after register_batch(estimator=2)."""

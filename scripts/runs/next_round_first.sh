@@ -1,12 +1,12 @@
 #!/bin/bash
 # First gpurun call of the next round (prepared at the end of round 1, when the GPU budget was spent; NOT run yet).
 # 1. confirm the opt-in paths that were written without a GPU: score mode 1 (float32 pre-filter, kernels_ransac.cuh);
-# 2. A/B the bench with and without it; 3. multi-rank e2e with / without the NUMA binding of bench.py.
+# 2. A/B the bench with and without it, and with the pipelined entry point (roreg_register_batch_pipelined); 3. multi-rank e2e with / without the NUMA binding of bench.py.
 set -x
 mkdir -p gpurun_out
-ROREG_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or ransac" > gpurun_out/n01_pytest_experimental.txt 2>&1
+ROREG_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or ransac or pipelined" > gpurun_out/n01_pytest_experimental.txt 2>&1
 tail -4 gpurun_out/n01_pytest_experimental.txt
-ROREG_TEST_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1" > gpurun_out/n01_sanitizer.txt 2>&1
+ROREG_TEST_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or pipelined" > gpurun_out/n01_sanitizer.txt 2>&1
 tail -3 gpurun_out/n01_sanitizer.txt
 for m in 0 1; do
   timeout 400 python bench.py --score-mode $m --cpu-sample-pairs 0 > gpurun_out/n01_bench_score$m.json 2> gpurun_out/n01_bench_score$m.err
@@ -14,5 +14,14 @@ for m in 0 1; do
 import json
 d=json.loads(open("gpurun_out/n01_bench_score$m.json").read().strip().splitlines()[-1])
 print("score_mode $m:", round(d["value"]), "pairs/s", {k:round(v,3) for k,v in d["roofline"]["stage_ms_per_step"].items()}, d["pose_check"])
+PY
+done
+for cfg in "--pipelined 1" "--pipelined 1 --score-mode 1" "--pipelined 1 --score-mode 1 --pairs-per-step 128" "--pairs-per-step 128"; do
+  tag=$(echo $cfg | tr -d ' -')
+  timeout 400 python bench.py $cfg --cpu-sample-pairs 0 > gpurun_out/n01_bench_$tag.json 2> gpurun_out/n01_bench_$tag.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/n01_bench_$tag.json").read().strip().splitlines()[-1])
+print("$cfg:", round(d["value"]), "pairs/s", d["pose_check"])
 PY
 done

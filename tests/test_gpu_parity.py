@@ -252,6 +252,44 @@ def test_score_mode1_equals_float64_scoring(pair, scores_kind):
     assert np.array_equal(out[0][2], out[1][2], equal_nan=True)
 
 
+@_experimental
+@pytest.mark.parametrize("nn_mode,corr_mode", [(0, 0), (4, 3)])
+def test_register_batch_pipelined_equals_serial(tables, nn_mode, corr_mode):
+    """roreg_register_batch_pipelined: the tail of batch i-1 beside the pooling of batch i, two workspace slots - a sequence of
+    batches of different sizes must return exactly what the serial entry point returns for each."""
+    from roreg_b200 import ops
+    c = ops.Context(0)
+    c.set_corr_mode(corr_mode)
+    sizes = [5, 9, 3, 9]
+    batches = []
+    for j, Bj in enumerate(sizes):
+        prs = [synth.make_pair(700 + 10 * j + i, n=700) for i in range(Bj)]
+        desc = c.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])]))
+        keys = c.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+        pc = c.dev(np.array([[2 * i, 2 * i + 1] for i in range(Bj)], np.int32))
+        batches.append((prs, desc, keys, pc))
+    ser = []
+    for j, (prs, desc, keys, pc) in enumerate(batches):
+        o = c.register_batch(desc, keys, pc, max_iter=300, seed=31 + j, nn_mode=nn_mode)
+        torch.cuda.synchronize()
+        ser.append({k: _np(v).copy() for k, v in o.items()})
+    for rep in range(2):                                         # second repetition reuses both workspace slots
+        outs = [c.register_batch_pipelined(desc, keys, pc, max_iter=300, seed=31 + j, nn_mode=nn_mode)
+                for j, (prs, desc, keys, pc) in enumerate(batches)]
+        c.flush_batches()
+        torch.cuda.synchronize()
+        for j, o in enumerate(outs):
+            got = {k: _np(v) for k, v in o.items()}
+            assert np.array_equal(got["n_matches"], ser[j]["n_matches"]) and np.array_equal(got["recall"], ser[j]["recall"])
+            for i in range(sizes[j]):
+                k = int(ser[j]["n_matches"][i])
+                assert np.array_equal(got["matches"][i, :k], ser[j]["matches"][i, :k])
+                assert np.array_equal(got["dr_index"][i, :k], ser[j]["dr_index"][i, :k])
+            assert np.array_equal(got["poses"], ser[j]["poses"]) and np.array_equal(got["best_overlap"], ser[j]["best_overlap"])
+    c.flush_batches()                                            # nothing owed: a no-op
+    c.close()
+
+
 # ---------------------------------------------------------------------------------------- a20
 def test_kabsch3_proper_branch(ctx, pair):
     k0, k1 = _matched(pair)
