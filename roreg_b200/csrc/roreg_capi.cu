@@ -797,7 +797,11 @@ static int pipe_get(roreg_ctx* c, PipeState** out) {
     c->pipe = ps;
     int lo = 0, hi = 0;
     RR_CUDA(c, cudaDeviceGetStreamPriorityRange(&lo, &hi));
-    RR_CUDA(c, cudaStreamCreateWithPriority(&ps->s_tail, cudaStreamNonBlocking, hi));   // small tail kernels get free slots first
+    // which of the two co-running phases gets freed CTA slots first is a tuning knob (ROREG_PIPE_TAIL_PRIO = hi | lo | same):
+    // hi (default) lets the small tail kernels in as pooling CTAs retire; lo runs them in whatever the pooling grid leaves
+    int prio = hi;
+    if (const char* e = getenv("ROREG_PIPE_TAIL_PRIO")) prio = !strcmp(e, "lo") ? lo : !strcmp(e, "same") ? 0 : hi;
+    RR_CUDA(c, cudaStreamCreateWithPriority(&ps->s_tail, cudaStreamNonBlocking, prio));
     RR_CUDA(c, cudaEventCreateWithFlags(&ps->ev_tc, cudaEventDisableTiming));
     RR_CUDA(c, cudaEventCreateWithFlags(&ps->ev_tail, cudaEventDisableTiming));
   }

@@ -25,3 +25,12 @@ d=json.loads(open("gpurun_out/n01_bench_$tag.json").read().strip().splitlines()[
 print("$cfg:", round(d["value"]), "pairs/s", d["pose_check"])
 PY
 done
+# which phase wins the freed CTA slots while T(i-1) and P(i) co-run
+for prio in lo same; do
+  ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --cpu-sample-pairs 0 > gpurun_out/n01_bench_pipe_$prio.json 2> gpurun_out/n01_bench_pipe_$prio.err
+  python - <<PY
+import json
+d=json.loads(open("gpurun_out/n01_bench_pipe_$prio.json").read().strip().splitlines()[-1])
+print("pipelined, tail priority $prio:", round(d["value"]), "pairs/s", d["pose_check"])
+PY
+done
