@@ -138,7 +138,9 @@ def cpu_pipeline(pr, tables, max_iter, ird, seed):
     return T
 
 
-def cpu_baseline(prs, n_pairs, max_iter, ird, seconds=10.0, ref_ops=True):
+def time_c_port(prs, n_pairs, max_iter, ird, seconds):
+    """Bounded sample of the OPTIMISED host port (oracle/oracle_c.c: C + pthreads hot loops, NumPy/LAPACK host logic; falls back
+    to the NumPy oracle on one core when the C library is missing).  Not what a RoReg user runs - the stronger figure."""
     from roreg_b200 import group
     try:
         from oracle import oracle_c
@@ -148,68 +150,97 @@ def cpu_baseline(prs, n_pairs, max_iter, ird, seconds=10.0, ref_ops=True):
     tables = group.load()
     t0 = time.perf_counter()
     done = 0
-    while True:                                   # bounded sample: cycle over the pairs for ~`seconds` of host work
+    while True:                                   # cycle over the pairs for ~`seconds` of host work
         i = done % n_pairs
         if have_c:
             oracle_c.register_pair(prs[i], tables, max_iter, ird, seed=done)
         else:
             cpu_pipeline(prs[i], tables, max_iter, ird, done)
         done += 1
-        if time.perf_counter() - t0 >= seconds and done >= 1:
-            break
-        if done >= 64 * n_pairs:
+        if time.perf_counter() - t0 >= seconds or done >= 64 * n_pairs:
             break
     dt = time.perf_counter() - t0
     if have_c:
         cores = oracle_c.threads()
-        how = "oracle/oracle_c.c hot loops (C + pthreads, all host threads) + NumPy/LAPACK host logic exactly as the reference"
+        how = "oracle/oracle_c.c hot loops (C + pthreads, all host threads) + NumPy/LAPACK host logic"
     else:
         cores = 1
         how = "oracle/roreg_oracle.py (NumPy restatement; BLAS-free difference-form kernels run on one core)"
-    out = {"value": done / dt, "unit": "pairs/s", "cores": cores, "kind": "port",
-           "sample": f"{done} pair registrations of the same workload ({n_pairs} distinct pairs), {dt:.1f} s wall, {how}"}
-    # second figure: the same pipeline with the REFERENCE'S OWN tensor operations (torch on CPU, all intra-op threads) - what a RoReg
-    # user runs without a GPU; the C port above is an optimised re-implementation, i.e. the stronger (conservative) baseline
-    if not ref_ops:
-        return out
+    return {"value": done / dt, "unit": "pairs/s", "cores": cores, "pairs": done, "seconds": dt,
+            "sample": f"{done} pair registrations ({n_pairs} distinct pairs), {dt:.1f} s wall, {how}"}
+
+
+def time_reference_ops(prs, n_pairs, max_iter, ird, seconds):
+    """Bounded sample of the path with the REFERENCE'S OWN tensor operations on the host (oracle/torch_mirror.py: the chunked torch
+    `pdist` + per-chunk min of utils/knn_search.py, the [K,32,60,60] gather + einsum of test/estimator.py:85-89, the NumPy yohoc
+    RANSAC + refiner), all intra-op threads - what the reference executes when CUDA is absent ("run the reference's
+    own classes with torch.set_num_threads(os.cpu_count())"; its real classes were probed at 0.12 pairs/s on 8 cores, this
+    restatement runs 0.24 there)."""
+    import torch
+    from oracle import torch_mirror
+    from roreg_b200 import group
+    tables = group.load()
+    t0 = time.perf_counter()
+    done = 0
+    while True:
+        torch_mirror.register_pair(prs[done % n_pairs], tables.perm, max_iter, ird, done)
+        done += 1
+        if time.perf_counter() - t0 >= seconds or done >= 64 * n_pairs:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": done / dt, "unit": "pairs/s", "cores": int(torch.get_num_threads()), "pairs": done, "seconds": dt,
+            "sample": f"{done} pair registration(s) ({n_pairs} distinct pairs), {dt:.1f} s wall, oracle/torch_mirror.py: the reference's "
+                      "tensor operations on the host (chunked torch pdist, [K,32,60,60] gather + einsum, NumPy RANSAC), all intra-op threads"}
+
+
+def cpu_baseline(prs, n_pairs, max_iter, ird, seconds=10.0):
+    """`cpu_baseline` of the JSON line: value = the reference's own operations (time_reference_ops); the optimised C port is
+    reported beside it as `optimised_c_port` (a stronger baseline than the reference itself: 6-7x faster)."""
     try:
-        import torch
-        from oracle import torch_mirror
-        t1 = time.perf_counter(); n_ref = 0
-        while n_ref < max(1, min(n_pairs, 3)) and time.perf_counter() - t1 < max(4.0, seconds * 0.6):
-            torch_mirror.register_pair(prs[n_ref % n_pairs], tables.perm, max_iter, ird, n_ref)
-            n_ref += 1
-        dt1 = time.perf_counter() - t1
-        out["reference_ops"] = {"value": n_ref / dt1, "unit": "pairs/s", "threads": torch.get_num_threads(),
-                                "sample": f"{n_ref} pair registration(s), {dt1:.1f} s wall, oracle/torch_mirror.py: chunked torch pdist + "
-                                          "[K,32,60,60] gather + einsum as utils/knn_search.py / test/estimator.py, NumPy RANSAC"}
-    except Exception as e:                     # the figure is informative only
-        out["reference_ops"] = {"unavailable": repr(e)}
+        r = time_reference_ops(prs, n_pairs, max_iter, ird, seconds)
+        out = {"value": r["value"], "unit": "pairs/s", "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    except Exception as e:                         # torch CPU ops unavailable: fall back to the C / NumPy port as the value
+        c = time_c_port(prs, n_pairs, max_iter, ird, seconds)
+        return {"value": c["value"], "unit": "pairs/s", "cores": c["cores"], "kind": "port", "sample": c["sample"],
+                "reference_ops_unavailable": repr(e)}
+    try:
+        c = time_c_port(prs, n_pairs, max_iter, ird, max(2.0, 0.5 * seconds))
+        out["optimised_c_port"] = {"value": c["value"], "unit": "pairs/s", "cores": c["cores"], "sample": c["sample"]}
+    except Exception as e:
+        out["optimised_c_port"] = {"unavailable": repr(e)}
     return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU arithmetic for the path (oracle port) on the host cores."""
+    """--impl reference: the reference's own CPU operations for the path (oracle/torch_mirror.py) on the host cores, rank 0 only."""
     if rank != 0:
         return
     prs, _, _, _ = make_inputs(max(1, args.cpu_sample_pairs), args.n, 0)
-    times, regs = [], []
     per_step = max(1.0, min(args.cpu_seconds, 200.0 / max(1, args.steps + args.warmup)))   # whole arm within a few minutes
-    ref_ops = None
+    timer, kind_note = time_reference_ops, None
+    try:
+        time_reference_ops(prs[:1], 1, min(args.max_iter, 50), 0.1, 0.0)                  # import + first-call costs outside the timed steps
+    except Exception as e:
+        timer, kind_note = time_c_port, repr(e)
+    pairs = secs = 0.0
+    last = None
     for s in range(args.warmup + args.steps):
-        t0 = time.perf_counter()
-        cb = cpu_baseline(prs, len(prs), args.max_iter, 0.1, per_step, ref_ops=False)
-        dt = time.perf_counter() - t0
+        last = timer(prs, len(prs), args.max_iter, 0.1, per_step)
         if s >= args.warmup:
-            times.append(dt); regs.append(cb["value"] * dt)
-    ref_ops = cpu_baseline(prs[:1], 1, args.max_iter, 0.1, 1.0, ref_ops=True).get("reference_ops")   # once, outside the timed steps
-    val = sum(regs) / sum(times)
-    cb["value"] = val
-    cb["sample"] = f"{args.steps} steps x ~{per_step:.1f} s bounded samples; " + cb["sample"]
-    if ref_ops:
-        cb["reference_ops"] = ref_ops
+            pairs += last["pairs"]; secs += last["seconds"]
+    val = pairs / secs
+    cb = {"value": val, "unit": "pairs/s", "cores": last["cores"], "kind": "port",
+          "sample": f"{args.steps} steps x ~{per_step:.1f} s bounded samples ({int(pairs)} pair registrations in {secs:.1f} s); " + last["sample"]}
+    if kind_note:
+        cb["reference_ops_unavailable"] = kind_note
+    else:
+        try:                                                                              # once, outside the timed steps
+            c = time_c_port(prs, len(prs), args.max_iter, 0.1, 4.0)
+            cb["optimised_c_port"] = {"value": c["value"], "unit": "pairs/s", "cores": c["cores"], "sample": c["sample"]}
+        except Exception as e:
+            cb["optimised_c_port"] = {"unavailable": repr(e)}
     line = {"impl": "reference", "metric": "pair registrations/sec (5000 kpt, 60-rot)", "value": val, "unit": "pairs/s",
-            "n_gpus": args.gpus, "steps": len(times), "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
             "config": workload_config(args, len(prs)), "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

@@ -1,9 +1,9 @@
 """TEST / MEASUREMENT INFRASTRUCTURE ONLY - never imported by the product.
 
 The reference's per-pair CPU path restated WITH THE REFERENCE'S OWN TENSOR OPERATIONS (torch on CPU, all intra-op
-threads), for the `cpu_baseline.reference_ops` figure of bench.py: the C/pthreads port (oracle_c.c) is an optimised
-re-implementation and therefore a *stronger* baseline than what a RoReg user actually runs; this module times the
-operations the reference executes when CUDA is absent:
+threads), for the `cpu_baseline` / `--impl reference` figure of bench.py: the C/pthreads port (oracle_c.c) is an optimised
+re-implementation and therefore a *stronger* baseline than what a RoReg user actually runs (reported beside it as
+`optimised_c_port`); this module times the operations the reference executes when CUDA is absent:
 
   * matcher  test/matcher.py:69-72,94-106 + utils/knn_search.py:17-66,138-162: mean over the group axis, L2 normalise,
     `pdist` = sqrt(sum((A[:,None]-B[None])**2, 2) + 1e-7) in 500-row chunks with `.min(dim=1)` per chunk, Python mutual loop;
