@@ -3,7 +3,7 @@
  * Drop-in boundary: the reference has no FFI of its own - its hot path is
  * stock PyTorch / NumPy called from test/{matcher,estimator}.py - so each entry point below names the
  * reference function (file:line, relative to the reference root) whose arithmetic it replaces.  The
- * Python mirror of the reference's plugin classes (roreg_b200/test/*.py) binds these with ctypes;
+ * Python mirror of the reference's plugin classes (the modules in roreg_b200/test) binds these with ctypes;
  * INTEGRATION.md shows the stub a reference maintainer would add.
  *
  * Conventions
