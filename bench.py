@@ -490,8 +490,8 @@ def main():
                                        "over HBM, DESIGN.md section 3); survey_8d_bytes = SURVEY.md 8(d)'s 77.6 MB per pair (every descriptor byte "
                                        "counted once)"},
                 "note": "algorithmic bytes/flops per step (B pairs) / CUDA-event duration of that stage, events recorded by the library on the "
-                        "launch stream in a serial replay of the timed steps (the timed region itself overlaps the stages of two "
-                        "half-batches on two streams: value / n_gpus vs serial_schedule_pairs_per_s is what the overlap buys)"}
+                        "launch stream in a replay of the timed steps with per-stage timing on (same serial schedule as the timed region unless "
+                        "--pipelined 1; fused_step.ms_overlapped = the timed region's own ms per step, events included in neither)"}
 
     if old_affinity is not None:
         try:
