@@ -263,18 +263,22 @@ __device__ __noinline__ bool is_inlier_recheck(const double* __restrict__ Tp, co
   return is_inlier(T, pt, pt + 3, r2);
 }
 
-__global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a) {
+// Work items = (hypothesis block, match tile, pair), hypothesis block fastest; the grid may be smaller than the item count (a cap on
+// resident CTAs leaves room for a co-running kernel, roreg_register_batch_pipelined): every CTA strides over the items.
+__global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a, int hx_blocks, long long items) {
   __shared__ double sk[RR_SCORE_TILE][7];
   __shared__ float4 sa[RR_SCORE_TILE], sb[RR_SCORE_TILE];
   __shared__ uint32_t smax[2][8];
-  const int p = blockIdx.z, tile = blockIdx.y, tid = threadIdx.x;
+  const int tid = threadIdx.x;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+  const int hx = (int)(item % hx_blocks), tile = (int)((item / hx_blocks) % a.tiles), p = (int)(item / ((long long)hx_blocks * a.tiles));
   const int K = mv_count(a.mv, p);
   const int k_begin = tile * RR_SCORE_TILE;
-  const int h = blockIdx.x * 256 + tid;
+  const int h = hx * 256 + tid;
   const int H = a.n_hyp ? min(a.H, a.n_hyp[p]) : a.H;
-  if (k_begin >= K) {
+  if (k_begin >= K) {                       // CTA-uniform
     if (h < a.H) a.partial[((long long)p * a.tiles + tile) * a.H + h] = 0.0;
-    return;
+    continue;
   }
   const int cnt = min(RR_SCORE_TILE, K - k_begin);
   float am = 0.f, bm = 0.f;
@@ -294,7 +298,6 @@ __global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a) {
   const uint32_t wa = __reduce_max_sync(0xffffffffu, __float_as_uint(am)), wb = __reduce_max_sync(0xffffffffu, __float_as_uint(bm));
   if ((tid & 31) == 0) { smax[0][tid >> 5] = wa; smax[1][tid >> 5] = wb; }
   __syncthreads();
-  if (h >= a.H) return;
   double acc = 0.0;
   if (h < H) {
     uint32_t ua = 0, ub = 0;
@@ -352,7 +355,9 @@ __global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a) {
     }
     if (!weighted) acc = (double)n_in;            // scores == NULL: every weight is 1.0, the float64 running sum is this integer
   }
-  a.partial[((long long)p * a.tiles + tile) * a.H + h] = acc;
+  if (h < a.H) a.partial[((long long)p * a.tiles + tile) * a.H + h] = acc;
+  __syncthreads();                          // the staged tile is overwritten by the next item
+  }
 }
 
 // first-best selection (strict '>' from 0, test/estimator.py:427-436).  One CTA per pair.

@@ -233,8 +233,14 @@ static int score_and_select(roreg_ctx* c, const MatchView& mv, int cap, const do
                             double* overlaps, int32_t* best_id, double* best_overlap, int B, cudaStream_t st) {
   const int tiles = (cap + RR_SCORE_TILE - 1) / RR_SCORE_TILE;
   ScoreArgs sa{mv, hyps, hyp_ps, order, n_hyp, H, ird * ird, partial, tiles, ird};
-  if (c->score_mode == 1) ransac_score_pre_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
-  else ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
+  if (c->score_mode == 1) {
+    const int hx = (H + 255) / 256;
+    const long long items = (long long)hx * tiles * B;
+    long long grid = items;
+    if (const char* e = getenv("ROREG_SCORE_CTAS_PER_SM")) { const long long cap = (long long)atoi(e) * c->sm_count; if (cap >= 1 && cap < grid) grid = cap; }
+    if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+    ransac_score_pre_kernel<<<(unsigned)grid, 256, 0, st>>>(sa, hx, items);
+  } else ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
   RR_LAUNCH_CHECK(c);
   SelectArgs se{partial, tiles, H, mv.n_matches, mv.K, overlaps, best_id, best_overlap};
   ransac_select_kernel<<<B, 256, 0, st>>>(se);

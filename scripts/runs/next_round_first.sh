@@ -34,3 +34,14 @@ d=json.loads(open("gpurun_out/n01_bench_pipe_$prio.json").read().strip().splitli
 print("pipelined, tail priority $prio:", round(d["value"]), "pairs/s", d["pose_check"])
 PY
 done
+# pipelined + score mode 1 with a cap on the scoring kernel's resident CTAs (room for the co-running pooling kernel)
+for cap in 1 2 4; do
+  for prio in hi same; do
+    ROREG_SCORE_CTAS_PER_SM=$cap ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --score-mode 1 --cpu-sample-pairs 0 > gpurun_out/n01_bench_pipe_cap${cap}_$prio.json 2> gpurun_out/n01_bench_pipe_cap${cap}_$prio.err
+    python - <<PY
+import json
+d=json.loads(open("gpurun_out/n01_bench_pipe_cap${cap}_$prio.json").read().strip().splitlines()[-1])
+print("pipelined, score mode 1, $cap scoring CTAs per SM, tail priority $prio:", round(d["value"]), "pairs/s", d["pose_check"])
+PY
+  done
+done
