@@ -49,6 +49,8 @@ def parse():
                     help="one-shot scoring arithmetic: 0 float64 (default), 1 float32 pre-filter + exact float64 re-check")
     ap.add_argument("--pipelined", type=int, default=int(os.environ.get("ROREG_PIPELINED", "0")),
                     help="1: the resident-input loop uses roreg_register_batch_pipelined (RANSAC tail of batch i-1 beside the pooling of batch i)")
+    ap.add_argument("--value-only", type=int, default=0,
+                    help="1 (kernel A/B experiments only): one untimed-quality step for the e2e / scene phases; their numbers are then meaningless")
     ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "3")),
                     help="0 = FP32 CUDA-core Gram, 1-2 = tcgen05 3xTF32 Gram, 3 = fp16 two-accumulator Gram, operands from registers (default)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
@@ -382,10 +384,11 @@ def main():
             desc_d[buf].copy_(desc_pin, non_blocking=True); keys_d[buf].copy_(keys_pin, non_blocking=True)
             ready[buf].record(copy_stream)
 
-    e2e_steps = max(4, min(args.steps, 12))
+    e2e_steps = 1 if args.value_only else max(4, min(args.steps, 12))
+    e2e_reps = 1 if args.value_only else 2
     for b in (0, 1):
         done[b].record(comp)
-    for rep in range(2):                                        # rep 0 = warm-up, rep 1 = timed
+    for rep in range(e2e_reps):                                        # rep 0 = warm-up, rep 1 = timed
         barrier()
         t0 = time.perf_counter()
         h2d(0)
@@ -412,10 +415,10 @@ def main():
         out_scene[0] = ctx.register_batch(desc_d[buf], keys_d[buf], pc_scene, max_iter=H, ird=0.1, seed=seed, nn_mode=args.nn_mode, out=out_scene[0])
         return out_scene[0]
 
-    scene_steps = max(3, min(args.steps, 6))
+    scene_steps = 1 if args.value_only else max(3, min(args.steps, 6))
     for b in (0, 1):
         done[b].record(comp)
-    for rep in range(2):                                        # rep 0 = warm-up (also grows the workspace), rep 1 = timed
+    for rep in range(e2e_reps):                                        # rep 0 = warm-up (also grows the workspace), rep 1 = timed
         barrier()
         t0 = time.perf_counter()
         h2d(0)
@@ -513,6 +516,8 @@ def main():
                                       "both clouds for every single pair"},
                 "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
                 "nn_mode": args.nn_mode, "corr_mode": args.corr_mode, "score_mode": args.score_mode, "pipelined": args.pipelined}
+        if args.value_only:
+            line["value_only"] = True; line["e2e"]["note"] = "--value-only run: e2e / e2e_scene were not measured properly"
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

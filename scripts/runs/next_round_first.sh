@@ -9,7 +9,7 @@ tail -4 gpurun_out/n01_pytest_experimental.txt
 ROREG_TEST_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or pipelined" > gpurun_out/n01_sanitizer.txt 2>&1
 tail -3 gpurun_out/n01_sanitizer.txt
 for m in 0 1; do
-  timeout 400 python bench.py --score-mode $m --cpu-sample-pairs 0 > gpurun_out/n01_bench_score$m.json 2> gpurun_out/n01_bench_score$m.err
+  timeout 400 python bench.py --score-mode $m --cpu-sample-pairs 0 --value-only 1 > gpurun_out/n01_bench_score$m.json 2> gpurun_out/n01_bench_score$m.err
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/n01_bench_score$m.json").read().strip().splitlines()[-1])
@@ -18,7 +18,7 @@ PY
 done
 for cfg in "--pipelined 1" "--pipelined 1 --score-mode 1" "--pipelined 1 --score-mode 1 --pairs-per-step 128" "--pairs-per-step 128"; do
   tag=$(echo $cfg | tr -d ' -')
-  timeout 400 python bench.py $cfg --cpu-sample-pairs 0 > gpurun_out/n01_bench_$tag.json 2> gpurun_out/n01_bench_$tag.err
+  timeout 400 python bench.py $cfg --cpu-sample-pairs 0 --value-only 1 > gpurun_out/n01_bench_$tag.json 2> gpurun_out/n01_bench_$tag.err
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/n01_bench_$tag.json").read().strip().splitlines()[-1])
@@ -27,7 +27,7 @@ PY
 done
 # which phase wins the freed CTA slots while T(i-1) and P(i) co-run
 for prio in lo same; do
-  ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --cpu-sample-pairs 0 > gpurun_out/n01_bench_pipe_$prio.json 2> gpurun_out/n01_bench_pipe_$prio.err
+  ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --cpu-sample-pairs 0 --value-only 1 > gpurun_out/n01_bench_pipe_$prio.json 2> gpurun_out/n01_bench_pipe_$prio.err
   python - <<PY
 import json
 d=json.loads(open("gpurun_out/n01_bench_pipe_$prio.json").read().strip().splitlines()[-1])
@@ -37,7 +37,7 @@ done
 # pipelined + score mode 1 with a cap on the scoring kernel's resident CTAs (room for the co-running pooling kernel)
 for cap in 1 2 4; do
   for prio in hi same; do
-    ROREG_SCORE_CTAS_PER_SM=$cap ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --score-mode 1 --cpu-sample-pairs 0 > gpurun_out/n01_bench_pipe_cap${cap}_$prio.json 2> gpurun_out/n01_bench_pipe_cap${cap}_$prio.err
+    ROREG_SCORE_CTAS_PER_SM=$cap ROREG_PIPE_TAIL_PRIO=$prio timeout 400 python bench.py --pipelined 1 --score-mode 1 --cpu-sample-pairs 0 --value-only 1 > gpurun_out/n01_bench_pipe_cap${cap}_$prio.json 2> gpurun_out/n01_bench_pipe_cap${cap}_$prio.err
     python - <<PY
 import json
 d=json.loads(open("gpurun_out/n01_bench_pipe_cap${cap}_$prio.json").read().strip().splitlines()[-1])
