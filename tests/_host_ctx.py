@@ -1,0 +1,113 @@
+"""TEST INFRASTRUCTURE: an oracle-backed stand-in for roreg_b200.ops.Context (same method names, argument order and return
+layout, CPU torch tensors) so that the HOST logic of the plugin mirrors in roreg_b200/test - sampling, global-RNG order, file
+layout, hypothesis bookkeeping, pre.log - can run in the `-m "not gpu"` suite against the reference-generated fixtures.  The
+product never imports this; on a GPU the same plugin code runs against the real context (tests/test_gpu_dropin.py)."""
+import numpy as np
+import torch
+from oracle import roreg_oracle as O
+from roreg_b200 import group
+
+
+def _np(t):
+    return None if t is None else (t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
+
+
+class HostContext:
+    def __init__(self, so3_dir=None):
+        self.tables = group.load(so3_dir)
+        self.device = torch.device("cpu")
+        self.corr_mode = 0
+
+    def set_corr_mode(self, mode):
+        self.corr_mode = int(mode)
+
+    def dev(self, a, dtype=None):
+        t = torch.as_tensor(np.ascontiguousarray(a)) if not torch.is_tensor(a) else a
+        return (t.to(dtype) if dtype is not None else t).contiguous()
+
+    def inv_pool(self, eqv, sample=None, normalise=True):
+        f = _np(eqv)
+        if sample is not None:
+            f = f[_np(sample).astype(np.int64)]
+        return torch.from_numpy(O.inv_pool(f, normalise))
+
+    def knn(self, target, source, k=1):
+        d, i = O.knn(_np(target), _np(source), k)
+        return torch.from_numpy(d), torch.from_numpy(i.astype(np.int32))
+
+    def mutual_match(self, f0, f1, mode=0):
+        pps, nn01, nn10 = O.mutual_matches(_np(f0), _np(f1))
+        out = np.zeros((min(f0.shape[0], f1.shape[0]), 2), np.int32); out[:pps.shape[0]] = pps
+        return (torch.from_numpy(out), torch.tensor([pps.shape[0]], dtype=torch.int32), torch.from_numpy(nn01.astype(np.int32)),
+                torch.from_numpy(nn10.astype(np.int32)))
+
+    def group_corr(self, X, Y, idxX=None, idxY=None, variant=1, want_cor=True, want_argmax=True):
+        x = _np(X); y = _np(Y)
+        if idxX is not None:
+            x = x[_np(idxX).astype(np.int64)]
+        if idxY is not None:
+            y = y[_np(idxY).astype(np.int64)]
+        assert variant == 1
+        cor = O.group_corr_v1(x, y, self.tables.perm)
+        return (torch.from_numpy(cor.astype(np.float32)) if want_cor else None,
+                torch.from_numpy(np.argmax(cor, 1).astype(np.int32)) if want_argmax else None)
+
+    def hypotheses_from_quat(self, quat, pre_idx, k0m, k1m):
+        return torch.from_numpy(O.hypotheses_from_quat(_np(quat), _np(pre_idx), _np(k0m), _np(k1m), self.tables.rot))
+
+    @staticmethod
+    def _scores(scores, K):
+        return np.ones(K) if scores is None else _np(scores)
+
+    def ransac_oneshot(self, k0m, k1m, scores, trans, order, ird, want_overlaps=False):
+        T = _np(trans)
+        if order is not None:
+            T = T[_np(order).astype(np.int64)]
+        k0 = _np(k0m); k1 = _np(k1m)
+        best, bov, ovs = O.oneshot_ransac(k0, k1, self._scores(scores, k0.shape[0]), T, ird)
+        return (torch.tensor([best], dtype=torch.int32), torch.tensor([float(bov)], dtype=torch.float64),
+                torch.from_numpy(ovs) if want_overlaps else None)
+
+    def _pick(self, T_in, order, T_index):
+        T = _np(T_in)
+        if T_index is None:
+            return T
+        j = int(_np(T_index).reshape(-1)[0])
+        if order is not None:
+            j = int(_np(order)[j])
+        return T[j]
+
+    def refine(self, k0m, k1m, scores, T_in, ird, order=None, T_index=None, want_mask=False):
+        k0 = _np(k0m); k1 = _np(k1m); s = self._scores(scores, k0.shape[0])
+        T0 = self._pick(T_in, order, T_index)
+        T1 = O.refine_once(k0, k1, T0, s, 2.0 * ird)
+        T2 = O.refine_once(k0, k1, T1, s, ird)
+        mask = torch.from_numpy(O.inlier_mask(k0, k1, T1, ird).astype(np.uint8)) if want_mask else None
+        return torch.from_numpy(T2), mask
+
+    def refine_once(self, k0m, k1m, scores, T_in, radius, want_mask=False):
+        k0 = _np(k0m); k1 = _np(k1m); s = self._scores(scores, k0.shape[0])
+        T0 = _np(T_in)
+        mask = torch.from_numpy(O.inlier_mask(k0, k1, T0, radius).astype(np.uint8)) if want_mask else None
+        return torch.from_numpy(O.refine_once(k0, k1, T0, s, radius)), mask
+
+    def kabsch3(self, k0s, k1s, triplets):
+        k0 = _np(k0s); k1 = _np(k1s)
+        return torch.from_numpy(np.stack([O.threepps2tran(k0[t], k1[t]) for t in _np(triplets).astype(np.int64)]))
+
+
+def install(monkeypatch):
+    """Route `context(cfg)` of every plugin module to one HostContext."""
+    import roreg_b200.test._common as common
+    import roreg_b200.test.matcher as matcher
+    import roreg_b200.test.estimator as estimator
+    ctx = HostContext()
+
+    def fake_context(cfg=None):
+        cm = getattr(cfg, "corr_mode", None) if cfg is not None else None
+        if cm is not None:
+            ctx.set_corr_mode(cm)
+        return ctx
+    for mod in (common, matcher, estimator):
+        monkeypatch.setattr(mod, "context", fake_context, raising=True)
+    return ctx

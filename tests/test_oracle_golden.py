@@ -132,3 +132,35 @@ def test_torch_mirror_equals_numpy_oracle():
     assert np.array_equal(pps, p2)
     assert np.array_equal(dr, O.rindex(pr["feats0"], pr["feats1"], p2, t.perm))
     assert np.abs(T[:3] - pr["gt"]).max() < 1e-2
+
+
+def test_oracle_nms_sampler_and_yohoc_helpers_equal_reference():
+    """a14 NMS_sample (test/matcher.py:11-42) and the host helpers of a20 (DR_statictic, Threepps2Tran, test/estimator.py:119-147)
+    against tests/golden/s400rdrm.npz (tests/golden/make_golden_rd_rm.py: the unmodified reference)."""
+    from conftest import load_golden
+    from roreg_b200 import synth
+    z, n, keynum, max_iter, seeds = load_golden("s400rdrm")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/s400rdrm", max_res_deg=2.0)
+    keys = ds.get_kps(ds.pc_ids[0]); sc0 = z[f"det_score_{ds.pc_ids[0]}"]
+    for num in (40, 300, 380, 500):
+        assert np.array_equal(O.nms_sample(keys, sc0, num), z[f"nms_{num}"])
+    for num in (40, 300):
+        assert np.array_equal(O.nms_sample(keys, z["nms_flat_scores"], num), z[f"nms_flat_{num}"])
+    dr = z[f"dr_index_{ds.pair_ids[0][0]}-{ds.pair_ids[0][1]}"]
+    stat, prob = O.dr_statistic(dr)
+    assert np.array_equal(prob, z["drstat_prob"])
+    assert np.array_equal(np.concatenate([np.asarray(stat[i], np.int64) for i in range(60)]), z["drstat_members"])
+    k0 = ds.get_kps(ds.pair_ids[0][0]); k1 = ds.get_kps(ds.pair_ids[0][1])
+    for t, T in zip(z["kabsch_triplets"], z["kabsch_T"]):
+        assert np.array_equal(O.threepps2tran(k0[t], k1[t]), T)
+    # --RM selection + one-shot RANSAC + refine of the reference (test/estimator.py:404-441) through the oracle
+    for pi, (id0, id1) in enumerate(ds.pair_ids):
+        m = z[f"match_{id0}-{id1}"]; s = z[f"scores_{id0}-{id1}"]
+        k0m = ds.get_kps(id0)[m[:, 0]]; k1m = ds.get_kps(id1)[m[:, 1]]
+        if pi == 0:
+            rng = np.random.RandomState(1357)
+        T, best, _ = O.yohoo_ransac(k0m, k1m, s, z[f"trans_pre_{id0}-{id1}"], 0.1, max_iter, RM=True, match_n=0.5, rng=rng)
+        assert best == int(z[f"yohoo_recall_{id0}-{id1}"]) and np.abs(T - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-10
+        T, recall, _ = O.yohoc_ransac(k0m, k1m, s, z[f"dr_index_{id0}-{id1}"], 0.1, max_iter, RM=True, match_n=0.5,
+                                      rng=np.random.RandomState(555 + pi))
+        assert recall == int(z[f"yohoc_recall_{id0}-{id1}"]) and np.abs(T - z[f"yohoc_trans_{id0}-{id1}"]).max() < 1e-10

@@ -1,0 +1,148 @@
+"""Host logic of the plugin mirrors (roreg_b200/test) on the CPU: the same drop-in scenario as tests/test_gpu_dropin.py - run
+the plugins through their reference signatures against a cache directory, compare the files they write with the fixtures
+recorded from the UNMODIFIED reference (tests/golden/make_golden.py) - but with the device context replaced by the oracle
+(tests/_host_ctx.py).  What is pinned here is everything around the kernels: keypoint sampling and the consumption order of
+the global NumPy RNG, index bookkeeping, dtypes and layout of every file, the yohoc draw loop + host Kabsch, the
+--RM top-score selection, pre.log, and the error behaviour."""
+import os
+import types
+import numpy as np
+import pytest
+from conftest import load_golden
+from roreg_b200 import synth
+import _host_ctx
+
+
+def _cfg(cache, **kw):
+    c = types.SimpleNamespace(output_cache_fn=cache, model_fn="", SO3_related_files=None, backbone="FCGF",
+                              bs_GF=1250, bs_ET=1000, RD=False, RM=False, match_n=0.5, ransac_ird=0.1,
+                              keynum=5000, max_iter=1000)
+    for k, v in kw.items():
+        setattr(c, k, v)
+    return c
+
+
+@pytest.mark.parametrize("name", ["s256", "s700"])
+def test_plugins_reproduce_reference_files_on_host(name, tmp_path, monkeypatch):
+    _host_ctx.install(monkeypatch)
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden(name)
+    ds = synth.SynthDataset(seeds, n=n, name=f"synth/{name}", max_res_deg=2.0)
+    cache = str(tmp_path / "cache")
+    ds.write_cache(cache)
+    cfg = _cfg(cache)
+    base = f"{cache}/{ds.name}/match_{keynum}"
+    assert set(rt.name2matcher) == {"matmul", "yoho_mat"} and set(rt.name2estimator) == {"yohoc", "yohoo"}
+    assert set(rt.name2extractor) == {"yoho_des"} and set(rt.name2detector) == {"yoho_det"}
+    np.random.seed(1234)
+    rt.name2matcher["matmul"](cfg).run(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        m = np.load(f"{base}/{id0}-{id1}.npy"); s = np.load(f"{base}/scores/{id0}-{id1}.npy")
+        assert m.dtype == np.int64 and np.array_equal(m, z[f"match_{id0}-{id1}"])
+        assert s.dtype == np.float64 and np.array_equal(s, z[f"scores_{id0}-{id1}"])
+    rt.extractor_dr_index(cfg).Rindex(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        d = np.load(f"{base}/DR_index/{id0}-{id1}.npy")
+        assert d.dtype == np.int64 and np.array_equal(d, z[f"dr_index_{id0}-{id1}"])
+    os.makedirs(f"{base}/Trans_pre", exist_ok=True)
+    for (id0, id1) in ds.pair_ids:
+        np.save(f"{base}/Trans_pre/{id0}-{id1}.npy", z[f"trans_pre_{id0}-{id1}"])
+    np.random.seed(4321)
+    rt.yohoo_ransac(cfg).ransac(ds, keynum, max_iter)
+    for (id0, id1) in ds.pair_ids:
+        r = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoo_recall_{id0}-{id1}"])
+        assert r["trans"].shape == (4, 4) and np.abs(r["trans"] - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-12
+    got = open(f"{base}/yohoo/{max_iter}iters/pre.log", "rb").read().decode().splitlines()
+    ref = bytes(z["pre_log_yohoo"]).decode().splitlines()
+    assert len(got) == len(ref) == 5 * len(ds.pair_ids)
+    for i, (a, b) in enumerate(zip(got, ref)):
+        if i % 5 in (0, 4):
+            assert a == b                                           # 'id0\tid1\tn_clouds' and the constant last row: byte for byte
+        else:
+            fa, fb = a.split("\t"), b.split("\t")
+            assert len(fa) == len(fb) == 4 and max(abs(float(x) - float(y)) for x, y in zip(fa, fb)) < 1e-12
+    os.makedirs(f"{base}/yohoc/{max_iter}iters", exist_ok=True)
+    yc = rt.yohoc_ransac(cfg)
+    for pi, pair in enumerate(ds.pair_ids):
+        np.random.seed(777 + pi)
+        yc.ransac_once(ds, keynum, max_iter, pair)
+        id0, id1 = pair
+        r = np.load(f"{base}/yohoc/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoc_recall_{id0}-{id1}"])
+        assert np.abs(r["trans"] - z[f"yohoc_trans_{id0}-{id1}"]).max() < 1e-12
+
+
+def test_rd_rm_paths_reproduce_reference_files_on_host(tmp_path, monkeypatch):
+    """--RD (NMS sampling on detector scores) and --RM (top-`match_n` selection by score) against tests/golden/s400rdrm.npz
+    (tests/golden/make_golden_rd_rm.py, unmodified reference)."""
+    _host_ctx.install(monkeypatch)
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden("s400rdrm")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/s400rdrm", max_res_deg=2.0)
+    cache = str(tmp_path / "cache")
+    ds.write_cache(cache)
+    os.makedirs(f"{cache}/{ds.name}/det_score", exist_ok=True)
+    for cid in ds.pc_ids:
+        np.save(f"{cache}/{ds.name}/det_score/{cid}.npy", z[f"det_score_{cid}"])
+    cfg = _cfg(cache, RD=True, RM=True, match_n=0.5)
+    base = f"{cache}/{ds.name}/match_{keynum}"
+    # the sampler alone: trim branch, top-up branch, fewer points than requested, heavy score ties
+    keys = ds.get_kps(ds.pc_ids[0]); sc0 = z[f"det_score_{ds.pc_ids[0]}"]
+    for num in (40, 300, 380, 500):
+        assert np.array_equal(rt.NMS_sample(num, 5, cfg).sample(keys, sc0), z[f"nms_{num}"])
+    for num in (40, 300):
+        assert np.array_equal(rt.NMS_sample(num, 5, cfg).sample(keys, z["nms_flat_scores"]), z[f"nms_flat_{num}"])
+    np.random.seed(2468)
+    rt.mutual(cfg).run(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        assert np.array_equal(np.load(f"{base}/{id0}-{id1}.npy"), z[f"match_{id0}-{id1}"])
+        np.save(f"{base}/scores/{id0}-{id1}.npy", z[f"scores_{id0}-{id1}"])
+    rt.extractor_dr_index(cfg).Rindex(ds, keynum)
+    os.makedirs(f"{base}/Trans_pre", exist_ok=True)
+    for (id0, id1) in ds.pair_ids:
+        assert np.array_equal(np.load(f"{base}/DR_index/{id0}-{id1}.npy"), z[f"dr_index_{id0}-{id1}"])
+        np.save(f"{base}/Trans_pre/{id0}-{id1}.npy", z[f"trans_pre_{id0}-{id1}"])
+    np.random.seed(1357)
+    rt.yohoo_ransac(cfg).ransac(ds, keynum, max_iter)
+    yc = rt.yohoc_ransac(cfg)
+    os.makedirs(f"{base}/yohoc/{max_iter}iters", exist_ok=True)
+    for pi, pair in enumerate(ds.pair_ids):
+        np.random.seed(555 + pi)
+        yc.ransac_once(ds, keynum, max_iter, pair)
+    for (id0, id1) in ds.pair_ids:
+        for est in ("yohoo", "yohoc"):
+            r = np.load(f"{base}/{est}/{max_iter}iters/{id0}-{id1}.npz")
+            assert int(r["recalltime"]) == int(z[f"{est}_recall_{id0}-{id1}"]), est
+            assert np.abs(r["trans"] - z[f"{est}_trans_{id0}-{id1}"]).max() < 1e-10, est     # float32 weights: the reference normalises them in float32
+    # host helpers of yohoc_ransac (test/estimator.py:119-147)
+    dr = z[f"dr_index_{ds.pair_ids[0][0]}-{ds.pair_ids[0][1]}"]
+    stat, prob = yc.DR_statictic(dr)
+    assert np.array_equal(prob, z["drstat_prob"])
+    assert np.array_equal(np.array([len(stat[i]) for i in range(60)]), z["drstat_counts"])
+    assert np.array_equal(np.concatenate([np.asarray(stat[i], np.int64) for i in range(60)]), z["drstat_members"])
+    assert yc.DR_statictic(np.arange(60))[0] is None and np.array_equal(yc.DR_statictic(np.arange(60))[1], np.zeros(60))
+    k0 = ds.get_kps(ds.pair_ids[0][0]); k1 = ds.get_kps(ds.pair_ids[0][1])
+    for t, T in zip(z["kabsch_triplets"], z["kabsch_T"]):
+        assert np.array_equal(yc.Threepps2Tran(k0[t], k1[t]), T)
+
+
+def test_plugin_error_behaviour_on_host(tmp_path, monkeypatch):
+    """No mutual match -> the ValueError np.concatenate([]) raises in the reference (test/matcher.py:106); a pair whose coarse
+    rotations never repeat -> yohoc writes a random 4x4 with recalltime 50000 and returns 0 (test/estimator.py:214-218)."""
+    _host_ctx.install(monkeypatch)
+    import roreg_b200.test as rt
+    ds = synth.SynthDataset([71], n=64, name="synth/err")
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    cfg = _cfg(cache)
+    base = f"{cache}/{ds.name}/match_64"
+    os.makedirs(f"{base}/scores"); os.makedirs(f"{base}/DR_index"); os.makedirs(f"{base}/yohoc/50iters")
+    id0, id1 = ds.pair_ids[0]
+    np.save(f"{base}/{id0}-{id1}.npy", np.stack([np.arange(60), np.arange(60)], 1))
+    np.save(f"{base}/scores/{id0}-{id1}.npy", np.ones(60))
+    np.save(f"{base}/DR_index/{id0}-{id1}.npy", np.arange(60))           # every coarse rotation exactly once
+    np.random.seed(5)
+    assert rt.yohoc_ransac(cfg).ransac_once(ds, 64, 50, (id0, id1)) == 0
+    r = np.load(f"{base}/yohoc/50iters/{id0}-{id1}.npz")
+    np.random.seed(5)
+    assert int(r["recalltime"]) == 50000 and np.array_equal(r["trans"], np.random.rand(4, 4)) and r["center"].shape == (6, 3)
