@@ -50,3 +50,54 @@ class CloudCache:
                 self.d.pop(next(iter(self.d)))
         self.d[path] = t
         return t
+
+
+class CacheLayout:
+    """The reference's on-disk contract under cfg.output_cache_fn: per-cloud files live under the dataset's
+    feature name (3dLomatch shares 3dmatch's clouds), per-pair files under `{dataset.name}/match_{keynum}`.
+
+        {cloud_root}/{backbone}_Input_Group_feature/{pc}.npy     testset.py:180          float32 [n,32,60]
+        {cloud_root}/YOHO_Output_Group_feature/{pc}.npy          test/extractor.py:60    float32 [n,32,60]
+        {cloud_root}/det_score/{pc}.npy                          test/detector.py:47     [n]
+        {match_dir}/{id0}-{id1}.npy, scores/{id0}-{id1}.npy      test/matcher.py:108-109,209-210   int64 [K,2], [K]
+        {match_dir}/DR_index/{id0}-{id1}.npy                     test/estimator.py:111   int64 [K]
+        {match_dir}/Trans_pre/{id0}-{id1}.npy                    test/estimator.py:367   float64 [K,3,4]
+        {match_dir}/{yohoc|yohoo}/{max_iter}iters/{id0}-{id1}.npz, pre.log     test/estimator.py:242,441,14-26
+    """
+
+    def __init__(self, cfg, dataset, keynum=None):
+        self.cloud_root = f'{cfg.output_cache_fn}/{feature_dataset_name(dataset)}'
+        self.backbone = cfg.backbone
+        self.match_dir = f'{cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
+        self.scores_dir = f'{self.match_dir}/scores'
+        self.dr_index_dir = f'{self.match_dir}/DR_index'
+        self.trans_pre_dir = f'{self.match_dir}/Trans_pre'
+        self.yoho_dir = f'{self.cloud_root}/YOHO_Output_Group_feature'
+        self.det_score_dir = f'{self.cloud_root}/det_score'
+
+    def fcgf_desc(self, pc):
+        return f'{self.cloud_root}/{self.backbone}_Input_Group_feature/{pc}.npy'
+
+    def yoho_desc(self, pc):
+        return f'{self.yoho_dir}/{pc}.npy'
+
+    def det_score(self, pc):
+        return f'{self.det_score_dir}/{pc}.npy'
+
+    def matches(self, id0, id1):
+        return f'{self.match_dir}/{id0}-{id1}.npy'
+
+    def scores(self, id0, id1):
+        return f'{self.scores_dir}/{id0}-{id1}.npy'
+
+    def dr_index(self, id0, id1):
+        return f'{self.dr_index_dir}/{id0}-{id1}.npy'
+
+    def trans_pre(self, id0, id1):
+        return f'{self.trans_pre_dir}/{id0}-{id1}.npy'
+
+    def result_dir(self, estimator, max_iter):
+        return f'{self.match_dir}/{estimator}/{max_iter}iters'
+
+    def result(self, estimator, max_iter, id0, id1):
+        return f'{self.result_dir(estimator, max_iter)}/{id0}-{id1}.npz'

@@ -1,11 +1,20 @@
 """Mirror of test/detector.py:10-47 (yoho_det): rotation-guided saliency per keypoint, replaced by its rank / N
-(:44-46) and written to det_score/{pc_id}.npy."""
+(:44-46) and written to det_score/{pc}.npy.  As in the reference the clouds are addressed by POSITION in dataset.pc_ids
+(range(len(pc_ids)), :33), and a cloud whose score file exists is skipped."""
 import os
 import numpy as np
 from tqdm import tqdm
-from ._common import context, make_non_exists_dir, feature_dataset_name
+from ._common import context, make_non_exists_dir, CacheLayout
 from .extractor import load_state_dict
 from .. import nets
+
+
+def rank_fraction(values):
+    """test/detector.py:44-46: every value replaced by (its rank in ascending order) / N - used by the NMS comparison only."""
+    out = np.asarray(values).copy()
+    n = out.shape[0]
+    out[np.argsort(values)] = np.arange(n) / n
+    return out
 
 
 class yoho_det():
@@ -17,15 +26,11 @@ class yoho_det():
         self.net = nets.RDNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass)
 
     def run(self, dataset):
-        datasetname = feature_dataset_name(dataset)
-        savedir = f'{self.cfg.output_cache_fn}/{datasetname}/det_score'
-        make_non_exists_dir(savedir)
+        lay = CacheLayout(self.cfg, dataset)
+        make_non_exists_dir(lay.det_score_dir)
         print(f'Evaluating the saliency of points using rotaion guided detector on {dataset.name}')
-        for pc_id in tqdm(range(len(dataset.pc_ids))):
-            if os.path.exists(f'{savedir}/{pc_id}.npy'): continue
-            feats = np.load(f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature/{pc_id}.npy')
-            scores = self.net.forward(self.ctx.dev(feats.astype(np.float32))).cpu().numpy()
-            # normalization for NMS comparision only (test/detector.py:44-46)
-            argscores = np.argsort(scores)
-            scores[argscores] = np.arange(scores.shape[0]) / scores.shape[0]
-            np.save(f'{savedir}/{pc_id}.npy', scores)
+        todo = [i for i in range(len(dataset.pc_ids)) if not os.path.exists(lay.det_score(i))]
+        for i in tqdm(todo):
+            eqv = self.ctx.dev(np.load(lay.yoho_desc(i)).astype(np.float32))
+            saliency = self.net.forward(eqv).cpu().numpy()
+            np.save(lay.det_score(i), rank_fraction(saliency))

@@ -1,34 +1,39 @@
 """Mirror of test/estimator.py: R_pre_log (:14-26), refiner (:28-72), extractor_dr_index (:75-111),
 yohoc_ransac (:113-264), yohoc (:266-272), extractor_localtrans (:275-367), yohoo_ransac (:369-443),
-yohoo (:445-454).  Same signatures, same files written, same consumption order of the global NumPy
-RNG; the arithmetic runs in libroreg_b200.so."""
-import os
+yohoo (:445-454).  Same class / method names and signatures, same files written, same consumption order of the global
+NumPy RNG; the arithmetic runs in libroreg_b200.so, the host-side rules live in _hostlogic.py and the file
+layout in _common.CacheLayout."""
 import numpy as np
 import torch
 from tqdm import tqdm
-from ._common import context, make_non_exists_dir, feature_dataset_name, CloudCache
+from ._common import context, make_non_exists_dir, CloudCache, CacheLayout
+from . import _hostlogic as host
 
 
 def R_pre_log(dataset, save_dir):
     """test/estimator.py:14-26 - 3DMatch trajectory text consumed by utils/RR_cal.py:339."""
-    writer = open(f'{save_dir}/pre.log', 'w')
-    pair_num = int(len(dataset.pc_ids))
-    for pair in dataset.pair_ids:
-        pc0, pc1 = pair
-        ransac_result = np.load(f'{save_dir}/{pc0}-{pc1}.npz', allow_pickle=True)
-        transform_pr = ransac_result['trans']
-        writer.write(f'{int(pc0)}\t{int(pc1)}\t{pair_num}\n')
-        writer.write(f'{transform_pr[0][0]}\t{transform_pr[0][1]}\t{transform_pr[0][2]}\t{transform_pr[0][3]}\n')
-        writer.write(f'{transform_pr[1][0]}\t{transform_pr[1][1]}\t{transform_pr[1][2]}\t{transform_pr[1][3]}\n')
-        writer.write(f'{transform_pr[2][0]}\t{transform_pr[2][1]}\t{transform_pr[2][2]}\t{transform_pr[2][3]}\n')
-        writer.write(f'{0.0}\t{0.0}\t{0.0}\t{1.0}\n')
-    writer.close()
+    host.write_trajectory(dataset, save_dir)
 
 
 def _scores_dev(ctx, scores):
     if scores.dtype == np.float64:
         return ctx.dev(scores, torch.float64)
     return ctx.dev(scores.astype(np.float32), torch.float32)
+
+
+class _PairInputs:
+    """What both estimators read for one pair (test/estimator.py:186-194, :404-411): keypoints of the matches, their scores,
+    and - with --RM - the indices of the top-scored matches the hypotheses are restricted to."""
+
+    def __init__(self, cfg, lay, dataset, id0, id1):
+        self.scores = np.load(lay.scores(id0, id1))
+        self.pps = np.load(lay.matches(id0, id1))
+        self.k0 = dataset.get_kps(id0)[self.pps[:, 0]]
+        self.k1 = dataset.get_kps(id1)[self.pps[:, 1]]
+        self.kept = host.top_scored(self.scores, cfg.match_n) if cfg.RM else None
+
+    def upload(self, ctx):
+        return ctx.dev(self.k0, torch.float64), ctx.dev(self.k1, torch.float64), _scores_dev(ctx, self.scores)
 
 
 class refiner:
@@ -58,8 +63,8 @@ class extractor_dr_index:
         self.cfg = cfg
         self.ctx = context(cfg)
 
-    def Batch_Des2R_torch(self, des1_eqv, des2_eqv):  # beforerot afterrot
-        """test/estimator.py:85-89 on device tensors [B,32,60]."""
+    def Batch_Des2R_torch(self, des1_eqv, des2_eqv):
+        """test/estimator.py:85-89 on device tensors [B,32,60] (des1 = before, des2 = after the rotation)."""
         _, am = self.ctx.group_corr(des1_eqv.contiguous(), des2_eqv.contiguous(), variant=1, want_cor=False)
         return am.to(torch.int64)
 
@@ -67,22 +72,17 @@ class extractor_dr_index:
         return self.Batch_Des2R_torch(des1_eqv[None], des2_eqv[None])[0]
 
     def Rindex(self, dataset, keynum):
-        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
-        Save_dir = f'{match_dir}/DR_index'
-        make_non_exists_dir(Save_dir)
-        datasetname = feature_dataset_name(dataset)
-        Feature_dir = f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature'
+        lay = CacheLayout(self.cfg, dataset, keynum)
+        make_non_exists_dir(lay.dr_index_dir)
         print(f'extract the drindex of the matches on {dataset.name}')
-        cache = CloudCache(self.ctx)
-        for pair in tqdm(dataset.pair_ids):
-            id0, id1 = pair
-            match_pps = np.load(f'{match_dir}/{id0}-{id1}.npy')
-            feats0 = cache.get(f'{Feature_dir}/{id0}.npy')
-            feats1 = cache.get(f'{Feature_dir}/{id1}.npy')
-            i0 = self.ctx.dev(match_pps[:, 0].astype(np.int32)); i1 = self.ctx.dev(match_pps[:, 1].astype(np.int32))
-            # Batch_Des2R_torch(feats1, feats0): X = cloud id1, Y = cloud id0   (:110)
-            _, am = self.ctx.group_corr(feats1, feats0, i1, i0, variant=1, want_cor=False)
-            np.save(f'{Save_dir}/{id0}-{id1}.npy', am.cpu().numpy().astype(np.int64))
+        clouds = CloudCache(self.ctx)
+        for id0, id1 in tqdm(dataset.pair_ids):
+            pps = np.load(lay.matches(id0, id1))
+            rows0 = self.ctx.dev(pps[:, 0].astype(np.int32)); rows1 = self.ctx.dev(pps[:, 1].astype(np.int32))
+            # the reference calls Batch_Des2R_torch(feats1, feats0) (:110): X = cloud id1, Y = cloud id0
+            _, am = self.ctx.group_corr(clouds.get(lay.yoho_desc(id1)), clouds.get(lay.yoho_desc(id0)), rows1, rows0,
+                                        variant=1, want_cor=False)
+            np.save(lay.dr_index(id0, id1), am.cpu().numpy().astype(np.int64))
 
 
 class yohoc_ransac:
@@ -102,108 +102,59 @@ class yohoc_ransac:
         self.mode = getattr(cfg, "yohoc_mode", "parity")
 
     def DR_statictic(self, DR_indexs):
-        R_index_pre_statistic = {}
-        for i in range(60):
-            R_index_pre_statistic[i] = []
-        for t in range(DR_indexs.shape[0]):
-            R_index_pre_statistic[DR_indexs[t]].append(t)
-        R_index_pre_probability = []
-        for i in range(60):
-            if len(R_index_pre_statistic[i]) < 2:
-                R_index_pre_probability.append(0)
-            else:
-                num = float(len(R_index_pre_statistic[i])) / 100.0
-                R_index_pre_probability.append(num * (num - 0.01) * (num - 0.02))
-        R_index_pre_probability = np.array(R_index_pre_probability)
-        if np.sum(R_index_pre_probability) == 0:
-            return None, np.zeros(60)
-        R_index_pre_probability = R_index_pre_probability / np.sum(R_index_pre_probability)
-        return R_index_pre_statistic, R_index_pre_probability
+        """:119-137 -> (matches per coarse rotation, sampling probability per coarse rotation)."""
+        return host.rotation_buckets(DR_indexs)
 
     def Threepps2Tran(self, kps0_init, kps1_init):
-        center0 = np.mean(kps0_init, 0, keepdims=True)
-        center1 = np.mean(kps1_init, 0, keepdims=True)
-        m = (kps1_init - center1).T @ (kps0_init - center0)
-        U, S, VT = np.linalg.svd(m)
-        rotation = VT.T @ U.T
-        offset = center0 - (center1 @ rotation.T)
-        return np.concatenate([rotation, offset.T], 1)
+        """:139-147 -> [3,4]."""
+        return host.kabsch_3pt(kps0_init, kps1_init)
 
     def ransac_once(self, dataset, keynum, max_iter, pair):
-        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
-        Index_dir = f'{match_dir}/DR_index'
-        Save_dir = f'{match_dir}/yohoc/{max_iter}iters'
+        lay = CacheLayout(self.cfg, dataset, keynum)
         id0, id1 = pair
-        Keys0 = dataset.get_kps(id0)
-        Keys1 = dataset.get_kps(id1)
-        scores = np.load(f'{match_dir}/scores/{id0}-{id1}.npy')
-        pps = np.load(f'{match_dir}/{id0}-{id1}.npy')
-        Keys_m0_init = Keys0[pps[:, 0]]
-        Keys_m1_init = Keys1[pps[:, 1]]
-        sample_index = np.arange(pps.shape[0])
-        if self.cfg.RM:
-            if self.cfg.match_n < 0.999:
-                num = max(scores.shape[0] * self.cfg.match_n, 10)
-            else:
-                num = self.cfg.match_n
-            sample_index = np.argsort(scores)[-int(num):]
-        Keys_m0 = Keys_m0_init[sample_index]
-        Keys_m1 = Keys_m1_init[sample_index]
-        Index = np.load(f'{Index_dir}/{id0}-{id1}.npy')[sample_index]
-        R_index_pre_statistic, R_index_pre_probability = self.DR_statictic(Index)
-        best_3p_in_0 = np.ones([3, 3]); best_3p_in_1 = np.ones([3, 3])
-        if np.sum(R_index_pre_probability) < 1e-5:
-            np.savez(f'{Save_dir}/{id0}-{id1}.npz', trans=np.random.rand(4, 4),
-                     center=np.concatenate([best_3p_in_0, best_3p_in_1], axis=0), recalltime=50000)
+        out_file = lay.result('yohoc', max_iter, id0, id1)
+        pin = _PairInputs(self.cfg, lay, dataset, id0, id1)
+        kept = pin.kept if pin.kept is not None else np.arange(pin.pps.shape[0])
+        k0_kept, k1_kept = pin.k0[kept], pin.k1[kept]            # triplets come from the kept matches, overlap is scored on all
+        members, prob = self.DR_statictic(np.load(lay.dr_index(id0, id1))[kept])
+        if np.sum(prob) < 1e-5:
+            # no coarse rotation is shared by two matches: the reference stores a random pose and the sentinel 50000 (:214-218)
+            np.savez(out_file, trans=np.random.rand(4, 4), center=np.ones([6, 3]), recalltime=50000)
             return 0
         ctx = self.ctx
-        k0 = ctx.dev(Keys_m0_init, torch.float64); k1 = ctx.dev(Keys_m1_init, torch.float64)
-        sc = _scores_dev(ctx, scores)
+        k0, k1, sc = pin.upload(ctx)
         if self.mode == 'device':
             seed = int(np.random.randint(0, 2 ** 31 - 1))
-            trip = self._device_triplets(Index, max_iter, seed)
-            hyps = ctx.kabsch3(ctx.dev(Keys_m0, torch.float64), ctx.dev(Keys_m1, torch.float64), ctx.dev(trip))
+            trip = self._device_triplets(members, prob, max_iter, seed)
+            hyps = ctx.kabsch3(ctx.dev(k0_kept, torch.float64), ctx.dev(k1_kept, torch.float64), ctx.dev(trip))
         else:
-            iter_ransac, exec_time, max_time = 0, 0, 50000
-            hyps = []
-            while iter_ransac < max_iter:
-                if exec_time > max_time: break
-                exec_time += 1
-                R_index = np.random.choice(range(60), p=R_index_pre_probability)
-                if (len(R_index_pre_statistic[R_index]) < 2):
-                    continue
-                iter_ransac += 1
-                idxs_init = np.random.choice(np.array(R_index_pre_statistic[R_index]), 3)
-                hyps.append(self.Threepps2Tran(Keys_m0[idxs_init], Keys_m1[idxs_init]))
-            hyps = ctx.dev(np.stack(hyps, 0), torch.float64)
-        best, bov, _ = ctx.ransac_oneshot(k0, k1, sc, hyps, None, self.inliner_dist)
+            trip = host.draw_guided_triplets(members, prob, max_iter)
+            hyps = ctx.dev(np.stack([self.Threepps2Tran(k0_kept[t], k1_kept[t]) for t in trip], 0), torch.float64)
+        best, _, _ = ctx.ransac_oneshot(k0, k1, sc, hyps, None, self.inliner_dist)
         b = int(best.item())
         if b < 0:
             raise ValueError("no 3-point hypothesis has a positive overlap (the reference fails in transform_points here)")
         T, _ = ctx.refine(k0, k1, sc, hyps, self.inliner_dist, order=None, T_index=best)
-        np.savez(f'{Save_dir}/{id0}-{id1}.npz', trans=T.cpu().numpy(), recalltime=b + 1)
+        np.savez(out_file, trans=T.cpu().numpy(), recalltime=b + 1)      # the reference counts iterations from 1 (:226,:236)
 
-    def _device_triplets(self, Index, max_iter, seed):
+    def _device_triplets(self, members, prob, max_iter, seed):
         # host-side draw with a private Generator (the 'device' mode of the single-pair path keeps the
         # kernel inputs explicit; the batched engine draws inside coarse_hyp_kernel)
         rng = np.random.default_rng(seed)
-        stat, prob = self.DR_statictic(Index)
-        rs = rng.choice(60, size=max_iter, p=prob)
         trip = np.empty((max_iter, 3), np.int32)
-        for i, r in enumerate(rs):
-            trip[i] = rng.choice(np.array(stat[r]), 3)
+        for i, r in enumerate(rng.choice(60, size=max_iter, p=prob)):
+            trip[i] = rng.choice(members[r], 3)
         return trip
 
     def ransac(self, dataset, keynum, max_iter=1000):
-        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
-        Save_dir = f'{match_dir}/yohoc/{max_iter}iters'
-        make_non_exists_dir(Save_dir)
+        lay = CacheLayout(self.cfg, dataset, keynum)
+        make_non_exists_dir(lay.result_dir('yohoc', max_iter))
         print(f'Ransac with YOHO-C on {dataset.name}:')
         # the reference forks Pool(len(pair_ids)) (:258); pairs are independent, so the single device
         # context processes them in order instead
         for pair in tqdm(dataset.pair_ids):
             self.ransac_once(dataset, keynum, max_iter, pair)
-        R_pre_log(dataset, Save_dir)
+        R_pre_log(dataset, lay.result_dir('yohoc', max_iter))
         print('Done')
 
 
@@ -245,28 +196,20 @@ class extractor_localtrans():
     def Rt_pre(self, dataset, keynum):
         self._load_model()
         ctx = self.ctx
-        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
-        DRindex_dir = f'{match_dir}/DR_index'
-        Save_dir = f'{match_dir}/Trans_pre'
-        make_non_exists_dir(Save_dir)
-        datasetname = feature_dataset_name(dataset)
-        FCGF_dir = f'{self.cfg.output_cache_fn}/{datasetname}/{self.cfg.backbone}_Input_Group_feature'
-        YOMO_dir = f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature'
+        lay = CacheLayout(self.cfg, dataset, keynum)
+        make_non_exists_dir(lay.trans_pre_dir)
         print(f'Extracting the local transformation on each correspondence of {dataset.name}')
-        cache = CloudCache(ctx)
-        for pair in tqdm(dataset.pair_ids):
-            id0, id1 = pair
-            pps = np.load(f'{match_dir}/{id0}-{id1}.npy')
-            Index_pre = np.load(f'{DRindex_dir}/{id0}-{id1}.npy')
-            i0 = ctx.dev(pps[:, 0].astype(np.int32)); i1 = ctx.dev(pps[:, 1].astype(np.int32))
-            pre = ctx.dev(Index_pre.astype(np.int32))
+        clouds = CloudCache(ctx)
+        for id0, id1 in tqdm(dataset.pair_ids):
+            pps = np.load(lay.matches(id0, id1))
+            rows0 = ctx.dev(pps[:, 0].astype(np.int32)); rows1 = ctx.dev(pps[:, 1].astype(np.int32))
+            coarse = ctx.dev(np.load(lay.dr_index(id0, id1)).astype(np.int32))
             # batch_create (:293-306): side 0 of the network = cloud id1 ("exchanged")
-            quat = self.net.forward(cache.get(f'{FCGF_dir}/{id1}.npy'), i1, cache.get(f'{FCGF_dir}/{id0}.npy'), i0,
-                                    cache.get(f'{YOMO_dir}/{id1}.npy'), i1, cache.get(f'{YOMO_dir}/{id0}.npy'), i0, pre)
-            Keys0 = dataset.get_kps(id0)[pps[:, 0], :]
-            Keys1 = dataset.get_kps(id1)[pps[:, 1], :]
-            Trans = ctx.hypotheses_from_quat(quat, pre, ctx.dev(Keys0, torch.float64), ctx.dev(Keys1, torch.float64))
-            np.save(f'{Save_dir}/{id0}-{id1}.npy', Trans.cpu().numpy())
+            quat = self.net.forward(clouds.get(lay.fcgf_desc(id1)), rows1, clouds.get(lay.fcgf_desc(id0)), rows0,
+                                    clouds.get(lay.yoho_desc(id1)), rows1, clouds.get(lay.yoho_desc(id0)), rows0, coarse)
+            k0 = ctx.dev(dataset.get_kps(id0)[pps[:, 0], :], torch.float64)
+            k1 = ctx.dev(dataset.get_kps(id1)[pps[:, 1], :], torch.float64)
+            np.save(lay.trans_pre(id0, id1), ctx.hypotheses_from_quat(quat, coarse, k0, k1).cpu().numpy())
 
 
 class yohoo_ransac:
@@ -278,41 +221,28 @@ class yohoo_ransac:
         self.ctx = context(cfg)
 
     def ransac(self, dataset, keynum, max_iter=1000):
-        match_dir = f'{self.cfg.output_cache_fn}/{dataset.name}/match_{keynum}'
-        Trans_dir = f'{match_dir}/Trans_pre'
-        Save_dir = f'{match_dir}/yohoo/{max_iter}iters'
-        make_non_exists_dir(Save_dir)
+        lay = CacheLayout(self.cfg, dataset, keynum)
+        out_dir = lay.result_dir('yohoo', max_iter)
+        make_non_exists_dir(out_dir)
         ctx = self.ctx
         print(f'Ransac with YOHO-O on {dataset.name}:')
-        for pair in tqdm(dataset.pair_ids):
-            id0, id1 = pair
-            Keys0 = dataset.get_kps(id0)
-            Keys1 = dataset.get_kps(id1)
-            scores = np.load(f'{match_dir}/scores/{id0}-{id1}.npy')
-            pps = np.load(f'{match_dir}/{id0}-{id1}.npy')
-            Keys_m0 = Keys0[pps[:, 0]]
-            Keys_m1 = Keys1[pps[:, 1]]
-            Trans = np.load(f'{Trans_dir}/{id0}-{id1}.npy')
-            if self.cfg.RM:
-                if self.cfg.match_n < 0.999:
-                    num = max(scores.shape[0] * self.cfg.match_n, 10)
-                else:
-                    num = self.cfg.match_n
-                sample_index = np.argsort(scores)[-int(num):]
-                Trans = Trans[sample_index]
-            index = np.arange(Trans.shape[0])
-            np.random.shuffle(index)
-            order = ctx.dev(index[0:max_iter].astype(np.int32))
-            k0 = ctx.dev(Keys_m0, torch.float64); k1 = ctx.dev(Keys_m1, torch.float64)
-            sc = _scores_dev(ctx, scores)
-            tr = ctx.dev(Trans, torch.float64)
+        for id0, id1 in tqdm(dataset.pair_ids):
+            pin = _PairInputs(self.cfg, lay, dataset, id0, id1)
+            hyps = np.load(lay.trans_pre(id0, id1))
+            if pin.kept is not None:
+                hyps = hyps[pin.kept]
+            visit = np.arange(hyps.shape[0])
+            np.random.shuffle(visit)                                     # the pair's only RNG use (:423-424)
+            order = ctx.dev(visit[0:max_iter].astype(np.int32))
+            k0, k1, sc = pin.upload(ctx)
+            tr = ctx.dev(hyps, torch.float64)
             best, _, _ = ctx.ransac_oneshot(k0, k1, sc, tr, order, self.inliner_dist)
             b = int(best.item())
             if b < 0:
                 raise ValueError("no hypothesis has a positive overlap (the reference fails in transform_points here)")
             T, _ = ctx.refine(k0, k1, sc, tr, self.inliner_dist, order=order, T_index=best)
-            np.savez(f'{Save_dir}/{id0}-{id1}.npz', trans=T.cpu().numpy(), recalltime=b)
-        R_pre_log(dataset, Save_dir)
+            np.savez(lay.result('yohoo', max_iter, id0, id1), trans=T.cpu().numpy(), recalltime=b)
+        R_pre_log(dataset, out_dir)
 
 
 class yohoo:

@@ -1,15 +1,16 @@
 """Mirror of test/extractor.py:13-60 (yoho_des): FCGF_Input_Group_feature/{id}.npy -> GF network ->
-YOHO_Output_Group_feature/{id}.npy (float32 [n,32,60]), skipping clouds already cached (:47)."""
+YOHO_Output_Group_feature/{id}.npy (float32 [n,32,60]); a cloud whose output file exists is skipped (:47)."""
 import os
 import numpy as np
 import torch
 from tqdm import tqdm
-from ._common import context, make_non_exists_dir, feature_dataset_name
+from ._common import context, make_non_exists_dir, CacheLayout
 from .. import nets
 
 
 def load_state_dict(path):
-    """checkpoint['network_state_dict'] as NumPy arrays (test/extractor.py:24-27)."""
+    """checkpoint['network_state_dict'] as NumPy arrays (test/extractor.py:24-27); a missing file is the reference's
+    ValueError("No model exists")."""
     if not os.path.exists(path):
         raise ValueError("No model exists")
     ck = torch.load(path, map_location="cpu", weights_only=False)
@@ -30,14 +31,10 @@ class yoho_des():
 
     def run(self, dataset):
         self._load_model()
-        datasetname = feature_dataset_name(dataset)
-        FCGF_input_dir = f'{self.cfg.output_cache_fn}/{datasetname}/{self.cfg.backbone}_Input_Group_feature'
-        YOHO_output_dir = f'{self.cfg.output_cache_fn}/{datasetname}/YOHO_Output_Group_feature'
-        make_non_exists_dir(YOHO_output_dir)
+        lay = CacheLayout(self.cfg, dataset)
+        make_non_exists_dir(lay.yoho_dir)
         print(f'Extracting the PartI descriptors on {dataset.name}')
-        for pc_id in tqdm(dataset.pc_ids):
-            if os.path.exists(f'{YOHO_output_dir}/{pc_id}.npy'): continue
-            Input_feature = np.load(f'{FCGF_input_dir}/{pc_id}.npy')          # 5000*32*60
-            x = self.ctx.dev(Input_feature.astype(np.float32))
-            out = self.net.forward(x)
-            np.save(f'{YOHO_output_dir}/{pc_id}.npy', out.cpu().numpy())
+        todo = [pc for pc in dataset.pc_ids if not os.path.exists(lay.yoho_desc(pc))]
+        for pc in tqdm(todo):
+            fcgf = self.ctx.dev(np.load(lay.fcgf_desc(pc)).astype(np.float32))      # [n,32,60]
+            np.save(lay.yoho_desc(pc), self.net.forward(fcgf).cpu().numpy())

@@ -62,6 +62,15 @@ def test_plugins_reproduce_reference_files_on_host(name, tmp_path, monkeypatch):
         else:
             fa, fb = a.split("\t"), b.split("\t")
             assert len(fa) == len(fb) == 4 and max(abs(float(x) - float(y)) for x, y in zip(fa, fb)) < 1e-12
+    # number formatting: exactly what the reference's f-strings print for the poses stored in the .npz files
+    want = ""
+    for (id0, id1) in ds.pair_ids:
+        T = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")["trans"]
+        want += f"{int(id0)}\t{int(id1)}\t{len(ds.pc_ids)}\n"
+        for r in range(3):
+            want += f"{T[r][0]}\t{T[r][1]}\t{T[r][2]}\t{T[r][3]}\n"
+        want += f"{0.0}\t{0.0}\t{0.0}\t{1.0}\n"
+    assert open(f"{base}/yohoo/{max_iter}iters/pre.log").read() == want
     os.makedirs(f"{base}/yohoc/{max_iter}iters", exist_ok=True)
     yc = rt.yohoc_ransac(cfg)
     for pi, pair in enumerate(ds.pair_ids):
