@@ -101,6 +101,8 @@ def install(monkeypatch):
     import roreg_b200.test._common as common
     import roreg_b200.test.matcher as matcher
     import roreg_b200.test.estimator as estimator
+    import roreg_b200.test.extractor as extractor
+    import roreg_b200.test.detector as detector
     ctx = HostContext()
 
     def fake_context(cfg=None):
@@ -108,6 +110,33 @@ def install(monkeypatch):
         if cm is not None:
             ctx.set_corr_mode(cm)
         return ctx
-    for mod in (common, matcher, estimator):
+    for mod in (common, matcher, estimator, extractor, detector):
         monkeypatch.setattr(mod, "context", fake_context, raising=True)
     return ctx
+
+
+class HostGFNet:
+    """Stand-in for roreg_b200.nets.GFNet (same constructor / forward signature), oracle arithmetic."""
+
+    def __init__(self, ctx, sd, npass=3, chunk=500):
+        self.ctx, self.sd = ctx, sd
+
+    def forward(self, x):
+        return torch.from_numpy(O.gf_forward(_np(x), self.sd, self.ctx.tables.nei)[0])
+
+
+class HostRDNet:
+    """Stand-in for roreg_b200.nets.RDNet."""
+
+    def __init__(self, ctx, sd, npass=3):
+        self.ctx, self.sd = ctx, sd
+
+    def forward(self, x):
+        return torch.from_numpy(O.rd_forward(_np(x), self.sd, self.ctx.tables.nei, self.ctx.tables.perm))
+
+
+def install_nets(monkeypatch):
+    import roreg_b200.test.extractor as extractor
+    import roreg_b200.test.detector as detector
+    monkeypatch.setattr(extractor.nets, "GFNet", HostGFNet, raising=True)
+    monkeypatch.setattr(detector.nets, "RDNet", HostRDNet, raising=True)

@@ -155,3 +155,40 @@ def test_plugin_error_behaviour_on_host(tmp_path, monkeypatch):
     r = np.load(f"{base}/yohoc/50iters/{id0}-{id1}.npz")
     np.random.seed(5)
     assert int(r["recalltime"]) == 50000 and np.array_equal(r["trans"], np.random.rand(4, 4)) and r["center"].shape == (6, 3)
+
+
+def test_per_cloud_plugins_on_host(tmp_path, monkeypatch):
+    """yoho_des.run / yoho_det.run (test/extractor.py:33-60, test/detector.py:26-47): files, dtypes, skip-if-cached, clouds addressed
+    by position, rank normalisation - with the networks replaced by the oracle's forward passes; outputs against the
+    reference-written fixture (random weights from the same seeds as tests/golden/make_golden.py)."""
+    import torch
+    from oracle import roreg_oracle as O
+    _host_ctx.install(monkeypatch); _host_ctx.install_nets(monkeypatch)
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden("s256")
+    ds = synth.SynthDataset(seeds[:1], n=n, name="synth/s256", max_res_deg=2.0)          # clouds 0, 1
+    cache = str(tmp_path / "cache"); ds.write_cache(cache, yoho=False)
+    model_fn = str(tmp_path / "ckpt")
+    for kind, seed in (("GF", 101), ("RD", 103)):
+        os.makedirs(f"{model_fn}/{kind}")
+        torch.save({"best_para": 0, "network_state_dict": {k: torch.from_numpy(v) for k, v in O.random_state_dict(kind, seed).items()}},
+                   f"{model_fn}/{kind}/model_best.pth")
+    cfg = _cfg(cache, model_fn=model_fn)
+    out_dir = f"{cache}/{ds.name}/YOHO_Output_Group_feature"
+    os.makedirs(out_dir)
+    sentinel = np.full((3, 32, 60), 7, np.float32)
+    np.save(f"{out_dir}/1.npy", sentinel)                                                  # cloud 1 is "already cached"
+    rt.yoho_des(cfg).run(ds)
+    got = np.load(f"{out_dir}/0.npy")
+    assert got.dtype == np.float32 and got.shape == (n, 32, 60) and np.abs(got[:40] - z["gf_eqv_0"]).max() < 5e-6
+    assert np.array_equal(np.load(f"{out_dir}/1.npy"), sentinel)
+    det_dir = f"{cache}/{ds.name}/det_score"
+    os.makedirs(det_dir)
+    np.save(f"{det_dir}/1.npy", np.zeros(3))
+    rt.yoho_det(cfg).run(ds)
+    s = np.load(f"{det_dir}/0.npy")
+    assert s.shape == (n,) and np.array_equal(np.sort(s), (np.arange(n) / n).astype(s.dtype))    # a permutation of rank / N
+    assert np.mean(np.abs(s - z["det_score_0"]) * n <= 1.0) > 0.98                          # ranks agree up to float32 near-ties
+    assert np.array_equal(np.load(f"{det_dir}/1.npy"), np.zeros(3))
+    with pytest.raises(ValueError):
+        rt.yoho_des(_cfg(cache, model_fn=str(tmp_path / "none"))).run(ds)
