@@ -135,7 +135,35 @@ class HostRDNet:
         return torch.from_numpy(O.rd_forward(_np(x), self.sd, self.ctx.tables.nei, self.ctx.tables.perm))
 
 
+class HostETNet:
+    """Stand-in for roreg_b200.nets.ETNet: forward(before0, rows, before1, rows, after0, rows, after1, rows, pre_idx) -> [K,4]."""
+
+    def __init__(self, ctx, sd, npass=3, chunk=1000):
+        self.ctx, self.sd = ctx, sd
+
+    def forward(self, before0, rows_b0, before1, rows_b1, after0, rows_a0, after1, rows_a1, pre_idx):
+        r = lambda t, i: _np(t)[_np(i).astype(np.int64)]
+        q = O.et_forward(r(before0, rows_b0), r(before1, rows_b1), r(after0, rows_a0), r(after1, rows_a1),
+                         _np(pre_idx).astype(np.int64), self.sd, self.ctx.tables.nei, self.ctx.tables.perm)
+        return torch.from_numpy(q)
+
+
+class HostMatchOT:
+    """Stand-in for roreg_b200.matchot.MatchOT: forward(src_eqv, tgt_eqv, keys_src, keys_tgt) -> (matches0, scores0)."""
+
+    def __init__(self, ctx, sd, npass=3, sinkhorn_iters=100):
+        self.ctx, self.sd, self.iters = ctx, sd, sinkhorn_iters
+
+    def forward(self, src_eqv, tgt_eqv, keys_src, keys_tgt):
+        out = O.match_ot_forward(_np(src_eqv), _np(tgt_eqv), _np(keys_src), _np(keys_tgt), self.sd, self.ctx.tables.perm, self.iters)
+        return torch.from_numpy(np.asarray(out[0]).astype(np.int32)), torch.from_numpy(np.asarray(out[1]).astype(np.float32))
+
+
 def install_nets(monkeypatch):
+    import roreg_b200.nets as nets_mod
+    import roreg_b200.matchot as matchot_mod
+    monkeypatch.setattr(matchot_mod, "MatchOT", HostMatchOT, raising=True)
+    monkeypatch.setattr(nets_mod, "ETNet", HostETNet, raising=True)
     import roreg_b200.test.extractor as extractor
     import roreg_b200.test.detector as detector
     monkeypatch.setattr(extractor.nets, "GFNet", HostGFNet, raising=True)

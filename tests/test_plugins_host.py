@@ -192,3 +192,59 @@ def test_per_cloud_plugins_on_host(tmp_path, monkeypatch):
     assert np.array_equal(np.load(f"{det_dir}/1.npy"), np.zeros(3))
     with pytest.raises(ValueError):
         rt.yoho_des(_cfg(cache, model_fn=str(tmp_path / "none"))).run(ds)
+
+
+def test_yohoo_run_end_to_end_on_host(tmp_path, monkeypatch):
+    """yohoo.run = Rindex + Rt_pre (ET network, side swap of test/estimator.py:293-306, pose arithmetic :349-366) + one-shot
+    RANSAC, with the ET forward pass from the oracle: Trans_pre and the final files against the reference-written fixture."""
+    import torch
+    from oracle import roreg_oracle as O
+    _host_ctx.install(monkeypatch); _host_ctx.install_nets(monkeypatch)
+    import roreg_b200.test as rt
+    z, n, keynum, max_iter, seeds = load_golden("s256")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/s256", max_res_deg=2.0)
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    model_fn = str(tmp_path / "ckpt"); os.makedirs(f"{model_fn}/ET")
+    torch.save({"best_para": 0, "network_state_dict": {k: torch.from_numpy(v) for k, v in O.random_state_dict("ET", 102).items()}},
+               f"{model_fn}/ET/model_best.pth")
+    cfg = _cfg(cache, model_fn=model_fn)
+    base = f"{cache}/{ds.name}/match_{keynum}"
+    os.makedirs(f"{base}/scores")
+    for (id0, id1) in ds.pair_ids:                                   # matcher output of the reference run
+        np.save(f"{base}/{id0}-{id1}.npy", z[f"match_{id0}-{id1}"]); np.save(f"{base}/scores/{id0}-{id1}.npy", z[f"scores_{id0}-{id1}"])
+    np.random.seed(4321)
+    rt.name2estimator["yohoo"](cfg).run(ds, keynum, max_iter)
+    for (id0, id1) in ds.pair_ids:
+        tr = np.load(f"{base}/Trans_pre/{id0}-{id1}.npy")
+        assert tr.dtype == np.float64 and tr.shape == z[f"trans_pre_{id0}-{id1}"].shape
+        assert np.abs(tr - z[f"trans_pre_{id0}-{id1}"]).max() < 2e-5          # float32 network, tolerance of tests/test_oracle_golden.py
+        r = np.load(f"{base}/yohoo/{max_iter}iters/{id0}-{id1}.npz")
+        assert int(r["recalltime"]) == int(z[f"yohoo_recall_{id0}-{id1}"])
+        assert np.abs(r["trans"] - z[f"yohoo_trans_{id0}-{id1}"]).max() < 1e-4
+    assert os.path.exists(f"{base}/yohoo/{max_iter}iters/pre.log")
+
+
+def test_yoho_mat_plugin_on_host(tmp_path, monkeypatch):
+    """yoho_mat.run (test/matcher.py:152-210): sampling, the source / target swap, index mapping back through the samples, float32
+    scores - with Match_ot's forward pass from the oracle; files against tests/golden/rm300.npz (unmodified reference)."""
+    import torch
+    from oracle import roreg_oracle as O
+    _host_ctx.install(monkeypatch); _host_ctx.install_nets(monkeypatch)
+    import roreg_b200.test as rt
+    z, n, keynum, _, seeds = load_golden("rm300")
+    ds = synth.SynthDataset(seeds, n=n, name="synth/rm", with_fcgf=False)
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    model_fn = str(tmp_path / "ckpt"); os.makedirs(f"{model_fn}/RM")
+    torch.save({"best_para": 0, "network_state_dict": {k: torch.from_numpy(np.asarray(v)) for k, v in O.random_state_dict("RM", 104).items()}},
+               f"{model_fn}/RM/model_best.pth")
+    cfg = _cfg(cache, model_fn=model_fn, RM=True)
+    np.random.seed(2468)
+    rt.name2matcher["yoho_mat"](cfg).run(ds, keynum)
+    for (id0, id1) in ds.pair_ids:
+        m = np.load(f"{cache}/synth/rm/match_{keynum}/{id0}-{id1}.npy"); s = np.load(f"{cache}/synth/rm/match_{keynum}/scores/{id0}-{id1}.npy")
+        ref = z[f"match_{id0}-{id1}"]
+        assert m.dtype == ref.dtype and s.dtype == z[f"scores_{id0}-{id1}"].dtype == np.float32
+        a = {tuple(r) for r in m.tolist()}; b = {tuple(r) for r in ref.tolist()}
+        assert len(a ^ b) <= max(2, len(b) // 50), (len(a), len(b), len(a ^ b))      # float32 top-k / argmax near ties (as the GPU test)
+        if np.array_equal(m, ref):
+            assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-3
