@@ -6,6 +6,8 @@ set -x
 mkdir -p gpurun_out
 ROREG_TEST_EXPERIMENTAL=1 timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or ransac or pipelined" > gpurun_out/n01_pytest_experimental.txt 2>&1
 tail -4 gpurun_out/n01_pytest_experimental.txt
+ROREG_TEST_EXPERIMENTAL=1 timeout 900 python -m pytest tests/test_gpu_dropin.py tests/test_gpu_nets.py tests/test_gpu_matchot.py -x -q -m gpu > gpurun_out/n01_pytest_plugins.txt 2>&1
+tail -4 gpurun_out/n01_pytest_plugins.txt
 ROREG_TEST_EXPERIMENTAL=1 timeout 300 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "score_mode1 or pipelined" > gpurun_out/n01_sanitizer.txt 2>&1
 tail -3 gpurun_out/n01_sanitizer.txt
 for m in 0 1; do
