@@ -248,3 +248,45 @@ def test_yoho_mat_plugin_on_host(tmp_path, monkeypatch):
         assert len(a ^ b) <= max(2, len(b) // 50), (len(a), len(b), len(a ^ b))      # float32 top-k / argmax near ties (as the GPU test)
         if np.array_equal(m, ref):
             assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-3
+
+
+def test_host_rules_equal_the_oracle_on_random_inputs():
+    """The plugin-side host rules (roreg_b200/test/_hostlogic.py) against the oracle's independent restatements on seeded random
+    inputs beyond the fixtures: heavy score ties, tiny buckets, --RM thresholds around the `max(.., 10)` floor, degenerate triplets."""
+    from oracle import roreg_oracle as O
+    from roreg_b200.test import _hostlogic as host
+    rng = np.random.RandomState(42)
+    for trial in range(40):
+        n = int(rng.randint(20, 400)); k = 5
+        keys = rng.rand(n, 3)
+        scores = rng.rand(n) if trial % 3 else np.round(rng.rand(n) * 6) / 6          # every third trial: many equal scores
+        _, nn = O.knn(keys.astype(np.float32), keys.astype(np.float32), k)
+        for num in (1, n // 7 + 1, n // 2, n - 1, n):
+            assert np.array_equal(host.nms_select(scores, nn, num), O.nms_sample(keys, scores, num, k)), (trial, num)
+    for trial in range(40):
+        K = int(rng.randint(1, 300))
+        dr = rng.randint(0, 60 if trial % 2 else 7, K)
+        members, prob = host.rotation_buckets(dr)
+        ref_members, ref_prob = O.dr_statistic(dr)
+        assert np.array_equal(prob, ref_prob)
+        assert (members is None) == (ref_members is None)
+        if members is not None:
+            assert all(np.array_equal(members[r], np.asarray(ref_members[r], np.int64)) for r in range(60))
+    for K in (3, 9, 10, 19, 20, 21, 57, 500):
+        s = rng.rand(K).astype(np.float32)
+        for match_n in (0.05, 0.5, 0.998, 0.9995, 5, 40):
+            assert np.array_equal(host.top_scored(s, match_n), O.select_hypotheses(s, K, True, match_n)), (K, match_n)
+    for trial in range(50):
+        p0 = rng.rand(3, 3) * 3; p1 = rng.rand(3, 3) * 3
+        if trial % 10 == 0:
+            p1[2] = p1[1]                                                             # repeated point: rank-1 cross-covariance
+        assert np.array_equal(host.kabsch_3pt(p0, p1), O.threepps2tran(p0, p1))
+    # the guided draw loop consumes the global RNG exactly as the oracle's restatement of test/estimator.py:221-228
+    dr = rng.randint(0, 12, 150)
+    members, prob = host.rotation_buckets(dr)
+    np.random.seed(31); mine = host.draw_guided_triplets(members, prob, 64)
+    np.random.seed(31); ref, _, _ = O.yohoc_draws(dr, 64)
+    assert mine.shape == (64, 3) and np.array_equal(mine, np.stack([d[1] for d in ref]))
+    np.random.seed(31); host.draw_guided_triplets(members, prob, 64); after_mine = np.random.rand()
+    np.random.seed(31); O.yohoc_draws(dr, 64); after_ref = np.random.rand()
+    assert after_mine == after_ref                                                    # same RNG state afterwards
