@@ -1,6 +1,7 @@
 #!/bin/bash
 # First gpurun call of the next round (prepared at the end of round 1, when the GPU budget was spent; NOT run yet).
-# 1. confirm the opt-in paths that were written without a GPU: score mode 1 (float32 pre-filter, kernels_ransac.cuh);
+# 1. confirm what was written without a GPU: score mode 1 (float32 pre-filter, kernels_ransac.cuh), the rewritten plugin mirrors,
+#    the RD/RM drop-in test and the scene driver (roreg_b200/scene.py);
 # 2. A/B the bench with and without it, and with the pipelined entry point (roreg_register_batch_pipelined); 3. multi-rank e2e with / without the NUMA binding of bench.py.
 set -x
 mkdir -p gpurun_out

@@ -91,6 +91,30 @@ class HostContext:
         mask = torch.from_numpy(O.inlier_mask(k0, k1, T0, radius).astype(np.uint8)) if want_mask else None
         return torch.from_numpy(O.refine_once(k0, k1, T0, s, radius)), mask
 
+    def register_batch(self, desc, keys, pair_cloud, keynum=None, sample=None, nn_mode=0, estimator=0, max_iter=1000,
+                       ird=0.1, seed=0, triplets=None, hyps=None, out=None):
+        """Oracle version of the batched engine (estimator 0, draws from a per-pair NumPy RandomState instead of the device's
+        counter-based RNG): same output dict layout as ops.Context.register_batch."""
+        assert estimator == 0 and triplets is None and hyps is None
+        D = _np(desc); Kp = _np(keys); pc = _np(pair_cloud); B = pc.shape[0]; n = D.shape[1]; S = keynum or n
+        smp = None if sample is None else _np(sample).astype(np.int64)
+        o = dict(matches=np.zeros((B, S, 2), np.int32), n_matches=np.zeros(B, np.int32), dr_index=np.zeros((B, S), np.int32),
+                 poses=np.zeros((B, 4, 4)), recall=np.full(B, -1, np.int32), best_overlap=np.zeros(B))
+        for p in range(B):
+            f0, f1 = D[pc[p, 0]], D[pc[p, 1]]
+            pps, sc = O.mutual_run(f0, f1, None if smp is None else smp[p, 0], None if smp is None else smp[p, 1])
+            k = pps.shape[0]
+            o["n_matches"][p] = k
+            if k == 0:
+                continue
+            dr = O.rindex(f0, f1, pps, self.tables.perm)
+            o["matches"][p, :k] = pps; o["dr_index"][p, :k] = dr
+            T, rec, info = O.yohoc_ransac(Kp[pc[p, 0]][pps[:, 0]], Kp[pc[p, 1]][pps[:, 1]], sc, dr, ird, max_iter,
+                                          rng=np.random.RandomState((int(seed) + p) % (2 ** 31)))
+            if T is not None and rec > 0:
+                o["poses"][p] = T; o["recall"][p] = rec; o["best_overlap"][p] = info["best_overlap"]
+        return {k: torch.from_numpy(v) for k, v in o.items()}
+
     def kabsch3(self, k0s, k1s, triplets):
         k0 = _np(k0s); k1 = _np(k1s)
         return torch.from_numpy(np.stack([O.threepps2tran(k0[t], k1[t]) for t in _np(triplets).astype(np.int64)]))
