@@ -48,3 +48,5 @@ print("pipelined, score mode 1, $cap scoring CTAs per SM, tail priority $prio:",
 PY
   done
 done
+# Registration-Recall parity on synthetic pairs of graded difficulty (CUDA engine vs reference arithmetic on the host)
+timeout 900 python scripts/rr_parity.py --pairs 200 --n 2000 > gpurun_out/n01_rr_parity.json 2> gpurun_out/n01_rr_parity.err; cat gpurun_out/n01_rr_parity.json
