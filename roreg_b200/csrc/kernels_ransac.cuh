@@ -289,8 +289,8 @@ __global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a, int 
     sk[tid][3] = y[0]; sk[tid][4] = y[1]; sk[tid][5] = y[2]; sk[tid][6] = s;
     sa[tid] = make_float4((float)x[0], (float)x[1], (float)x[2], 0.f);
     sb[tid] = make_float4((float)y[0], (float)y[1], (float)y[2], 0.f);
-    am = __double2float_ru(fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2]))));
-    bm = __double2float_ru(fmax(fabs(y[0]), fmax(fabs(y[1]), fabs(y[2]))));
+    am = f32_at_or_above(fmax(fabs(x[0]), fmax(fabs(x[1]), fabs(x[2]))));
+    bm = f32_at_or_above(fmax(fabs(y[0]), fmax(fabs(y[1]), fabs(y[2]))));
     if (!(am == am)) am = __int_as_float(0x7f800000);          // NaN coordinates: widen the band to everything
     if (!(bm == bm)) bm = __int_as_float(0x7f800000);
   }
@@ -307,28 +307,17 @@ __global__ void __launch_bounds__(256) ransac_score_pre_kernel(ScoreArgs a, int 
     const long long src = a.order ? a.order[h] : h;
     const double* Tp = a.hyps + p * a.hyp_pair_stride + src * 12;
     float T[12];
-    double rrow = 0.0, tmax = 0.0;
+    double Td[12];
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc) {
-      const double r0 = Tp[4 * cc], r1 = Tp[4 * cc + 1], r2_ = Tp[4 * cc + 2], t = Tp[4 * cc + 3];
-      T[4 * cc] = (float)r0; T[4 * cc + 1] = (float)r1; T[4 * cc + 2] = (float)r2_; T[4 * cc + 3] = (float)t;
-      rrow = fmax(rrow, fabs(r0) + fabs(r1) + fabs(r2_));
-      tmax = fmax(tmax, fabs(t));
-    }
-    const double u = 5.9604644775390625e-8;                                    // 2^-24
-    const double E = u * (Amax + 6.0 * (rrow * Bmax + tmax));
-    const double m = 2.0 * (3.4641016151377549 * E * a.r + 4.0 * E * E + 6.0 * u * a.r2);
+    for (int j = 0; j < 12; ++j) { Td[j] = Tp[j]; T[j] = (float)Td[j]; }
+    const double m = prefilter_band(Td, Amax, Bmax, a.r, a.r2);                 // math3.cuh (shared with the host test)
     // NaN in T (fmax drops NaN operands) must reach the float64 path: the float products below are NaN then, both comparisons false
-    const float lo = __double2float_rd(a.r2 - m), hi = __double2float_ru(a.r2 + m);
+    const float lo = f32_at_or_below(a.r2 - m), hi = f32_at_or_above(a.r2 + m);
     const bool weighted = a.mv.scores != nullptr;
     int n_in = 0;
     auto dist2 = [&](int k) -> float {
       const float4 pa = sa[k], pb = sb[k];
-      const float x = fmaf(T[0], pb.x, fmaf(T[1], pb.y, fmaf(T[2], pb.z, T[3])));
-      const float y = fmaf(T[4], pb.x, fmaf(T[5], pb.y, fmaf(T[6], pb.z, T[7])));
-      const float z = fmaf(T[8], pb.x, fmaf(T[9], pb.y, fmaf(T[10], pb.z, T[11])));
-      const float dx = pa.x - x, dy = pa.y - y, dz = pa.z - z;
-      return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+      return prefilter_dist2(T, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z);
     };
     auto count = [&](int k, bool in) {
       if (weighted) { if (in) acc += sk[k][6]; }      // same order of float64 additions as ransac_score_kernel

@@ -173,4 +173,49 @@ RR_HD void quat_times_anchor(const float q[4], const float Rg[9], double R[9]) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One-shot scoring, float32 pre-filter (score mode 1, kernels_ransac.cuh ransac_score_pre_kernel).  The per-test arithmetic
+// lives here so that the host build (tests/test_score_prefilter_bound.py) runs the very expressions the kernel runs.
+// ---------------------------------------------------------------------------------------------
+// float32 at or below / at or above a float64 value
+RR_HD float f32_at_or_below(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2float_rd(x);
+#else
+  const float f = (float)x;
+  return ((double)f > x) ? nextafterf(f, -INFINITY) : f;
+#endif
+}
+RR_HD float f32_at_or_above(double x) {
+#ifdef __CUDA_ARCH__
+  return __double2float_ru(x);
+#else
+  const float f = (float)x;
+  return ((double)f < x) ? nextafterf(f, INFINITY) : f;
+#endif
+}
+
+// Half-width m of the undecided band around r2 for hypothesis T = [R|t] (row-major 3x4, float64) against points whose
+// coordinates are bounded by amax (k0 side) and bmax (k1 side); u = 2^-24:
+//   E = u (amax + 6 (max_c sum_j |R_cj| * bmax + max_c |t_c|)),  m = 2 (2 sqrt(3) E r + 4 E^2 + 6 u r2)     (derivation: kernels_ransac.cuh)
+RR_HD double prefilter_band(const double T[12], double amax, double bmax, double r, double r2) {
+  double rrow = 0.0, tmax = 0.0;
+  for (int c = 0; c < 3; ++c) {
+    rrow = fmax(rrow, fabs(T[4 * c]) + fabs(T[4 * c + 1]) + fabs(T[4 * c + 2]));
+    tmax = fmax(tmax, fabs(T[4 * c + 3]));
+  }
+  const double u = 5.9604644775390625e-8;
+  const double E = u * (amax + 6.0 * (rrow * bmax + tmax));
+  return 2.0 * (3.4641016151377549 * E * r + 4.0 * E * E + 6.0 * u * r2);
+}
+
+// float32 squared distance |a - (R b + t)|^2 with the fixed fma order the bound is derived for
+RR_HD float prefilter_dist2(const float T[12], float ax, float ay, float az, float bx, float by, float bz) {
+  const float x = fmaf(T[0], bx, fmaf(T[1], by, fmaf(T[2], bz, T[3])));
+  const float y = fmaf(T[4], bx, fmaf(T[5], by, fmaf(T[6], bz, T[7])));
+  const float z = fmaf(T[8], bx, fmaf(T[9], by, fmaf(T[10], bz, T[11])));
+  const float dx = ax - x, dy = ay - y, dz = az - z;
+  return fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+}
+
 }  // namespace roreg

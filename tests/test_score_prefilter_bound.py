@@ -109,3 +109,42 @@ def test_synthetic_workload_band_fraction():
     ex, _ = exact(T, a, b, r)
     assert np.array_equal(inl[dec], ex[dec])
     assert (~dec).mean() < 1e-3
+
+
+def _host_prefilter(T, a, b, r):
+    """The kernel's own expressions (roreg_b200/csrc/math3.cuh: prefilter_band, prefilter_dist2, f32_at_or_below / above) compiled
+    for the host - real fmaf, real float32 - through libmath3_host.so."""
+    import ctypes
+    from test_math3_host import _lib, dp
+    L = _lib()
+    H, K = T.shape[0], a.shape[0]
+    T = np.ascontiguousarray(T.reshape(H, 12)); a = np.ascontiguousarray(a); b = np.ascontiguousarray(b)
+    dec = np.empty((H, K), np.int8); band = np.empty((H, (K + 255) // 256))
+    L.rr_host_prefilter(T.ctypes.data_as(dp), H, a.ctypes.data_as(dp), b.ctypes.data_as(dp), K, ctypes.c_double(r),
+                        dec.ctypes.data_as(ctypes.POINTER(ctypes.c_int8)), band.ctypes.data_as(dp))
+    return dec, band
+
+
+def test_kernel_source_on_the_host_never_decides_wrongly():
+    """Same adversarial cases through the HOST BUILD of the kernel's arithmetic: every decided test equals the float64 decision,
+    the undecided ones are within the band, and the per-tile band is no wider than the whole-cloud band of the NumPy replay."""
+    rng = np.random.RandomState(11)
+    total = undecided = 0
+    for scale, tscale, r in [(3.0, 3.0, 0.1), (3.0, 8.0, 0.1), (50.0, 50.0, 0.5), (1.0, 0.5, 0.02), (10.0, 100.0, 0.1), (3.0, 3.0, 0.1)]:
+        T, a, b = case(rng, scale, tscale, r, H=40, K=3000)
+        dec, band = _host_prefilter(T, a, b, r)
+        ex, d2 = exact(T, a, b, r)
+        decided = dec != 2
+        assert np.array_equal(dec[decided] == 1, ex[decided]), (scale, tscale, r)
+        m_full = np.repeat(band, 256, axis=1)[:, :a.shape[0]]
+        assert np.all(np.abs(d2[~decided] - r * r) <= 1.5 * m_full[~decided] + 1e-12)
+        _, _, m_numpy = prefilter(T, a, b, r)
+        assert np.all(band <= m_numpy[:, None] * (1 + 1e-12))
+        planted = (np.arange(a.shape[0])[None, :] % T.shape[0]) == np.arange(T.shape[0])[:, None]
+        total += (~planted).sum(); undecided += (~decided & ~planted).sum()
+    assert undecided <= 1e-3 * total
+    # hypotheses with NaN / inf entries never decide anything (the kernel sends them to float64)
+    T, a, b = case(rng, 3.0, 3.0, 0.1, H=4, K=300)
+    T[0, 1, 1] = np.nan; T[1, 2, 3] = np.inf; T[2, 0, 0] = -np.inf
+    dec, _ = _host_prefilter(T, a, b, 0.1)
+    assert np.all(dec[:3] == 2)
