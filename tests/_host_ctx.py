@@ -12,6 +12,16 @@ def _np(t):
     return None if t is None else (t.detach().cpu().numpy() if torch.is_tensor(t) else np.asarray(t))
 
 
+def _chk(t, dtype, name, optional=False):
+    """What the C ABI assumes about every buffer it is handed (ops.Context._chk checks some of these, the kernels assume the rest):
+    a contiguous torch tensor of exactly this dtype."""
+    if t is None:
+        assert optional, f"{name}: required"
+        return
+    dts = dtype if isinstance(dtype, tuple) else (dtype,)
+    assert torch.is_tensor(t) and t.dtype in dts and t.is_contiguous(), f"{name}: need a contiguous {dts} tensor, got {getattr(t, 'dtype', type(t))}"
+
+
 class HostContext:
     def __init__(self, so3_dir=None):
         self.tables = group.load(so3_dir)
@@ -26,22 +36,26 @@ class HostContext:
         return (t.to(dtype) if dtype is not None else t).contiguous()
 
     def inv_pool(self, eqv, sample=None, normalise=True):
+        _chk(eqv, torch.float32, "eqv"); _chk(sample, torch.int32, "sample", True)
         f = _np(eqv)
         if sample is not None:
             f = f[_np(sample).astype(np.int64)]
         return torch.from_numpy(O.inv_pool(f, normalise))
 
     def knn(self, target, source, k=1):
+        _chk(target, torch.float32, "target"); _chk(source, torch.float32, "source")
         d, i = O.knn(_np(target), _np(source), k)
         return torch.from_numpy(d), torch.from_numpy(i.astype(np.int32))
 
     def mutual_match(self, f0, f1, mode=0):
+        _chk(f0, torch.float32, "f0"); _chk(f1, torch.float32, "f1")
         pps, nn01, nn10 = O.mutual_matches(_np(f0), _np(f1))
         out = np.zeros((min(f0.shape[0], f1.shape[0]), 2), np.int32); out[:pps.shape[0]] = pps
         return (torch.from_numpy(out), torch.tensor([pps.shape[0]], dtype=torch.int32), torch.from_numpy(nn01.astype(np.int32)),
                 torch.from_numpy(nn10.astype(np.int32)))
 
     def group_corr(self, X, Y, idxX=None, idxY=None, variant=1, want_cor=True, want_argmax=True):
+        _chk(X, torch.float32, "X"); _chk(Y, torch.float32, "Y"); _chk(idxX, torch.int32, "idxX", True); _chk(idxY, torch.int32, "idxY", True)
         x = _np(X); y = _np(Y)
         if idxX is not None:
             x = x[_np(idxX).astype(np.int64)]
@@ -53,6 +67,7 @@ class HostContext:
                 torch.from_numpy(np.argmax(cor, 1).astype(np.int32)) if want_argmax else None)
 
     def hypotheses_from_quat(self, quat, pre_idx, k0m, k1m):
+        _chk(quat, torch.float32, "quat"); _chk(pre_idx, torch.int32, "pre_idx"); _chk(k0m, torch.float64, "k0m"); _chk(k1m, torch.float64, "k1m")
         return torch.from_numpy(O.hypotheses_from_quat(_np(quat), _np(pre_idx), _np(k0m), _np(k1m), self.tables.rot))
 
     @staticmethod
@@ -60,6 +75,8 @@ class HostContext:
         return np.ones(K) if scores is None else _np(scores)
 
     def ransac_oneshot(self, k0m, k1m, scores, trans, order, ird, want_overlaps=False):
+        _chk(k0m, torch.float64, "k0m"); _chk(k1m, torch.float64, "k1m"); _chk(scores, (torch.float32, torch.float64), "scores", True)
+        _chk(trans, torch.float64, "trans"); _chk(order, torch.int32, "order", True)
         T = _np(trans)
         if order is not None:
             T = T[_np(order).astype(np.int64)]
@@ -78,6 +95,8 @@ class HostContext:
         return T[j]
 
     def refine(self, k0m, k1m, scores, T_in, ird, order=None, T_index=None, want_mask=False):
+        _chk(k0m, torch.float64, "k0m"); _chk(k1m, torch.float64, "k1m"); _chk(scores, (torch.float32, torch.float64), "scores", True)
+        _chk(T_in, torch.float64, "T_in"); _chk(order, torch.int32, "order", True); _chk(T_index, torch.int32, "T_index", True)
         k0 = _np(k0m); k1 = _np(k1m); s = self._scores(scores, k0.shape[0])
         T0 = self._pick(T_in, order, T_index)
         T1 = O.refine_once(k0, k1, T0, s, 2.0 * ird)
@@ -86,6 +105,8 @@ class HostContext:
         return torch.from_numpy(T2), mask
 
     def refine_once(self, k0m, k1m, scores, T_in, radius, want_mask=False):
+        _chk(k0m, torch.float64, "k0m"); _chk(k1m, torch.float64, "k1m"); _chk(scores, (torch.float32, torch.float64), "scores", True)
+        _chk(T_in, torch.float64, "T_in")
         k0 = _np(k0m); k1 = _np(k1m); s = self._scores(scores, k0.shape[0])
         T0 = _np(T_in)
         mask = torch.from_numpy(O.inlier_mask(k0, k1, T0, radius).astype(np.uint8)) if want_mask else None
@@ -96,6 +117,7 @@ class HostContext:
         """Oracle version of the batched engine (estimator 0, draws from a per-pair NumPy RandomState instead of the device's
         counter-based RNG): same output dict layout as ops.Context.register_batch."""
         assert estimator == 0 and triplets is None and hyps is None
+        _chk(desc, torch.float32, "desc"); _chk(keys, torch.float64, "keys"); _chk(pair_cloud, torch.int32, "pair_cloud"); _chk(sample, torch.int32, "sample", True)
         D = _np(desc); Kp = _np(keys); pc = _np(pair_cloud); B = pc.shape[0]; n = D.shape[1]; S = keynum or n
         smp = None if sample is None else _np(sample).astype(np.int64)
         o = dict(matches=np.zeros((B, S, 2), np.int32), n_matches=np.zeros(B, np.int32), dr_index=np.zeros((B, S), np.int32),
@@ -116,6 +138,7 @@ class HostContext:
         return {k: torch.from_numpy(v) for k, v in o.items()}
 
     def kabsch3(self, k0s, k1s, triplets):
+        _chk(k0s, torch.float64, "k0s"); _chk(k1s, torch.float64, "k1s"); _chk(triplets, torch.int32, "triplets")
         k0 = _np(k0s); k1 = _np(k1s)
         return torch.from_numpy(np.stack([O.threepps2tran(k0[t], k1[t]) for t in _np(triplets).astype(np.int64)]))
 

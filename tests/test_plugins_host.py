@@ -290,3 +290,20 @@ def test_host_rules_equal_the_oracle_on_random_inputs():
     np.random.seed(31); host.draw_guided_triplets(members, prob, 64); after_mine = np.random.rand()
     np.random.seed(31); O.yohoc_draws(dr, 64); after_ref = np.random.rand()
     assert after_mine == after_ref                                                    # same RNG state afterwards
+
+
+def test_yohoc_run_device_mode_on_host(tmp_path, monkeypatch):
+    """yohoc.run end to end (Rindex + ransac + pre.log) with cfg.yohoc_mode = 'device' (private Generator draws + kabsch3 entry point):
+    CPU twin of tests/test_gpu_dropin.py::test_yohoc_run_device_mode."""
+    _host_ctx.install(monkeypatch)
+    import roreg_b200.test as rt
+    ds = synth.SynthDataset([61, 62], n=300, name="synth/dev")
+    cache = str(tmp_path / "cache"); ds.write_cache(cache)
+    cfg = _cfg(cache, yohoc_mode="device")
+    np.random.seed(9)
+    rt.mutual(cfg).run(ds, 300)
+    rt.yohoc(cfg).run(ds, 300, 200)
+    for pi, (id0, id1) in enumerate(ds.pair_ids):
+        r = np.load(f"{cache}/{ds.name}/match_300/yohoc/200iters/{id0}-{id1}.npz")
+        assert 1 <= int(r["recalltime"]) <= 200 and np.abs(r["trans"][:3] - ds.pairs[pi]["gt"]).max() < 1e-2
+    assert os.path.exists(f"{cache}/{ds.name}/match_300/yohoc/200iters/pre.log")
