@@ -29,6 +29,8 @@ def test_reference_arm_prints_the_contract_line():
     cb = d["cpu_baseline"]
     assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
     assert "workload" in d["config"] and "model" not in d["config"]
+    # value = the reference's own tensor operations (oracle/torch_mirror.py); the optimised C port is reported beside it
+    assert "torch_mirror" in cb["sample"] and cb["optimised_c_port"]["value"] > 0
 
 
 def test_reference_arm_other_ranks_exit_without_work():
