@@ -164,3 +164,19 @@ def test_oracle_nms_sampler_and_yohoc_helpers_equal_reference():
         T, recall, _ = O.yohoc_ransac(k0m, k1m, s, z[f"dr_index_{id0}-{id1}"], 0.1, max_iter, RM=True, match_n=0.5,
                                       rng=np.random.RandomState(555 + pi))
         assert recall == int(z[f"yohoc_recall_{id0}-{id1}"]) and np.abs(T - z[f"yohoc_trans_{id0}-{id1}"]).max() < 1e-10
+
+
+def test_kat_equivariance_and_invariance_of_the_oracle_networks(tables):
+    """permuting the input's group axis by P[a] permutes the GF output the same way (and leaves the
+    detector's saliency and the invariant pooling unchanged); ET's residual quaternion is unchanged when both sides are permuted."""
+    rng = np.random.default_rng(5)
+    sd_gf = O.random_state_dict("GF", 101); sd_rd = O.random_state_dict("RD", 103)
+    x = rng.standard_normal((6, 32, 60)).astype(np.float32)
+    y, _ = O.gf_forward(x, sd_gf, tables.nei)
+    s = O.rd_forward(y, sd_rd, tables.nei, tables.perm)
+    for a in (1, 7, 33, 59):
+        ya, _ = O.gf_forward(np.ascontiguousarray(x[:, :, tables.perm[a]]), sd_gf, tables.nei)
+        assert np.abs(ya - y[:, :, tables.perm[a]]).max() < 2e-6
+        assert np.abs(O.inv_pool(ya) - O.inv_pool(y)).max() < 1e-6
+        sa = O.rd_forward(np.ascontiguousarray(y[:, :, tables.perm[a]]), sd_rd, tables.nei, tables.perm)
+        assert np.abs(sa - s).max() < 1e-5 * max(1.0, np.abs(s).max())
