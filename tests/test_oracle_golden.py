@@ -168,7 +168,7 @@ def test_oracle_nms_sampler_and_yohoc_helpers_equal_reference():
 
 def test_kat_equivariance_and_invariance_of_the_oracle_networks(tables):
     """permuting the input's group axis by P[a] permutes the GF output the same way (and leaves the
-    detector's saliency and the invariant pooling unchanged); ET's residual quaternion is unchanged when both sides are permuted."""
+    detector's saliency and the invariant pooling unchanged)."""
     rng = np.random.default_rng(5)
     sd_gf = O.random_state_dict("GF", 101); sd_rd = O.random_state_dict("RD", 103)
     x = rng.standard_normal((6, 32, 60)).astype(np.float32)
