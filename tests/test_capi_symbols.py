@@ -50,3 +50,14 @@ def test_ops_fail_loudly_without_cuda():
     from roreg_b200 import ops, _lib
     with pytest.raises(_lib.RoregLibraryError):
         ops.Context(0)
+
+
+def test_header_is_plain_c(tmp_path):
+    """The drop-in boundary is a C ABI: include/roreg_b200.h must compile as C (no C++ or torch types in the signatures) and a C
+    translation unit calling an entry point must link against the shared library."""
+    import subprocess
+    hdr = os.path.join(REPO, "include", "roreg_b200.h")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", "c", hdr])
+    src = tmp_path / "use.c"
+    src.write_text('#include "roreg_b200.h"\nint main(void) { return roreg_version() > 0 ? 0 : 1; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(REPO, "include"), "-c", str(src), "-o", str(tmp_path / "use.o")])
