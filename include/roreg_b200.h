@@ -204,7 +204,7 @@ typedef struct {
   int32_t* n_matches;         /* [B]                                                                */
   int32_t* dr_index;          /* [B][keynum]                                                        */
   double* poses;              /* [B][4][4]                                                          */
-  int32_t* recall;            /* [B] index (yohoo: 0-based, yohoc: 1-based) of the winning hypothesis */
+  int32_t* recall;            /* [B] 0-based index of the winning hypothesis in the scored order, -1 = none */
   double* best_overlap;       /* [B]                                                                */
 } roreg_batch;
 

@@ -526,10 +526,21 @@ def multi_head_attention(q, kf, vf, sd, p):
     return _conv1x1(x.astype(F32), sd, p + ".merge")
 
 
-def cross_attention_block(src, tgt, src_eqv, tgt_eqv, featinv, k, s2t, sd, p, perm):
+def _knn_hook(score, k, p, forced, trace):
+    """Test hook (not a reference function): record the block's score matrix and own top-k in `trace`, and - for the
+    teacher-forced parity test of the CUDA matcher - continue with the neighbour lists given in `forced`."""
+    knn = knn_index_desc(score, k)
+    if trace is not None:
+        trace[p] = dict(score=score, knn=knn)
+    if forced is not None and p in forced:
+        knn = np.asarray(forced[p]).astype(np.int64)
+    return knn
+
+
+def cross_attention_block(src, tgt, src_eqv, tgt_eqv, featinv, k, s2t, sd, p, perm, forced=None, trace=None):
     """Cross_attention_block.forward rot_coh_match.py:132-165.  src/tgt/featinv [32,m]/[32,n]; *_eqv [m,32,60]."""
     score = (src.T @ tgt).astype(F32)                      # score_mat
-    knn = knn_index_desc(score, k); nn = knn_index_desc(score, 1)[:, 0]
+    knn = _knn_hook(score, k, p, forced, trace); nn = knn[:, 0]          # :145 argsort(1) = first column of the stable argsort
     knn_fea = tgt[:, knn]                                  # [32,m,k]
     feat = multi_head_attention(src, knn_fea, knn_fea, sd, p + ".cross_attn")
     feat = mlp_2layer(np.concatenate([featinv, src, feat], 0), sd, p + ".merge")
@@ -541,11 +552,11 @@ def cross_attention_block(src, tgt, src_eqv, tgt_eqv, featinv, k, s2t, sd, p, pe
     return feat, rind.T.astype(F32)                        # [32,m], [60,m]
 
 
-def self_attention_block(feat, coor, rind, featinv, k, sd, p):
+def self_attention_block(feat, coor, rind, featinv, k, sd, p, forced=None, trace=None):
     """Self_attention_block.forward rot_coh_match.py:187-210.  feat/featinv [32,m], coor [3,m], rind [60,m]."""
     m = feat.shape[1]
     score = (feat.T @ feat).astype(F32)
-    knn = knn_index_desc(score, k)
+    knn = _knn_hook(score, k, p, forced, trace)
     knn_fea = feat[:, knn]                                 # [32,m,k]
     knn_coor = coor[:, knn] - coor[:, :, None]             # [3,m,k]
     pe = mlp_2layer(knn_coor.reshape(3, m * k).astype(F32), sd, p + ".pos_en").reshape(32, m, k)
@@ -578,7 +589,7 @@ def log_sinkhorn(scores, alpha, iters=100):
     return (Z + u[:, None] + v[None, :] - norm).astype(F32)
 
 
-def match_ot_forward(feats0, feats1, keys0, keys1, sd, perm, iters=100):
+def match_ot_forward(feats0, feats1, keys0, keys1, sd, perm, iters=100, forced=None, trace=None):
     """Match_ot.forward rot_coh_match.py:339-390 for one pair.  feats0/keys0 = the batch's 'source' side
     (test/matcher.py:192-197 feeds cloud id1 there).  Returns matches0 [m] (-1 = none), matching_scores0 [m],
     matches1 [n], matching_scores1 [n], and the OT matrix."""
@@ -588,14 +599,16 @@ def match_ot_forward(feats0, feats1, keys0, keys1, sd, perm, iters=100):
     src, tgt = s_inv, t_inv
     for li, k in enumerate((16, 8)):
         p = f"Graph.merge_blocks.{li}"
-        s2t, r_s = cross_attention_block(src, tgt, src_eqv, tgt_eqv, s_inv, k, True, sd, p + ".cross_graph_s2t", perm)
-        eh_s = self_attention_block(s2t, sc, r_s, s_inv, k, sd, p + ".self_graph_s")
-        t2s, r_t = cross_attention_block(tgt, src, tgt_eqv, src_eqv, t_inv, k, False, sd, p + ".cross_graph_t2s", perm)
-        eh_t = self_attention_block(t2s, tc, r_t, t_inv, k, sd, p + ".self_graph_t")
+        s2t, r_s = cross_attention_block(src, tgt, src_eqv, tgt_eqv, s_inv, k, True, sd, p + ".cross_graph_s2t", perm, forced, trace)
+        eh_s = self_attention_block(s2t, sc, r_s, s_inv, k, sd, p + ".self_graph_s", forced, trace)
+        t2s, r_t = cross_attention_block(tgt, src, tgt_eqv, src_eqv, t_inv, k, False, sd, p + ".cross_graph_t2s", perm, forced, trace)
+        eh_t = self_attention_block(t2s, tc, r_t, t_inv, k, sd, p + ".self_graph_t", forced, trace)
         src, tgt = eh_s, eh_t
     s_fin = mlp_2layer(np.concatenate([s_inv, src], 0), sd, "final_mlp")
     t_fin = mlp_2layer(np.concatenate([t_inv, tgt], 0), sd, "final_mlp")
     score = (s_fin.T @ t_fin).astype(F32)
+    if trace is not None:
+        trace["final_score"] = score
     Z = log_sinkhorn(score, F32(sd["ot_layer.bin_score"]), iters)
     inner = Z[:-1, :-1]
     i0 = inner.argmax(1); i1 = inner.argmax(0)

@@ -23,6 +23,7 @@ class MatchOT:
         self.sd = sd
         self.L = {}
         self.alpha = float(sd["ot_layer.bin_score"])
+        self.trace = None              # set to a dict to record every block's neighbour lists and the final score matrix (parity tests)
 
     # ---------------------------------------------------------------- helpers
     def _f(self, *shape):
@@ -112,6 +113,8 @@ class MatchOT:
         S = self.score(src, m, tgt, n)
         knn = self.topk(S, m, n, k)
         del S
+        if self.trace is not None:
+            self.trace[p] = knn
         nn = knn[:, 0].contiguous()
         knn_fea = self.gather(tgt, knn, 32)
         kA = self.prep([knn_fea], m * k)
@@ -129,6 +132,8 @@ class MatchOT:
         S = self.score(feat, m, feat, m)
         knn = self.topk(S, m, m, k)
         del S
+        if self.trace is not None:
+            self.trace[p] = knn
         knn_fea = self.gather(feat, knn, 32)
         rel = self._f(m * k, 32)
         rc = self.lib.roreg_rel_coor(self.ctx.h, _ptr(coor), _ptr(knn), m, k, C.c_float(0.025), _ptr(rel), _stream())
@@ -163,6 +168,8 @@ class MatchOT:
         s_fin = self.mlp(self.prep([s_inv, src], m), m, "final_mlp")
         t_fin = self.mlp(self.prep([t_inv, tgt], n), n, "final_mlp")
         S = self.score(s_fin, m, t_fin, n)
+        if self.trace is not None:
+            self.trace["final_score"] = S
         u = self._f(m + 1); v = self._f(n + 1)
         matches0 = torch.empty(m, dtype=torch.int32, device=ctx.device); ms0 = self._f(m)
         rc = self.lib.roreg_sinkhorn_match(ctx.h, _ptr(S), m, n, n, C.c_float(self.alpha), self.iters, _ptr(u), _ptr(v), _ptr(matches0),

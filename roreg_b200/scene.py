@@ -127,6 +127,8 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
                         T, r = np.random.rand(4, 4), 50000
                     else:
                         raise ValueError(f"pair {id0}-{id1}: no 3-point hypothesis has a positive overlap")
+                else:
+                    r += 1                                                      # engine: 0-based id of the winner; reference: 1-based iteration (test/estimator.py:226,236)
                 poses[s - lo + j] = T; recall[s - lo + j] = r; counts[s - lo + j] = k
                 writer.submit(_write_pair, lay, max_iter, id0, id1, m, dr, T, r)
     finally:

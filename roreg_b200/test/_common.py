@@ -15,11 +15,11 @@ def context(cfg=None):
     key = (dev, so3)
     if key not in _ctx:
         _ctx[key] = ops.Context(dev, so3_dir=so3)
-        # extension knob (absent from the reference's parser -> default 0 = float32 reference arithmetic under Test.py):
-        # 3 = the tcgen05 fp16 two-accumulator Gram for Des2R / the R-indicator (same argmax outside float32 near ties)
-        cm = getattr(cfg, "corr_mode", None) if cfg is not None else None
-        if cm is not None:
-            _ctx[key].set_corr_mode(int(cm))
+    # extension knob (absent from the reference's parser -> default 0 = float32 reference arithmetic under Test.py):
+    # 3 = the tcgen05 fp16 two-accumulator Gram for Des2R / the R-indicator (same argmax outside float32 near ties).
+    # Applied on EVERY lookup: plugins built from configurations with different corr_mode share the context.
+    cm = getattr(cfg, "corr_mode", None) if cfg is not None else None
+    _ctx[key].set_corr_mode(int(cm) if cm is not None else 0)
     return _ctx[key]
 
 

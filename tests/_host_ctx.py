@@ -134,7 +134,7 @@ class HostContext:
             T, rec, info = O.yohoc_ransac(Kp[pc[p, 0]][pps[:, 0]], Kp[pc[p, 1]][pps[:, 1]], sc, dr, ird, max_iter,
                                           rng=np.random.RandomState((int(seed) + p) % (2 ** 31)))
             if T is not None and rec > 0:
-                o["poses"][p] = T; o["recall"][p] = rec; o["best_overlap"][p] = info["best_overlap"]
+                o["poses"][p] = T; o["recall"][p] = rec - 1; o["best_overlap"][p] = info["best_overlap"]
         return {k: torch.from_numpy(v) for k, v in o.items()}
 
     def kabsch3(self, k0s, k1s, triplets):

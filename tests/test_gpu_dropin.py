@@ -97,8 +97,6 @@ def test_missing_checkpoint_raises_like_the_reference():
         rt.yoho_des(cfg).run(types.SimpleNamespace(name="x", pc_ids=[], pair_ids=[]))
 
 
-@pytest.mark.skipif(os.environ.get("ROREG_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's GPU budget was spent: not yet confirmed on a B200 (set ROREG_TEST_EXPERIMENTAL=1)")
 def test_rd_rm_paths_reproduce_reference_files(tmp_path):
     """--RD (NMS sampling on detector scores, device 5-NN) and --RM (top-`match_n` selection by score, float32 match scores)
     through the real context, against tests/golden/s400rdrm.npz (tests/golden/make_golden_rd_rm.py, unmodified reference).
@@ -142,8 +140,6 @@ def test_rd_rm_paths_reproduce_reference_files(tmp_path):
             assert np.abs(r["trans"] - z[f"{est}_trans_{id0}-{id1}"]).max() < 2e-6, est   # float32 weights, normalised in float32 by the reference
 
 
-@pytest.mark.skipif(os.environ.get("ROREG_TEST_EXPERIMENTAL") != "1",
-                    reason="added after the round's GPU budget was spent: not yet confirmed on a B200 (set ROREG_TEST_EXPERIMENTAL=1)")
 @pytest.mark.parametrize("nn_mode,corr_mode", [(0, 0), (4, 3)])
 def test_scene_driver_equals_the_plugins(tmp_path, nn_mode, corr_mode):
     """roreg_b200.scene.register_scene (clouds uploaded once, batched engine, background writer): same samples and - with the

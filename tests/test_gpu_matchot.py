@@ -63,18 +63,64 @@ def test_sinkhorn_against_oracle(ctx):
     assert np.abs(_np(s0) - np.where(mut, np.exp(inner.max(1)), 0)).max() < 1e-4
 
 
-def test_match_ot_forward_against_oracle(ctx, tables):
+KNN_BAND = 2e-4      # relative to the row's largest |score|: float32 (3xTF32 GEMM) evaluation error of a score_mat entry
+OT_BAND = 2e-3       # absolute, log domain: error of a Sinkhorn-normalised score (100 iterations of float32 logsumexp)
+
+
+def _adjudicate_forward(ctx, tables, seed, n, capsys):
+    """Teacher-forced parity of MatchOT.forward (rot_coh_match.py:339-390).  The matcher is a chain of DISCRETE decisions
+    (8 top-k neighbour lists, then the mutual argmax on the OT matrix) joined by continuous float32 layers, so:
+      1. every neighbour list the CUDA path chose must be a valid top-k of the ORACLE's score matrix for that block (the
+         oracle runs with the CUDA lists forced, so both see the same inputs up to rounding): chosen scores in descending
+         order and no unchosen column better than the k-th, both within KNN_BAND; rows where the oracle's own stable argsort
+         would have picked differently are counted (near ties), not tolerated silently;
+      2. the final score matrix agrees to 1e-3 of its scale;
+      3. matches0: equal to the oracle's, except rows whose OT row / column top-2 gap is inside OT_BAND."""
     from roreg_b200 import matchot
-    pr = synth.make_pair(58, n=400)
+    pr = synth.make_pair(seed, n=n)
     sd = O.random_state_dict("RM", 104)
     mo = matchot.MatchOT(ctx, sd, npass=3)
+    mo.trace = {}
     m0, s0 = mo.forward(ctx.dev(pr["feats1"]), ctx.dev(pr["feats0"]), ctx.dev(pr["keys1"].astype(np.float32)), ctx.dev(pr["keys0"].astype(np.float32)))
     torch.cuda.synchronize()
-    r0, rs0, _, _, Z = O.match_ot_forward(pr["feats1"], pr["feats0"], pr["keys1"], pr["keys0"], sd, tables.perm)
-    agree = (_np(m0) == r0).mean()
-    assert agree > 0.98, agree                                    # float32 top-k / argmax near ties may flip a few assignments
-    both = (_np(m0) == r0) & (r0 >= 0)
+    forced = {k: _np(v).astype(np.int64) for k, v in mo.trace.items() if k != "final_score"}
+    assert len(forced) == 8
+    tr = {}
+    r0, rs0, _, _, Z = O.match_ot_forward(pr["feats1"], pr["feats0"], pr["keys1"], pr["keys0"], sd, tables.perm, forced=forced, trace=tr)
+    knn_ties = 0
+    for p, knn in forced.items():
+        Sc = tr[p]["score"]; own = tr[p]["knn"]
+        band = KNN_BAND * np.abs(Sc).max(axis=1)
+        chosen = np.take_along_axis(Sc, knn, 1)
+        assert np.all(chosen[:, :-1] - chosen[:, 1:] >= -band[:, None]), p                 # descending order
+        rest = Sc.copy(); np.put_along_axis(rest, knn, -np.inf, 1)
+        assert np.all(chosen[:, -1] >= rest.max(axis=1) - band), p                          # nothing better left out
+        assert all(len(set(r)) == len(r) for r in knn.tolist()), p
+        knn_ties += int((knn != own).any(axis=1).sum())
+    S = _np(mo.trace["final_score"]); Sr = tr["final_score"]
+    assert np.abs(S - Sr).max() < 1e-3 * max(1.0, np.abs(Sr).max())
+    got = _np(m0); inner = Z[:-1, :-1]
+    bad = np.flatnonzero(got != r0)
+    if bad.size:
+        row2 = np.sort(inner, axis=1)[:, -2:]; col2 = np.sort(inner, axis=0)[-2:, :]
+        row_tie = (row2[:, 1] - row2[:, 0]) < OT_BAND; col_tie = (col2[1] - col2[0]) < OT_BAND
+        i0 = inner.argmax(1)
+        for i in bad:
+            cols = {int(i0[i])} | ({int(got[i])} if got[i] >= 0 else set())
+            assert row_tie[i] or any(col_tie[j] for j in cols), (int(i), int(got[i]), int(r0[i]))
+    both = (got == r0) & (r0 >= 0)
     assert np.abs(_np(s0)[both] - rs0[both]).max() < 1e-3 * max(1.0, rs0.max())
+    with capsys.disabled():
+        print(f"\n[Match_ot parity n={n}] rows with a near-tied neighbour list (of {8 * n}): {knn_ties}; "
+              f"assignments inside the OT near-tie band: {bad.size} of {n}; matched {int((r0 >= 0).sum())}")
+
+
+def test_match_ot_forward_against_oracle(ctx, tables, capsys):
+    _adjudicate_forward(ctx, tables, 58, 400, capsys)
+
+
+def test_match_ot_forward_against_oracle_larger(ctx, tables, capsys):
+    _adjudicate_forward(ctx, tables, 59, 1100, capsys)
 
 
 def test_yoho_mat_plugin_reproduces_reference_files(tmp_path):
