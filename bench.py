@@ -27,6 +27,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv:
+    # --impl reference: torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every host thread it
+    # can (round 1's N >= 2 reference lines ran on ONE core).  Must happen before NumPy / torch read the variables at import.
+    for _v in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ.pop(_v, None)
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -217,6 +223,8 @@ def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU operations for the path (oracle/torch_mirror.py) on the host cores, rank 0 only."""
     if rank != 0:
         return
+    import torch
+    torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))            # all host threads this process may run on
     prs, _, _, _ = make_inputs(max(1, args.cpu_sample_pairs), args.n, 0)
     per_step = max(1.0, min(args.cpu_seconds, 200.0 / max(1, args.steps + args.warmup)))   # whole arm within a few minutes
     timer, kind_note = time_reference_ops, None
@@ -232,7 +240,10 @@ def run_reference(args, rank, world):
             pairs += last["pairs"]; secs += last["seconds"]
     val = pairs / secs
     cb = {"value": val, "unit": "pairs/s", "cores": last["cores"], "kind": "port",
-          "sample": f"{args.steps} steps x ~{per_step:.1f} s bounded samples ({int(pairs)} pair registrations in {secs:.1f} s); " + last["sample"]}
+          "sample": f"{args.steps} steps x ~{per_step:.1f} s bounded samples ({int(pairs)} pair registrations in {secs:.1f} s, cycling over "
+                    f"{len(prs)} distinct pairs of the workload; per-pair rate, so the arm's pairs_per_step label equals the GPU arm's); the "
+                    "reference's per-pair file I/O (3 re-reads of both 38 MB descriptor files, test/matcher.py:66-67, test/estimator.py:106-107) "
+                    "is EXCLUDED - inputs are in memory; " + last["sample"]}
     if kind_note:
         cb["reference_ops_unavailable"] = kind_note
     else:
@@ -244,7 +255,7 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": "pair registrations/sec (5000 kpt, 60-rot)", "value": val, "unit": "pairs/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-            "config": workload_config(args, len(prs)), "cpu_baseline": cb,
+            "config": workload_config(args, args.pairs_per_step), "cpu_baseline": cb,
             "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 

@@ -24,6 +24,7 @@
 #include <cuda_fp16.h>
 #include "kernels_corr_tc.cuh"
 #include "kernels_nn_tc4.cuh"
+#include "icosa_cosets.cuh"
 
 namespace roreg {
 
@@ -32,7 +33,8 @@ constexpr int C3_LOADERS = 11;                            // loader warps: a poo
 constexpr int C3_THREADS = (C3_LOADERS + 1 + 8) * 32;     // 640: 11 loader warps, the MMA warp, two epilogue sets of 4 warps
 constexpr int C3_OP_BYTES = 32 * 128;                     // one match's operand tile: 32 f-rows x 64 h fp16 = 4 KB
 constexpr int C3_BUF_BYTES = 8 * C3_OP_BYTES;             // Xhi m0|m1, Xlo m0|m1, Yhi m0|m1, Ylo m0|m1 = 32 KB
-constexpr int C3_GS_BYTES = 2 * 60 * 64 * 4;              // transposed Gram of both matches [2][60 g][64 h], one per epilogue set
+constexpr int C3_GS_STRIDE = 68;                          // floats per Gram row: 64 slots + 4 -> 16-byte stores of 8 consecutive rows hit 8 distinct bank quads (17 odd)
+constexpr int C3_GS_BYTES = 2 * 64 * C3_GS_STRIDE * 4;    // Gram of both matches [2][64 h][68], columns at their coset slots (icosa_cosets.cuh), one per epilogue set
 constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + 2 * C3_GS_BYTES + 3600 + 32 + 256 + 1024;   // 165 KB
 // kind::f16, A and B MN-major, D = f32, M = N = 128
 constexpr uint32_t C3_IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -62,12 +64,12 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
 }
 
-template <bool TRACE>
+template <bool TRACE, int VARIANT>
 __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                                    // one 32 KB operand-tile set per loader group
-  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [2 epilogue sets][2 matches][60 g][64 h]
+  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [2 epilogue sets][2 matches][64 h][68]
   uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + 2 * C3_GS_BYTES;                        // 3600 B
   uint32_t* red_k = reinterpret_cast<uint32_t*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_k + 4);   // [2 sets][2 matches] each
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_i + 4);                                 // 8-byte aligned: every size above is a multiple of 8
@@ -79,7 +81,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
-  for (int e = threadIdx.x; e < 3600; e += C3_THREADS) tabs[e] = a.tab[e];
+  // read table of the diagonal sums, by ROW of the Gram: tabs[a][h] = slot of the column g with tab[a][g] = h
+  {
+    const uint8_t* slot = VARIANT == 1 ? C3_SLOT_V1 : C3_SLOT_V2;
+    for (int e = threadIdx.x; e < 3600; e += C3_THREADS) { const int aa = e / 60, g = e - aa * 60; tabs[aa * 60 + a.tab[e]] = slot[g]; }
+  }
   // operand tiles start as zeros: the loaders never write the padding columns h = 60..63
   for (int e = threadIdx.x; e < C3_GROUPS * C3_BUF_BYTES / 16; e += C3_THREADS) reinterpret_cast<uint4*>(bufs)[e] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
@@ -212,16 +218,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     const int eset = (warp - 12) >> 2;
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
-    const int h = (q & 1) * 32 + lane;                 // Gram row (h) == the 'a' this thread later sums
-    float* G = Gs + (eset * 2 + m) * 60 * 64;
+    const int h = (q & 1) * 32 + lane;                 // Gram row (h) this thread owns in TMEM and stores
+    float* G = Gs + (eset * 2 + m) * 64 * C3_GS_STRIDE;
+    float* grow = G + h * C3_GS_STRIDE;
     const int nbar = 2 + eset * 2 + m;                 // named barrier of this (set, match) warp pair
     uint32_t* rk = red_k + eset * 2; int* ri = red_i + eset * 2;
-    // this thread always sums the generalised diagonal a = h: keep its 60 table bytes in registers
+    // the generalised diagonal this thread sums: the two warps of a match take the two lane lists of icosa_cosets.cuh (30 lanes
+    // each), whose columns are a transversal of the cosets in every row -> each LDS below touches 30 distinct banks
+    const int my_a = (VARIANT == 1 ? C3_LANE_A_V1 : C3_LANE_A_V2)[q & 1][lane];
+    const bool has_a = my_a < RR_G;
     uint32_t trow[15];
+    __syncwarp();
 #pragma unroll
     for (int w4 = 0; w4 < 15; ++w4) {
-      const uint8_t* t = tabs + (h < RR_G ? h : 0) * 60 + 4 * w4;
-      trow[w4] = 4u * ((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24));   // bytes = 4 * P < 240: byte offsets
+      const uint8_t* t = tabs + (has_a ? my_a : 0) * 60 + 4 * w4;
+      trow[w4] = 4u * ((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24));   // bytes = 4 * slot < 248: byte offsets
     }
     const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
     uint32_t it = 0;
@@ -247,20 +258,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
           if (lane == 0) mbar_arrive(BAR(8 + buf));    // accumulators free as soon as they sit in registers
           if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 8);
         }
-        // transposed store: Gs[m][g][h]; a warp writes 32 consecutive h -> conflict-free
+        // row store: this thread's row h, column g at slot(g), as 16-byte stores (8 consecutive rows = 8 distinct bank quads)
+        float v[32];
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const int g = half * 32 + u;
-          if (g < 60) G[g * 64 + h] = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
-        }
+        for (int u = 0; u < 32; ++u) v[u] = fmaf(__uint_as_float(r2[u]), T4_LO_UNSCALE, __uint_as_float(r1[u]));
+        if (VARIANT == 1) { if (half == 0) C3_STORE_V1_H0(grow, v); else C3_STORE_V1_H1(grow, v); }
+        else              { if (half == 0) C3_STORE_V2_H0(grow, v); else C3_STORE_V2_H1(grow, v); }
       }
       asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");
       if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 10);
       float c = -INFINITY;
-      if (h < RR_G) {
-        // all 60 loads first (independent addresses straight from the table bytes), then a fixed-shape tree: the warp is alone on
-        // its latency chain, so the shared-memory latency must be paid once, not 15 times (the sum order differs from
-        // g = 0..59 only in rounding)
+      if (has_a) {
+        // 20 loads in flight at a time (independent addresses straight from the table bytes), then a fixed-shape tree: the warp is
+        // alone on its latency chain, so the shared-memory latency must be paid three times, not 60 (the sum runs over the rows
+        // h = 0..59 of the Gram instead of g = 0..59: same terms, different rounding order)
         float c8[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int part = 0; part < 3; ++part) {           // 20 loads in flight at a time (register budget: 96 per thread)
@@ -269,10 +280,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
           for (int w = 0; w < 5; ++w) {
             const int w4 = part * 5 + w;
             const uint32_t tw = trow[w4];
-            gv[4 * w + 0] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 0) * 256 + __byte_perm(tw, 0, 0x4440));
-            gv[4 * w + 1] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 1) * 256 + __byte_perm(tw, 0, 0x4441));
-            gv[4 * w + 2] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 2) * 256 + __byte_perm(tw, 0, 0x4442));
-            gv[4 * w + 3] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 3) * 256 + __byte_perm(tw, 0, 0x4443));
+            gv[4 * w + 0] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 0) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4440));
+            gv[4 * w + 1] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 1) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4441));
+            gv[4 * w + 2] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 2) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4442));
+            gv[4 * w + 3] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 3) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4443));
           }
 #pragma unroll
           for (int k = 0; k < 20; ++k) c8[(part * 20 + k) & 7] += gv[k];
@@ -282,16 +293,16 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
       if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 11);
       const bool valid = m < avail;
       const long long w = (long long)p * a.K + k0 + m;
-      if (valid && h < RR_G && a.cor_out) a.cor_out[w * RR_G + h] = c;
-      // first maximal index (torch.argmax): warp-wide integer max of the order-preserving key, then the smallest h attaining it
-      const uint32_t key = (h < RR_G) ? t4_ord(c + 0.f) : 0u;              // + 0.f: -0 and +0 compare equal, as in float arithmetic
+      if (valid && has_a && a.cor_out) a.cor_out[w * RR_G + my_a] = c;
+      // first maximal index (torch.argmax): warp-wide integer max of the order-preserving key, then the smallest a attaining it
+      const uint32_t key = has_a ? t4_ord(c + 0.f) : 0u;                   // + 0.f: -0 and +0 compare equal, as in float arithmetic
       const uint32_t kmax = __reduce_max_sync(0xffffffffu, key);
-      const int ix = (int)__reduce_min_sync(0xffffffffu, key == kmax ? (uint32_t)h : 0x7fffffffu);
-      if ((q & 1) == 1 && lane == 0) { rk[m] = kmax; ri[m] = ix; }          // upper half-row warp (h 32..63) publishes
+      const int ix = (int)__reduce_min_sync(0xffffffffu, (has_a && key == kmax) ? (uint32_t)my_a : 0x7fffffffu);
+      if ((q & 1) == 1 && lane == 0) { rk[m] = kmax; ri[m] = ix; }          // the second warp of the match publishes
       asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");
       if ((q & 1) == 0 && lane == 0 && valid && a.argmax_out) {
-        int best = ix;                                                      // lower warp holds the smaller indices
-        if (rk[m] > kmax) best = ri[m];
+        int best = ix;                                                      // the lane lists interleave: equal keys -> the smaller a
+        if (rk[m] > kmax || (rk[m] == kmax && ri[m] < ix)) best = ri[m];
         a.argmax_out[w] = best;
       }
       asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");             // Gs / red reusable
@@ -305,24 +316,26 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
 
 // X, Y: descriptor arrays [rows][32][60] float32, 16-byte aligned (a row is 7680 B)
 static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const float* Y, CorrTcArgs a, cudaStream_t st) {
+  const bool v2 = (a.tab == c->d_permT8);               // variant 2 (R-indicator convention): its own coset layout
   RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   a.X = X; a.Y = Y; a.trace = nullptr;
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
   }
   const long long items = (long long)a.B * ((a.K + 1) / 2);
   RR_ARG(c, items < (1LL << 31));
   const int grid = (int)(items < c->sm_count ? items : c->sm_count);
   const char* trace_fn = getenv("ROREG_DEBUG_CORR_TRACE");
   static bool traced = false;
-  if (trace_fn && !traced && items >= 50000) {           // one-off timeline dump of CTA 0 (debug only; synchronises)
+  if (trace_fn && !traced && !v2 && items >= 50000) {           // one-off timeline dump of CTA 0 (debug only; synchronises)
     traced = true;
     const size_t nb = (size_t)grid * 256 * 12 * sizeof(long long);
     RR_CUDA(c, cudaMalloc(&a.trace, nb));
     RR_CUDA(c, cudaMemsetAsync(a.trace, 0, nb, st));
-    group_corr_tc3_kernel<true><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
+    group_corr_tc3_kernel<true, 1><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
     RR_LAUNCH_CHECK(c);
     RR_CUDA(c, cudaStreamSynchronize(st));
     long long* h = (long long*)malloc(256 * 12 * sizeof(long long));
@@ -340,7 +353,8 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
     free(h); cudaFree(a.trace);
     return ROREG_OK;
   }
-  group_corr_tc3_kernel<false><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
+  if (v2) group_corr_tc3_kernel<false, 2><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
+  else group_corr_tc3_kernel<false, 1><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

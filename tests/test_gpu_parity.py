@@ -527,7 +527,7 @@ def test_fast_path_full_size_against_oracle(tables, seed, capsys):
     k = int(o["n_matches"][0]); got_m = _np(o["matches"][0, :k]).astype(np.int64); got_dr = _np(o["dr_index"][0, :k]).astype(np.int64)
     # ---- NN both ways on the pooled invariants (the same kernels register_batch ran)
     f0 = oracle_c.inv_pool(pr["feats0"]); f1 = oracle_c.inv_pool(pr["feats1"])
-    assert np.abs(_np(c.inv_pool(desc[0])) - f0).max() < 2e-7
+    assert np.abs(_np(c.inv_pool(desc[0])) - f0).max() < 4e-7           # float32 sums of 60 terms in two orders, 5000 x 32 values
     _, r01 = oracle_c.nn(f1, f0); _, r10 = oracle_c.nn(f0, f1)
     _, _, nn01, nn10 = c.mutual_match(c.dev(f0), c.dev(f1), 4)
     torch.cuda.synchronize()
