@@ -55,6 +55,18 @@ def kabsch_3pt(p0, p1):
     return np.hstack([R, t.T])
 
 
+def kabsch_3pt_batch(p0, p1):
+    """kabsch_3pt for a stack of triplets p0, p1 [H,3,3] -> [H,3,4].  NumPy's stacked mean / matmul / svd run the same
+    per-matrix routines (LAPACK gesdd included) as the reference's per-hypothesis calls, so every entry is bit-identical to
+    kabsch_3pt on that triplet - reflections included (tests/test_plugins_host.py checks the equality)."""
+    mu0 = np.mean(p0, 1, keepdims=True)
+    mu1 = np.mean(p1, 1, keepdims=True)
+    U, _, Vt = np.linalg.svd(np.matmul((p1 - mu1).transpose(0, 2, 1), p0 - mu0))
+    R = np.matmul(Vt.transpose(0, 2, 1), U.transpose(0, 2, 1))
+    t = mu0 - np.matmul(mu1, R.transpose(0, 2, 1))
+    return np.concatenate([R, t.transpose(0, 2, 1)], axis=2)
+
+
 def draw_guided_triplets(members, prob, max_iter, max_draws=50000):
     """The RNG-consuming loop of yohoc_ransac.ransac_once (test/estimator.py:221-228) on the GLOBAL NumPy RNG: per iteration one
     categorical draw of a coarse rotation (rejected, without counting, when its bucket has < 2 matches) and one draw of three

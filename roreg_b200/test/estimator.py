@@ -1,8 +1,10 @@
 """Mirror of test/estimator.py: R_pre_log (:14-26), refiner (:28-72), extractor_dr_index (:75-111),
 yohoc_ransac (:113-264), yohoc (:266-272), extractor_localtrans (:275-367), yohoo_ransac (:369-443),
 yohoo (:445-454).  Same class / method names and signatures, same files written, same consumption order of the global
-NumPy RNG; the arithmetic runs in libroreg_b200.so, the host-side rules live in _hostlogic.py and the file
-layout in _common.CacheLayout."""
+NumPy RNG - with one caveat: the reference's yohoc forks multiprocessing.Pool(len(pair_ids)) (:258), so every
+pair's draws start from a COPY of the parent's RNG state and the parent's state is not advanced; yohoc_ransac.ransac reproduces
+exactly that (state restored before every pair and after the loop).  The arithmetic runs in libroreg_b200.so, the host-side
+rules live in _hostlogic.py and the file layout in _common.CacheLayout."""
 import numpy as np
 import torch
 from tqdm import tqdm
@@ -90,9 +92,9 @@ class yohoc_ransac:
 
     cfg.yohoc_mode (extension, default 'parity'):
       'parity' - the triplet draws consume the global NumPy RNG exactly as :224-228 and the 3-point
-                 Kabsch runs through np.linalg.svd on the host, because the rank-2 SVD's sign (rotation
-                 vs reflection) is LAPACK rounding noise; scoring, selection and refinement
-                 run on the device.
+                 Kabsch runs through ONE stacked np.linalg.svd on the host (the same LAPACK routine per
+                 matrix as the reference's loop), because the rank-2 SVD's sign (rotation vs reflection)
+                 is LAPACK rounding noise; scoring, selection and refinement run on the device.
       'device' - draws (counter-based RNG) and the proper-rotation Kabsch also run on the device."""
 
     def __init__(self, cfg):
@@ -129,7 +131,7 @@ class yohoc_ransac:
             hyps = ctx.kabsch3(ctx.dev(k0_kept, torch.float64), ctx.dev(k1_kept, torch.float64), ctx.dev(trip))
         else:
             trip = host.draw_guided_triplets(members, prob, max_iter)
-            hyps = ctx.dev(np.stack([self.Threepps2Tran(k0_kept[t], k1_kept[t]) for t in trip], 0), torch.float64)
+            hyps = ctx.dev(host.kabsch_3pt_batch(k0_kept[trip], k1_kept[trip]), torch.float64)   # == Threepps2Tran per triplet, bit for bit
         best, _, _ = ctx.ransac_oneshot(k0, k1, sc, hyps, None, self.inliner_dist)
         b = int(best.item())
         if b < 0:
@@ -150,10 +152,14 @@ class yohoc_ransac:
         lay = CacheLayout(self.cfg, dataset, keynum)
         make_non_exists_dir(lay.result_dir('yohoc', max_iter))
         print(f'Ransac with YOHO-C on {dataset.name}:')
-        # the reference forks Pool(len(pair_ids)) (:258); pairs are independent, so the single device
-        # context processes them in order instead
+        # the reference forks Pool(len(pair_ids)) (:258): one worker per pair, each starting from a copy of the parent's global
+        # NumPy RNG state, the parent's own state untouched.  Pairs are independent, so the single device context processes them
+        # in order - from the same starting state each, which is restored afterwards.
+        state = np.random.get_state()
         for pair in tqdm(dataset.pair_ids):
+            np.random.set_state(state)
             self.ransac_once(dataset, keynum, max_iter, pair)
+        np.random.set_state(state)
         R_pre_log(dataset, lay.result_dir('yohoc', max_iter))
         print('Done')
 
