@@ -35,7 +35,7 @@ constexpr int C3_OP_BYTES = 32 * 128;                     // one match's operand
 constexpr int C3_BUF_BYTES = 8 * C3_OP_BYTES;             // Xhi m0|m1, Xlo m0|m1, Yhi m0|m1, Ylo m0|m1 = 32 KB
 constexpr int C3_GS_STRIDE = 68;                          // floats per Gram row: 64 slots + 4 -> 16-byte stores of 8 consecutive rows hit 8 distinct bank quads (17 odd)
 constexpr int C3_GS_BYTES = 2 * 64 * C3_GS_STRIDE * 4;    // Gram of both matches [2][64 h][68], columns at their coset slots (icosa_cosets.cuh), one per epilogue set
-constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + 2 * C3_GS_BYTES + 3600 + 32 + 256 + 1024;   // 165 KB
+constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + 2 * C3_GS_BYTES + 3840 + 32 + 256 + 1024;   // 169 KB
 // kind::f16, A and B MN-major, D = f32, M = N = 128
 constexpr uint32_t C3_IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // MN-major SWIZZLE_128B descriptor: LBO = 4096 B, SBO = 1024 B, version 1, layout type 2
@@ -70,8 +70,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                                    // one 32 KB operand-tile set per loader group
   float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [2 epilogue sets][2 matches][64 h][68]
-  uint8_t* tabs = reinterpret_cast<uint8_t*>(Gs) + 2 * C3_GS_BYTES;                        // 3600 B
-  uint32_t* red_k = reinterpret_cast<uint32_t*>(tabs + 3600); int* red_i = reinterpret_cast<int*>(red_k + 4);   // [2 sets][2 matches] each
+  uint32_t* tabw = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(Gs) + 2 * C3_GS_BYTES);   // [2 warp halves][15][32 lanes] packed byte offsets, 3840 B
+  uint32_t* red_k = tabw + 2 * 15 * 32; int* red_i = reinterpret_cast<int*>(red_k + 4);   // [2 sets][2 matches] each
   uint64_t* bars = reinterpret_cast<uint64_t*>(red_i + 4);                                 // 8-byte aligned: every size above is a multiple of 8
   // barriers: 0..2 conv_done[set], 3..5 tiles_free[set], 6..7 mma_done[acc], 8..9 acc_free[acc].
   // Every waiter must only ever have to distinguish ADJACENT phases of a barrier (run 34: with three loader groups sharing
@@ -81,10 +81,20 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
 
-  // read table of the diagonal sums, by ROW of the Gram: tabs[a][h] = slot of the column g with tab[a][g] = h
+  // read table of the diagonal sums, by ROW of the Gram: lane l of warp half w sums a = LANE_A[w][l] and needs, in row h, the
+  // column g with tab[a][g] = h, stored at slot(g).  Kept in shared memory as packed words tabw[w][h / 4][l] (byte h % 4 =
+  // 4 * slot: a byte offset into the row) - consecutive lanes read consecutive words, and nothing table-sized lives in
+  // registers across the item loop (run c2: ptxas had spilled 40 pre-extracted offsets, 40 LDL per item on the critical chain).
   {
     const uint8_t* slot = VARIANT == 1 ? C3_SLOT_V1 : C3_SLOT_V2;
-    for (int e = threadIdx.x; e < 3600; e += C3_THREADS) { const int aa = e / 60, g = e - aa * 60; tabs[aa * 60 + a.tab[e]] = slot[g]; }
+    uint8_t* tmp = reinterpret_cast<uint8_t*>(Gs);                       // [60 a][60 h] slot bytes, aliased on the (still unused) Gram buffers
+    for (int e = threadIdx.x; e < 3600; e += C3_THREADS) { const int aa = e / 60, g = e - aa * 60; tmp[aa * 60 + a.tab[e]] = slot[g]; }
+    __syncthreads();
+    for (int e = threadIdx.x; e < 2 * 32 * 60; e += C3_THREADS) {
+      const int w = e / (32 * 60), l = (e / 60) & 31, hh = e % 60;
+      const int aa = (VARIANT == 1 ? C3_LANE_A_V1 : C3_LANE_A_V2)[w][l];
+      reinterpret_cast<uint8_t*>(tabw)[((w * 15 + (hh >> 2)) * 32 + l) * 4 + (hh & 3)] = aa < RR_G ? (uint8_t)(4 * tmp[aa * 60 + hh]) : (uint8_t)0;
+    }
   }
   // operand tiles start as zeros: the loaders never write the padding columns h = 60..63
   for (int e = threadIdx.x; e < C3_GROUPS * C3_BUF_BYTES / 16; e += C3_THREADS) reinterpret_cast<uint4*>(bufs)[e] = make_uint4(0, 0, 0, 0);
@@ -110,11 +120,14 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   // every role walks the same item sequence (item = blockIdx.x + i * gridDim.x -> pair p, first match k0 = 2 j) and skips the
   // same items (device-side match counts); the walk carries (p, j) along so that the loops contain no division
   const int step_p = (int)gridDim.x / items_per_pair, step_j = (int)gridDim.x % items_per_pair;
-  struct Walk { int item, p, j; };
-  auto walk_begin = [&]() -> Walk { return Walk{(int)blockIdx.x, (int)blockIdx.x / items_per_pair, (int)blockIdx.x % items_per_pair}; };
+  struct Walk { int item, p, j, cp, cn; };             // cp / cn: the pair whose match count is cached, and that count
+  auto walk_begin = [&]() -> Walk { return Walk{(int)blockIdx.x, (int)blockIdx.x / items_per_pair, (int)blockIdx.x % items_per_pair, -1, 0}; };
   auto walk_next = [&](Walk& w) { w.item += gridDim.x; w.p += step_p; w.j += step_j; if (w.j >= items_per_pair) { w.j -= items_per_pair; ++w.p; } };
-  auto walk_avail = [&](const Walk& w) -> int {        // <= 0: nothing, 1: one match, >= 2: two matches
-    return (a.n_matches ? a.n_matches[w.p] : a.K) - 2 * w.j;
+  auto walk_avail = [&](Walk& w) -> int {              // <= 0: nothing, 1: one match, >= 2: two matches
+    // a CTA stays ~11 consecutive items inside one pair: the count is re-read only when the pair changes (run c2: the
+    // per-item global load sat on every role's critical path, ~1000 clk per item in the epilogue warps)
+    if (w.p != w.cp) { w.cp = w.p; w.cn = a.n_matches ? a.n_matches[w.p] : a.K; }
+    return w.cn - 2 * w.j;
   };
 
   if (warp < C3_LOADERS) {
@@ -227,13 +240,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     // each), whose columns are a transversal of the cosets in every row -> each LDS below touches 30 distinct banks
     const int my_a = (VARIANT == 1 ? C3_LANE_A_V1 : C3_LANE_A_V2)[q & 1][lane];
     const bool has_a = my_a < RR_G;
-    uint32_t trow[15];
-    __syncwarp();
-#pragma unroll
-    for (int w4 = 0; w4 < 15; ++w4) {
-      const uint8_t* t = tabs + (has_a ? my_a : 0) * 60 + 4 * w4;
-      trow[w4] = 4u * ((uint32_t)t[0] | ((uint32_t)t[1] << 8) | ((uint32_t)t[2] << 16) | ((uint32_t)t[3] << 24));   // bytes = 4 * slot < 248: byte offsets
-    }
+    const uint32_t* tw_lane = tabw + (q & 1) * 15 * 32 + lane;
     const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
     uint32_t it = 0;
     for (Walk wk = walk_begin(); wk.item < n_items; walk_next(wk)) {
@@ -279,7 +286,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
 #pragma unroll
           for (int w = 0; w < 5; ++w) {
             const int w4 = part * 5 + w;
-            const uint32_t tw = trow[w4];
+            const uint32_t tw = tw_lane[w4 * 32];
             gv[4 * w + 0] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 0) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4440));
             gv[4 * w + 1] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 1) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4441));
             gv[4 * w + 2] = *reinterpret_cast<const float*>(Gb + (4 * w4 + 2) * (C3_GS_STRIDE * 4) + __byte_perm(tw, 0, 0x4442));
@@ -305,7 +312,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
         if (rk[m] > kmax || (rk[m] == kmax && ri[m] < ix)) best = ri[m];
         a.argmax_out[w] = best;
       }
-      asm volatile("bar.sync %0, 64;" ::"r"(nbar) : "memory");             // Gs / red reusable
+      // no third barrier: the partner warp finished reading Gs before the barrier above, and it reaches the next item's first
+      // barrier (after which `red` is rewritten) only after this warp has read `red`
       if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 9);
       ++it;
     }
