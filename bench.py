@@ -10,9 +10,13 @@ the device.
 
   value  - pairs/s with descriptors + keypoints already resident in HBM (B x 77 MB > L2, so every step
            streams its inputs from HBM: no L2 flush needed, stated in config.l2)
-  e2e    - same metric through the same call with HOST (pinned) buffers: per step the descriptors and
-           keypoints are copied host->device and the poses device->host inside the timed region
-           (double-buffered on two streams so copies overlap compute)
+  e2e    - same metric through the reference-facing scene driver (roreg_b200.scene.register_scene = mutual.run +
+           yohoc.run of the plugins for a whole dataset): a synthetic 60-cloud / 225-pair scene with the cloud
+           reuse of the reference's test sets; the timed region reads the 60 cached descriptor files, copies
+           them host->device, registers the pairs and WRITES the reference's per-pair files (match / scores /
+           DR_index .npy, {id0}-{id1}.npz) and pre.log
+  e2e_pair_upload / e2e_cloud_reuse4 (extras) - the batched C-ABI call fed from pinned host buffers: both clouds
+           re-uploaded for every pair / every uploaded cloud used by 4 registrations
   roofline / cpu_baseline - see DESIGN.md "Measurement"
 
 Multi-GPU (torchrun, one rank per GPU): pairs shard across ranks with no data-path collective
@@ -59,6 +63,8 @@ def parse():
                     help="1 (kernel A/B experiments only): one untimed-quality step for the e2e / scene phases; their numbers are then meaningless")
     ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "3")),
                     help="0 = FP32 CUDA-core Gram, 1-2 = tcgen05 3xTF32 Gram, 3 = fp16 two-accumulator Gram, operands from registers (default)")
+    ap.add_argument("--scene-clouds", type=int, default=60, help="e2e scene: clouds (files read + uploaded once each)")
+    ap.add_argument("--scene-pairs", type=int, default=225, help="e2e scene: pairs registered (3DMatch: 433 clouds / 1623 pairs)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="bounded CPU-baseline sample (seconds of host work)")
     return ap.parse_args()
@@ -268,6 +274,55 @@ def workload_config(args, B):
             "l2": "inputs larger than L2 (B x 77 MB streamed per step), no flush needed"}
 
 
+def scene_e2e(args, ctx, rank, world, barrier):
+    """The headline e2e: one whole synthetic scene per rank through scene.register_scene - descriptor files read from the cache
+    directory, host->device copies, batched registration, the reference's per-pair files and pre.log written - timed from the call
+    to its return (the background writer has finished by then).  Rep 0 warms up (pinned ring, workspace, page cache), rep 1 is timed."""
+    import shutil
+    import tempfile
+    import types
+    import torch
+    from roreg_b200 import scene, synth
+    from roreg_b200.test._common import CacheLayout
+    n_clouds, n_pairs = (8, 12) if args.value_only else (args.scene_clouds, args.scene_pairs)
+    need = n_clouds * args.n * 7680 * 1.1
+    root = None
+    for cand in ("/dev/shm", tempfile.gettempdir()):
+        try:
+            if shutil.disk_usage(cand).free > need + (1 << 30):
+                root = tempfile.mkdtemp(prefix=f"roreg_scene_r{rank}_", dir=cand); break
+        except Exception:
+            pass
+    if root is None:
+        return {"unavailable": "no scratch directory with room for the scene's descriptor files"}
+    try:
+        sc = synth.SynthScene(7000 + rank, n_clouds=n_clouds, n_pairs=n_pairs, n=args.n, name="synth/bench_scene")
+        sc.write_cache(root)
+        cfg = types.SimpleNamespace(output_cache_fn=root, model_fn="", SO3_related_files=None, backbone="FCGF", bs_GF=1250, bs_ET=1000,
+                                    RD=False, RM=False, match_n=0.5, ransac_ird=0.1, corr_mode=args.corr_mode)
+        gt = np.stack([sc.get_transform64(a, b) for a, b in sc.pair_ids])
+        dt = err = None
+        for rep in range(2):
+            np.random.seed(11)
+            barrier()
+            t0 = time.perf_counter()
+            res = scene.register_scene(cfg, sc, keynum=args.n, max_iter=args.max_iter, batch_pairs=args.pairs_per_step, nn_mode=args.nn_mode,
+                                       seed=rep, ctx=ctx, shard=False)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            err = float(np.abs(res["poses"][:, :3] - gt).max())
+        lay = CacheLayout(cfg, sc, args.n)
+        files = sum(len(fs) for _, _, fs in os.walk(lay.match_dir))
+        out_bytes = sum(os.path.getsize(os.path.join(d, f)) for d, _, fs in os.walk(lay.match_dir) for f in fs)
+        kmean = float(res["n_matches"].mean())
+        return {"seconds": dt, "pairs": len(sc.pair_ids), "clouds": n_clouds, "max_abs_err_vs_gt": err,
+                "h2d_bytes": n_clouds * args.n * (7680 + 24),
+                "d2h_bytes": len(sc.pair_ids) * (args.n * 8 + args.n * 4 + 4 + 128 + 4 + 8),
+                "files_read": n_clouds, "files_written": files, "bytes_written": out_bytes, "matches_per_pair": kmean, "dir": os.path.dirname(root)}
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 # ------------------------------------------------------------------------------------------------
 def main():
     args = parse()
@@ -448,6 +503,8 @@ def main():
         dist.all_reduce(ts, op=dist.ReduceOp.MAX)
     e2e_scene_val = world * REUSE * B * scene_steps / float(ts.item())
     scene_err = float(np.abs(o2["poses"][:B].cpu().numpy()[:, :3] - gt).max())
+    sc_res = scene_e2e(args, ctx, rank, world, barrier)
+    ctx.set_corr_mode(args.corr_mode)
     clocks = sampler.stop()          # sampled over the resident-input region and the host-buffer (e2e) regions
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -455,6 +512,13 @@ def main():
     e2e_val = world * B * e2e_steps / float(te.item())
     h2d_bytes = desc_pin.numel() * 4 + keys_pin.numel() * 8
     d2h_bytes = poses_pin.numel() * 8
+    if "seconds" in sc_res:
+        tsc = torch.tensor([sc_res["seconds"]], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tsc, op=dist.ReduceOp.MAX)
+        scene_val = world * sc_res["pairs"] / float(tsc.item())
+    else:
+        scene_val = None
 
     # ---------------- roofline of the dominant stage ----------------
     peaks = {}
@@ -518,17 +582,29 @@ def main():
                 "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_max / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32 (matcher, correlation) + f64 (RANSAC, Kabsch)",
                 "data": "synthetic", "config": workload_config(args, B), "clocks": clocks,
-                "e2e": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
-                        "steps": e2e_steps},
-                "e2e_scene": {"value": e2e_scene_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes * REUSE,
-                              "pairs_per_step": REUSE * B, "steps": scene_steps, "max_abs_err_vs_gt": scene_err,
-                              "note": f"extra: same host buffers, but every uploaded cloud is used by {REUSE} registrations per step (scene "
-                                      "access pattern of the reference's test sets; the plugin's CloudCache); the headline e2e above uploads "
-                                      "both clouds for every single pair"},
+                "e2e": ({"value": scene_val, "unit": "pairs/s", "h2d_bytes_per_step": sc_res["h2d_bytes"], "d2h_bytes_per_step": sc_res["d2h_bytes"],
+                         "steps": 1, "seconds": sc_res["seconds"], "pairs_per_step": sc_res["pairs"], "clouds": sc_res["clouds"],
+                         "files_read": sc_res["files_read"], "files_written": sc_res["files_written"], "bytes_written": sc_res["bytes_written"],
+                         "matches_per_pair": sc_res["matches_per_pair"], "max_abs_err_vs_gt": sc_res["max_abs_err_vs_gt"], "scratch": sc_res["dir"],
+                         "h2d_gb_per_s_per_rank": sc_res["h2d_bytes"] / sc_res["seconds"] / 1e9,
+                         "note": "through roreg_b200.scene.register_scene (the plugins' mutual.run + yohoc.run for a whole dataset), one scene per "
+                                 "rank: timed region = read the cached descriptor files (one per cloud) -> pinned ring -> HBM, register every pair "
+                                 "in batches, device->host results, write match / scores / DR_index .npy + .npz per pair and pre.log; a step = "
+                                 "one scene; warm-up = one untimed pass over the same scene"}
+                        if scene_val is not None else
+                        {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes, "steps": e2e_steps,
+                         "note": "scene e2e unavailable (" + sc_res.get("unavailable", "?") + "): per-pair upload figure instead"}),
+                "e2e_pair_upload": {"value": e2e_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes,
+                                    "steps": e2e_steps, "h2d_gb_per_s_per_rank": h2d_bytes * e2e_steps / e2e_s / 1e9,
+                                    "note": "extra (round 1's headline): roreg_register_batch fed from pinned host buffers, BOTH clouds of every "
+                                            "pair re-uploaded each step (no real run does that: 433 clouds / 1623 pairs on 3DMatch); PCIe-bound"},
+                "e2e_cloud_reuse4": {"value": e2e_scene_val, "unit": "pairs/s", "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h_bytes * REUSE,
+                                     "pairs_per_step": REUSE * B, "steps": scene_steps, "max_abs_err_vs_gt": scene_err,
+                                     "note": f"extra: same pinned buffers, every uploaded cloud used by {REUSE} registrations per step, no files"},
                 "gpu_launches": int(launches), "roofline": roofline, "pose_check": {"max_abs_err_vs_gt": float(err), "ok": ok},
                 "nn_mode": args.nn_mode, "corr_mode": args.corr_mode, "score_mode": args.score_mode, "pipelined": args.pipelined}
         if args.value_only:
-            line["value_only"] = True; line["e2e"]["note"] = "--value-only run: e2e / e2e_scene were not measured properly"
+            line["value_only"] = True; line["e2e"]["note"] = "--value-only run: the e2e figures were not measured properly (tiny scene, one step)"
         if cb:
             line["cpu_baseline"] = cb
         print(json.dumps(line), flush=True)

@@ -29,13 +29,14 @@
 namespace roreg {
 
 constexpr int C3_GROUPS = 3;                              // operand-tile sets (items in flight between the loaders and the tensor pipe)
-constexpr int C3_LOADERS = 11;                            // loader warps: a pool that takes the (item, row) tasks round-robin
-constexpr int C3_THREADS = (C3_LOADERS + 1 + 8) * 32;     // 640: 11 loader warps, the MMA warp, two epilogue sets of 4 warps
+// Warp roles are template parameters: LOADERS loader warps (a pool that takes the (item, row) tasks round-robin), one MMA warp,
+// ESETS epilogue sets of 4 warps.  Default <11, 2> = 640 threads; <11, 3> = 768 threads adds a third epilogue set at 80 registers per thread (registers are allocated per 4 warps: 21-24 warps cost the same).
+__host__ __device__ constexpr int c3_threads(int loaders, int esets) { return (loaders + 1 + 4 * esets) * 32; }
 constexpr int C3_OP_BYTES = 32 * 128;                     // one match's operand tile: 32 f-rows x 64 h fp16 = 4 KB
 constexpr int C3_BUF_BYTES = 8 * C3_OP_BYTES;             // Xhi m0|m1, Xlo m0|m1, Yhi m0|m1, Ylo m0|m1 = 32 KB
 constexpr int C3_GS_STRIDE = 68;                          // floats per Gram row: 64 slots + 4 -> 16-byte stores of 8 consecutive rows hit 8 distinct bank quads (17 odd)
 constexpr int C3_GS_BYTES = 2 * 64 * C3_GS_STRIDE * 4;    // Gram of both matches [2][64 h][68], columns at their coset slots (icosa_cosets.cuh), one per epilogue set
-constexpr int C3_SMEM_BYTES = C3_GROUPS * C3_BUF_BYTES + 2 * C3_GS_BYTES + 3840 + 32 + 256 + 1024;   // 169 KB
+__host__ __device__ constexpr int c3_smem_bytes(int esets) { return C3_GROUPS * C3_BUF_BYTES + esets * C3_GS_BYTES + 3840 + 64 + 256 + 1024; }   // 169 KB (2 sets) / 203 KB (3 sets)
 // kind::f16, A and B MN-major, D = f32, M = N = 128
 constexpr uint32_t C3_IDESC = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(128 >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 // MN-major SWIZZLE_128B descriptor: LBO = 4096 B, SBO = 1024 B, version 1, layout type 2
@@ -64,16 +65,21 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
   asm volatile("{\n.reg .pred e;\nelect.sync _|e, 0xffffffff;\n@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n}" ::"r"(bar) : "memory");
 }
 
-template <bool TRACE, int VARIANT>
-__global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArgs a) {
+template <bool TRACE, int VARIANT, int LOADERS, int ESETS>
+__global__ void __launch_bounds__(c3_threads(LOADERS, ESETS), 1) group_corr_tc3_kernel(CorrTcArgs a) {
+  constexpr int C3_LOADERS = LOADERS, C3_THREADS = c3_threads(LOADERS, ESETS);
+  constexpr int NSLOT = (ESETS == 2) ? 2 : 2 * ESETS;      // mma_done barriers: one per (accumulator, epilogue set) combination an item can have
+  static_assert(ESETS >= 2 && ESETS <= 3 && LOADERS >= 4, "role layout");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
   uint8_t* bufs = smem;                                                                    // one 32 KB operand-tile set per loader group
-  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [2 epilogue sets][2 matches][64 h][68]
-  uint32_t* tabw = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(Gs) + 2 * C3_GS_BYTES);   // [2 warp halves][15][32 lanes] packed byte offsets, 3840 B
-  uint32_t* red_k = tabw + 2 * 15 * 32; int* red_i = reinterpret_cast<int*>(red_k + 4);   // [2 sets][2 matches] each
-  uint64_t* bars = reinterpret_cast<uint64_t*>(red_i + 4);                                 // 8-byte aligned: every size above is a multiple of 8
-  // barriers: 0..2 conv_done[set], 3..5 tiles_free[set], 6..7 mma_done[acc], 8..9 acc_free[acc].
+  float* Gs = reinterpret_cast<float*>(smem + C3_GROUPS * C3_BUF_BYTES);                   // [ESETS epilogue sets][2 matches][64 h][68]
+  uint32_t* tabw = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(Gs) + ESETS * C3_GS_BYTES);   // [2 warp halves][15][32 lanes] packed byte offsets, 3840 B
+  uint32_t* red_k = tabw + 2 * 15 * 32; int* red_i = reinterpret_cast<int*>(red_k + 8);   // [ESETS sets][2 matches] each (room for 4 sets)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(red_i + 8);                                 // 8-byte aligned: every size above is a multiple of 8
+  // barriers: 0..2 conv_done[set], 3..5 tiles_free[set], 6..11 mma_done[it % NSLOT], 12..13 acc_free[acc].
+  // mma_done has one barrier per (accumulator, epilogue set) pairing so that its only waiters - the 4 warps of ONE set - see its
+  // phases strictly in order (with 3 sets sharing 2 accumulators a per-accumulator barrier could be a phase behind its waiter).
   // Every waiter must only ever have to distinguish ADJACENT phases of a barrier (run 34: with three loader groups sharing
   // two tile sets a group ran two phases ahead of tiles_free and passed the parity test early -> deadlock).
   __shared__ uint32_t tmem_base_s;
@@ -100,7 +106,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   for (int e = threadIdx.x; e < C3_GROUPS * C3_BUF_BYTES / 16; e += C3_THREADS) reinterpret_cast<uint4*>(bufs)[e] = make_uint4(0, 0, 0, 0);
   if (threadIdx.x == 0) {
     for (int s = 0; s < C3_GROUPS; ++s) { mbar_init(BAR(0 + s), 4); mbar_init(BAR(3 + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR(6 + s), 1); mbar_init(BAR(8 + s), 4); }
+    for (int s = 0; s < NSLOT; ++s) mbar_init(BAR(6 + s), 1);
+    for (int s = 0; s < 2; ++s) mbar_init(BAR(12 + s), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == C3_LOADERS) {
@@ -115,25 +122,30 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
 
   // timeline instrumentation (TRACE instantiation only, unpredicated stores - see kernels_corr_tc2.cuh): event e of this CTA's i-th live item
 #define C3_TRACE(i, e) do { if (TRACE) a.trace[((size_t)blockIdx.x * 256 + ((i) < 255u ? (i) : 255u)) * 12 + (e)] = clock64(); } while (0)
-  const int items_per_pair = (a.K + 1) / 2;
-  const int n_items = a.B * items_per_pair;            // < 2^31 (checked by the launcher): 32-bit divisions only
-  // every role walks the same item sequence (item = blockIdx.x + i * gridDim.x -> pair p, first match k0 = 2 j) and skips the
-  // same items (device-side match counts); the walk carries (p, j) along so that the loops contain no division
-  const int step_p = (int)gridDim.x / items_per_pair, step_j = (int)gridDim.x % items_per_pair;
-  struct Walk { int item, p, j, cp, cn; };             // cp / cn: the pair whose match count is cached, and that count
-  auto walk_begin = [&]() -> Walk { return Walk{(int)blockIdx.x, (int)blockIdx.x / items_per_pair, (int)blockIdx.x % items_per_pair, -1, 0}; };
-  auto walk_next = [&](Walk& w) { w.item += gridDim.x; w.p += step_p; w.j += step_j; if (w.j >= items_per_pair) { w.j -= items_per_pair; ++w.p; } };
-  auto walk_avail = [&](Walk& w) -> int {              // <= 0: nothing, 1: one match, >= 2: two matches
-    // a CTA stays ~11 consecutive items inside one pair: the count is re-read only when the pair changes (run c2: the
-    // per-item global load sat on every role's critical path, ~1000 clk per item in the epilogue warps)
-    if (w.p != w.cp) { w.cp = w.p; w.cn = a.n_matches ? a.n_matches[w.p] : a.K; }
-    return w.cn - 2 * w.j;
+  const int items_per_pair = (a.K + 1) / 2;           // items are numbered p * items_per_pair + j (< 2^31, checked by the launcher)
+  // Every role walks the same item sequence: CTA b owns the items congruent to b modulo the grid; item (p, j) covers the matches
+  // 2 j, 2 j + 1 of pair p and is live while 2 j < n_matches[p].  The live items of a pair are its FIRST ones, so the walk goes
+  // pair by pair: one count load and one modulo per pair, then j advances by the grid size - no per-item global load, and the
+  // dead tail of each pair (a third of the item space at 3400 of 5000 matches) is never visited (run c3: the walk was 18 % of
+  // the epilogue warps' time and 25 % of the loaders').
+  struct Walk { int p, j, cn; };                       // cn = match count of pair p;  p >= B: end
+  auto walk_pair = [&](Walk& w) {                      // settle on the first live item of pair w.p or a later pair
+    for (; w.p < a.B; ++w.p) {
+      w.cn = a.n_matches ? a.n_matches[w.p] : a.K;
+      const int first = (int)(((long long)w.p * items_per_pair) % (int)gridDim.x);       // residue of the pair's item 0
+      w.j = (int)blockIdx.x - first; if (w.j < 0) w.j += (int)gridDim.x;
+      if (2 * w.j < w.cn) return;
+    }
   };
+  auto walk_begin = [&]() -> Walk { Walk w{0, 0, 0}; walk_pair(w); return w; };
+  auto walk_live = [&](const Walk& w) -> bool { return w.p < a.B; };
+  auto walk_next = [&](Walk& w) { w.j += (int)gridDim.x; if (2 * w.j >= w.cn) { ++w.p; walk_pair(w); } };
+  auto walk_avail = [&](const Walk& w) -> int { return w.cn - 2 * w.j; };   // 1: one match (odd tail), >= 2: two matches
 
   if (warp < C3_LOADERS) {
     // ===================== loaders =====================
-    // Row task T = 4 * (live item index) + role, role: 0 X m0, 1 X m1, 2 Y m0, 3 Y m1; warp w takes the tasks T = w (mod 11).
-    // A warp's successive items are 2-3 apart and the MMAs retire in item order, so when it waits for tiles_free of item L
+    // Row task T = 4 * (live item index) + role, role: 0 X m0, 1 X m1, 2 Y m0, 3 Y m1; warp w takes the tasks T = w (mod LOADERS).
+    // A warp's successive items are at most 3 apart and the MMAs retire in item order, so when it waits for tiles_free of item L
     // (the MMAs of item L-3) the barrier is at most one phase behind - the parity test stays unambiguous.
     // row of a (side, slot) for an item; the odd tail's second slot re-reads the first match
     auto row_ptr = [&](int p, int k0, int avail, int role) -> const float4* {
@@ -150,9 +162,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     const float4* next = nullptr; uint32_t next_it = 0; int next_role = 0;
     auto advance = [&]() {
       next = nullptr;
-      for (; wk.item < n_items; walk_next(wk)) {
+      for (; walk_live(wk); walk_next(wk)) {
         const int avail = walk_avail(wk);
-        if (avail <= 0) continue;
         const uint32_t my = live++;
         const int role = role_next;
         role_next = role_next >= 4 ? role_next - 4 : role_next + C3_LOADERS - 4;
@@ -202,12 +213,11 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
   } else if (warp == C3_LOADERS) {
     // ===================== MMA issuer: the whole warp walks the loop, one elected lane issues =====================
     uint32_t it = 0;
-    for (Walk wk = walk_begin(); wk.item < n_items; walk_next(wk)) {
-      if (walk_avail(wk) <= 0) continue;
+    for (Walk wk = walk_begin(); walk_live(wk); walk_next(wk)) {
       const int g = it % C3_GROUPS, acc = it & 1; const uint32_t gph = (it / C3_GROUPS) & 1, aph = (it >> 1) & 1;
       mbar_wait_lean(BAR(0 + g), gph);                 // operand tiles written and visible to the async proxy
       if (lane == 0) C3_TRACE(it, 4);
-      mbar_wait_lean(BAR(8 + acc), aph ^ 1);           // accumulators drained
+      mbar_wait_lean(BAR(12 + acc), aph ^ 1);          // accumulators drained
       if (lane == 0) C3_TRACE(it, 5);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t tb = smem_u32(bufs + g * C3_BUF_BYTES);
@@ -220,15 +230,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
       umma_f16_elect(d2, c3_desc(xhi), c3_desc(ylo), C3_IDESC, 1u);                 // hi.lo'
       umma_f16_elect(d2, c3_desc(xhi + 2048), c3_desc(ylo + 2048), C3_IDESC, 1u);
       umma_commit_elect(BAR(3 + g));                   // operand tiles reusable by their loader group
-      umma_commit_elect(BAR(6 + acc));                 // accumulators ready for the epilogue
+      umma_commit_elect(BAR(6 + it % NSLOT));          // accumulators ready for this item's epilogue set
       if (lane == 0) C3_TRACE(it, 6);
       ++it;
     }
   } else {
     // ===================== epilogue =====================
-    // two sets of 4 warps (12..15, 16..19): set s takes the items with it % 2 == s, i.e. accumulator buffer s - a warp is alone on
-    // its latency chain (run 39/40: 2100 clk per item), so two items are drained side by side
-    const int eset = (warp - 12) >> 2;
+    // ESETS sets of 4 warps: set s takes the items with it % ESETS == s (accumulator buffer it & 1) - a warp is alone on its
+    // latency chain (run 39/40: 2100 clk per item), so ESETS items are drained side by side
+    const int eset = (warp - (C3_LOADERS + 1)) >> 2;
     const int q = warp & 3;                            // TMEM lane quadrant of this warp
     const int m = q >> 1;                              // match slot: lanes 0..63 -> 0, 64..127 -> 1
     const int h = (q & 1) * 32 + lane;                 // Gram row (h) this thread owns in TMEM and stores
@@ -243,13 +253,12 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
     const uint32_t* tw_lane = tabw + (q & 1) * 15 * 32 + lane;
     const uint8_t* Gb = reinterpret_cast<const uint8_t*>(G);
     uint32_t it = 0;
-    for (Walk wk = walk_begin(); wk.item < n_items; walk_next(wk)) {
+    for (Walk wk = walk_begin(); walk_live(wk); walk_next(wk)) {
       const int avail = walk_avail(wk);
-      if (avail <= 0) continue;
-      if ((int)(it & 1) != eset) { ++it; continue; }
+      if ((int)(it % ESETS) != eset) { ++it; continue; }
       const int p = wk.p, k0 = 2 * wk.j;
-      const int buf = it & 1; const uint32_t ph = (it >> 1) & 1;
-      mbar_wait_lean(BAR(6 + buf), ph);
+      const int buf = it & 1; const uint32_t ph = (it / NSLOT) & 1;
+      mbar_wait_lean(BAR(6 + it % NSLOT), ph);
       if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 7);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * 256 + m * 64;
@@ -262,7 +271,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) group_corr_tc3_kernel(CorrTcArg
         if (half == 1) {
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
-          if (lane == 0) mbar_arrive(BAR(8 + buf));    // accumulators free as soon as they sit in registers
+          if (lane == 0) mbar_arrive(BAR(12 + buf));   // accumulators free as soon as they sit in registers
           if ((warp & 3) == 0 && lane == 0) C3_TRACE(it, 8);
         }
         // row store: this thread's row h, column g at slot(g), as 16-byte stores (8 consecutive rows = 8 distinct bank quads)
@@ -327,23 +336,27 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
   const bool v2 = (a.tab == c->d_permT8);               // variant 2 (R-indicator convention): its own coset layout
   RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   a.X = X; a.Y = Y; a.trace = nullptr;
+  static int sets = 0;                                   // role layout: ROREG_CORR_SETS=3 -> <11 loaders, 3 epilogue sets>, default <11, 2>
+  if (!sets) { const char* e = getenv("ROREG_CORR_SETS"); sets = (e && atoi(e) == 3) ? 3 : 2; }
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, C3_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true, 1, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(3)));
+    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(3)));
   }
   const long long items = (long long)a.B * ((a.K + 1) / 2);
   RR_ARG(c, items < (1LL << 31));
   const int grid = (int)(items < c->sm_count ? items : c->sm_count);
   const char* trace_fn = getenv("ROREG_DEBUG_CORR_TRACE");
   static bool traced = false;
-  if (trace_fn && !traced && !v2 && items >= 50000) {           // one-off timeline dump of CTA 0 (debug only; synchronises)
+  if (trace_fn && !traced && !v2 && items >= 50000) {    // one-off timeline dump of CTA 0 (debug only; synchronises)
     traced = true;
     const size_t nb = (size_t)grid * 256 * 12 * sizeof(long long);
     RR_CUDA(c, cudaMalloc(&a.trace, nb));
     RR_CUDA(c, cudaMemsetAsync(a.trace, 0, nb, st));
-    group_corr_tc3_kernel<true, 1><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
+    group_corr_tc3_kernel<true, 1, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
     RR_LAUNCH_CHECK(c);
     RR_CUDA(c, cudaStreamSynchronize(st));
     long long* h = (long long*)malloc(256 * 12 * sizeof(long long));
@@ -361,8 +374,13 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
     free(h); cudaFree(a.trace);
     return ROREG_OK;
   }
-  if (v2) group_corr_tc3_kernel<false, 2><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
-  else group_corr_tc3_kernel<false, 1><<<grid, C3_THREADS, C3_SMEM_BYTES, st>>>(a);
+  if (sets == 3) {
+    if (v2) group_corr_tc3_kernel<false, 2, 11, 3><<<grid, c3_threads(11, 3), c3_smem_bytes(3), st>>>(a);
+    else group_corr_tc3_kernel<false, 1, 11, 3><<<grid, c3_threads(11, 3), c3_smem_bytes(3), st>>>(a);
+  } else {
+    if (v2) group_corr_tc3_kernel<false, 2, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
+    else group_corr_tc3_kernel<false, 1, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
+  }
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

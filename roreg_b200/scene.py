@@ -38,22 +38,84 @@ class AsyncWriter:
         self.pending = []
 
 
-def load_scene(ctx, lay, dataset):
+def _read_npy_into(path, dst):
+    """Read a C-ordered .npy file straight into `dst` (a NumPy view of pinned host memory): header parsed with numpy.lib.format,
+    payload read with readinto - one copy (page cache -> pinned buffer), the GIL released while it runs."""
+    with open(path, "rb") as f:
+        major, _ = np.lib.format.read_magic(f)
+        shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if major == 1 else np.lib.format.read_array_header_2_0)(f)
+        if fortran or dtype != dst.dtype or tuple(shape) != tuple(dst.shape):
+            raise ValueError(f"{path}: {dtype} {shape} (fortran={fortran}), expected C-ordered {dst.dtype} {dst.shape}")
+        buf = dst.reshape(-1).view(np.uint8)
+        got = f.readinto(memoryview(buf))
+        if got != buf.nbytes:
+            raise ValueError(f"{path}: truncated ({got} of {buf.nbytes} bytes)")
+
+
+def load_scene(ctx, lay, dataset, readers=8, ring=6):
     """Every cloud of the dataset once: descriptors [C,n,32,60] float32 and keypoints [C,n,3] float64 on the device, plus the
-    cloud id -> arena slot map.  Clouds are uploaded one by one (host peak = one cloud)."""
+    cloud id -> arena slot map.  `readers` threads read the descriptor files into a ring of pinned host buffers (host peak =
+    `ring` clouds); each buffer is copied host->device asynchronously on a side stream as soon as it is full and recycled when
+    that copy has finished, so file reads, PCIe copies and (for the caller) the first batches overlap."""
     ids = list(dataset.pc_ids)
     slot = {pc: i for i, pc in enumerate(ids)}
-    desc = keys = None
-    for i, pc in enumerate(ids):
-        d = np.load(lay.yoho_desc(pc)); k = dataset.get_kps(pc)
-        if desc is None:
-            n = d.shape[0]
-            desc = torch.empty((len(ids), n, 32, 60), dtype=torch.float32, device=ctx.device)
-            keys = torch.empty((len(ids), n, 3), dtype=torch.float64, device=ctx.device)
-        if d.shape != tuple(desc.shape[1:]) or k.shape != (desc.shape[1], 3):
-            raise ValueError(f"cloud {pc}: {d.shape} descriptors / {k.shape} keypoints, the arena holds clouds of {desc.shape[1]} "
-                             "keypoints (the reference's caches are 5000 per cloud)")
-        desc[i].copy_(ctx.dev(d.astype(np.float32))); keys[i].copy_(ctx.dev(k, torch.float64))
+    first = np.load(lay.yoho_desc(ids[0]), mmap_mode="r")
+    n = first.shape[0]
+    if first.shape != (n, 32, 60) or first.dtype != np.float32:
+        raise ValueError(f"cloud {ids[0]}: {first.dtype} {first.shape}, expected float32 [n,32,60]")
+    del first
+    desc = torch.empty((len(ids), n, 32, 60), dtype=torch.float32, device=ctx.device)
+    keys = torch.empty((len(ids), n, 3), dtype=torch.float64, device=ctx.device)
+    ring = max(1, min(ring, len(ids)))
+    on_gpu = torch.device(ctx.device).type == "cuda"            # the oracle-backed context of the CPU test suite has no streams to overlap
+    cache = getattr(ctx, "_scene_ring", None)                    # pinning ~40 MB buffers costs tens of ms each: keep the ring with the context
+    if cache is not None and cache[0] == (n, ring):
+        pinned = cache[1]
+    else:
+        pinned = [torch.empty((n, 32, 60), dtype=torch.float32) for _ in range(ring)]
+        if on_gpu:
+            pinned = [p.pin_memory() for p in pinned]
+        try:
+            ctx._scene_ring = ((n, ring), pinned)
+        except AttributeError:
+            pass
+    views = [p.numpy() for p in pinned]
+    free = [torch.cuda.Event() for _ in range(ring)] if on_gpu else None
+    side = torch.cuda.Stream(device=ctx.device) if on_gpu else None
+
+    def read(i, b):
+        try:
+            _read_npy_into(lay.yoho_desc(ids[i]), views[b])
+        except ValueError as e:
+            raise ValueError(f"cloud {ids[i]}: {e} (the arena holds clouds of {n} keypoints; the reference's caches are 5000 per cloud)")
+        return i, b
+
+    with cf.ThreadPoolExecutor(max_workers=max(1, readers)) as pool:
+        pending = {}
+        nxt = 0
+        for b in range(ring):                                   # prime the ring
+            pending[b] = pool.submit(read, nxt, b); nxt += 1
+        done_clouds = 0
+        while done_clouds < len(ids):
+            b = done_clouds % ring                              # buffers complete in submission order
+            i, _ = pending.pop(b).result()
+            if on_gpu:
+                with torch.cuda.stream(side):
+                    desc[i].copy_(pinned[b], non_blocking=True)
+                    free[b].record(side)
+            else:
+                desc[i].copy_(pinned[b])
+            k = dataset.get_kps(ids[i])
+            if k.shape != (n, 3):
+                raise ValueError(f"cloud {ids[i]}: {k.shape} keypoints, the arena holds clouds of {n} keypoints")
+            keys[i].copy_(torch.from_numpy(np.ascontiguousarray(k, np.float64)))
+            done_clouds += 1
+            if nxt < len(ids):
+                if on_gpu:
+                    free[b].synchronize()                       # the copy out of this buffer has finished: refill it
+                pending[b] = pool.submit(read, nxt, b); nxt += 1
+    if on_gpu:
+        torch.cuda.current_stream(ctx.device).wait_stream(side)
     return desc, keys, slot
 
 
@@ -86,7 +148,8 @@ def _write_pair(lay, max_iter, id0, id1, matches, dr_index, pose, recall):
     np.savez(lay.result('yohoc', max_iter, id0, id1), trans=pose, recalltime=recall)
 
 
-def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_mode=4, seed=0, writer_threads=2, ctx=None):
+def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_mode=4, seed=0, writer_threads=4, ctx=None, shard=True,
+                   readers=8):
     """mutual.run + yohoc.run of the reference for a whole dataset on the batched engine.  Returns (on every rank) a dict with this
     rank's slice: pair indices `lo, hi`, `poses` [hi-lo,4,4] float64, `recall` [hi-lo], `n_matches` [hi-lo] (NumPy).  Files are
     written for the rank's own pairs; rank 0 writes pre.log after a barrier."""
@@ -97,11 +160,11 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
     out_dir = lay.result_dir('yohoc', max_iter)
     for d in (lay.match_dir, lay.scores_dir, lay.dr_index_dir, out_dir):
         make_non_exists_dir(d)
-    dist_on = dist.is_available() and dist.is_initialized()
+    dist_on = shard and dist.is_available() and dist.is_initialized()      # shard=False: this rank registers the WHOLE dataset itself
     rank = dist.get_rank() if dist_on else 0
     world = dist.get_world_size() if dist_on else 1
     pairs_all = list(dataset.pair_ids)
-    desc, keys, slot = load_scene(ctx, lay, dataset)
+    desc, keys, slot = load_scene(ctx, lay, dataset, readers=readers)
     n = desc.shape[1]
     if keynum > n:
         raise ValueError(f"keynum {keynum} exceeds the {n} keypoints per cloud")
@@ -136,5 +199,5 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
     if dist_on:
         dist.barrier()
     if rank == 0:
-        host.write_trajectory(dataset, out_dir)
+        host.write_trajectory(dataset, out_dir, poses if (lo, hi) == (0, len(pairs_all)) else None)
     return dict(lo=lo, hi=hi, poses=poses, recall=recall, n_matches=counts)

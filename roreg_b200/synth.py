@@ -101,3 +101,55 @@ class SynthDataset:
             os.makedirs(d_out, exist_ok=True)
             for cid in self.pc_ids:
                 np.save(f"{d_out}/{cid}.npy", self.get_feats(cid))
+
+
+class SynthScene:
+    """A whole synthetic SCENE with the access pattern of the reference's test sets (3DMatch: 433 clouds / 1623 pairs, a cloud takes
+    part in ~7.5 pairs): `n_clouds` views of one world of keypoints, every view = the world rotated by R_c = R_res . Rgroup[a_c]
+    (descriptors permuted by P[a_c], the equivariance law of the module docstring), translated, sub-sampled to n keypoints and
+    perturbed; pairs = each cloud with its next `span` neighbours.  Same duck type as SynthDataset / dataops/dataset.py:41-129.
+    For pair (id0 = c, id1 = d):  R_c R_d^T . pts(d) + (t_c - R_c R_d^T t_d) = pts(c)   (dataops/dataset.py:27-30)."""
+
+    def __init__(self, seed, n_clouds=60, n_pairs=225, n=5000, name="synth/scene", overlap=0.67, sigma_desc=0.08, sigma_xyz=0.01,
+                 max_res_deg=7.0, tables=None):
+        tb = tables or _group.load()
+        rng = np.random.default_rng(seed)
+        self.name, self.n = name, n
+        n_world = int(round(n / overlap))
+        world_xyz = rng.uniform(0.0, 3.0, (n_world, 3))
+        world_desc = _unit(rng.standard_normal((n_world, 32, 60), dtype=np.float32), 1)
+        self.pc_ids = [str(c) for c in range(n_clouds)]
+        self.keys, self.feats, self.pose, self.rows = [], [], [], []
+        for c in range(n_clouds):
+            a = int(rng.integers(0, 60))
+            R = small_rotation(rng, max_res_deg) @ tb.rot[a]
+            t = rng.uniform(-1.0, 1.0, 3)
+            rows = rng.permutation(n_world)[:n]
+            self.keys.append(world_xyz[rows] @ R.T + t + sigma_xyz * rng.standard_normal((n, 3)))
+            self.feats.append(_unit(world_desc[rows][:, :, tb.perm[a]] + sigma_desc * rng.standard_normal((n, 32, 60), dtype=np.float32), 1))
+            self.pose.append((R, t)); self.rows.append(rows)
+        span = -(-n_pairs // n_clouds)
+        self.pair_ids = [(str(c), str((c + g) % n_clouds)) for g in range(1, span + 1) for c in range(n_clouds)][:n_pairs]
+        self.pair_ids = [(a_, b_) if int(a_) < int(b_) else (b_, a_) for a_, b_ in self.pair_ids]
+
+    def get_kps(self, cid):
+        return self.keys[int(cid)]
+
+    def get_feats(self, cid):
+        return self.feats[int(cid)]
+
+    def get_transform64(self, id0, id1):
+        (Rc, tc), (Rd, td) = self.pose[int(id0)], self.pose[int(id1)]
+        R = Rc @ Rd.T
+        return np.concatenate([R, (tc - R @ td)[:, None]], 1)
+
+    def get_transform(self, id0, id1):
+        return self.get_transform64(id0, id1).astype(np.float32)
+
+    def write_cache(self, cache_root):
+        """YOHO_Output_Group_feature/{pc}.npy as test/extractor.py:60 leaves them."""
+        import os
+        d_out = f"{cache_root}/{self.name}/YOHO_Output_Group_feature"
+        os.makedirs(d_out, exist_ok=True)
+        for cid in self.pc_ids:
+            np.save(f"{d_out}/{cid}.npy", self.feats[int(cid)])
