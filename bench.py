@@ -55,16 +55,19 @@ def parse():
     ap.add_argument("--max-iter", type=int, default=1000)
     ap.add_argument("--nn-mode", type=int, default=int(os.environ.get("ROREG_NN_MODE", "4")),
                     help="0 = float32 difference form (reference arithmetic), 1-3 = tcgen05 3xTF32 Gram variants, 4 = one fp16 two-accumulator Gram per pair (default)")
-    ap.add_argument("--score-mode", type=int, default=int(os.environ.get("ROREG_SCORE_MODE", "0")),
-                    help="one-shot scoring arithmetic: 0 float64 (default), 1 float32 pre-filter + exact float64 re-check")
-    ap.add_argument("--pipelined", type=int, default=int(os.environ.get("ROREG_PIPELINED", "0")),
-                    help="1: the resident-input loop uses roreg_register_batch_pipelined (RANSAC tail of batch i-1 beside the pooling of batch i)")
+    ap.add_argument("--score-mode", type=int, default=int(os.environ.get("ROREG_SCORE_MODE", "1")),
+                    help="one-shot scoring arithmetic: 0 float64, 1 float32 pre-filter + exact float64 re-check (default; bit-identical overlaps, tests/test_gpu_parity.py::test_score_mode1_equals_float64_scoring)")
+    ap.add_argument("--pipelined", type=int, default=int(os.environ.get("ROREG_PIPELINED", "1")),
+                    help="1 (default): the resident-input loop uses roreg_register_batch_pipelined (RANSAC tail of batch i-1 beside the pooling of batch i; identical results, test_register_batch_pipelined_equals_serial); 0: one serial enqueue per batch")
     ap.add_argument("--value-only", type=int, default=0,
                     help="1 (kernel A/B experiments only): one untimed-quality step for the e2e / scene phases; their numbers are then meaningless")
     ap.add_argument("--corr-mode", type=int, default=int(os.environ.get("ROREG_CORR_MODE", "3")),
                     help="0 = FP32 CUDA-core Gram, 1-2 = tcgen05 3xTF32 Gram, 3 = fp16 two-accumulator Gram, operands from registers (default)")
     ap.add_argument("--scene-clouds", type=int, default=60, help="e2e scene: clouds (files read + uploaded once each)")
     ap.add_argument("--scene-pairs", type=int, default=225, help="e2e scene: pairs registered (3DMatch: 433 clouds / 1623 pairs)")
+    ap.add_argument("--extras", type=int, default=1, help="1: also time the tensor-core workloads (yohoo estimator with the ET network; Match_ot matcher) as extra blocks")
+    ap.add_argument("--extra-pairs", type=int, default=32, help="pairs per step of the yohoo extra workload")
+    ap.add_argument("--net-passes", type=int, default=1, help="GEMM passes of the extra workloads' networks: 1 = TF32 (what the reference's cuDNN / cuBLAS path does on Ampere+), 3 = 3xTF32 (float32-class, the parity mode)")
     ap.add_argument("--cpu-sample-pairs", type=int, default=8)
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="bounded CPU-baseline sample (seconds of host work)")
     return ap.parse_args()
@@ -274,6 +277,86 @@ def workload_config(args, B):
             "l2": "inputs larger than L2 (B x 77 MB streamed per step), no flush needed"}
 
 
+def extra_workloads(args, ctx, peaks):
+    """Tensor-core-heavy configurations of the same path, timed on rank 0 as EXTRA blocks of the JSON line (the headline stays the
+    reference's default CLI pipeline):
+      yohoo  - mutual -> Des2R -> ET network on the <= max_iter hypotheses that are scored (network/eqv_trans.py:119-138, only group
+               element 0 of the head and its 13 + 60 inputs are computed) -> hypotheses -> one-shot RANSAC -> 2x refine, through
+               pipeline.YohooEngine at --extra-pairs pairs per step (test/estimator.py:445-454);
+      match_ot - the rotation-coherence matcher's forward (network/rot_coh_match.py:339-390) on one pair of 2 x n keypoints.
+    Networks use random weights of the checkpoints' shapes (synth.random_weights); inputs are resident."""
+    import torch
+    from roreg_b200 import matchot, pipeline, synth
+    out = {}
+    n, H, Bx, npass = args.n, args.max_iter, args.extra_pairs, args.net_passes
+    tf32_peak = 0.5 * peaks.get("bf16_tflops_sustained", 1400.0)
+    prs = [synth.make_pair(5000 + i, n=n, with_fcgf=True, max_res_deg=2.0) for i in range(min(Bx, 4))]
+    reps = -(-Bx // len(prs))                                  # the batch cycles over a few distinct pairs (host RAM / generation time)
+    desc = ctx.dev(np.stack([x for pr in prs for x in (pr["feats0"], pr["feats1"])])); fcgf = ctx.dev(np.stack([x for pr in prs for x in (pr["fcgf0"], pr["fcgf1"])]))
+    keys = ctx.dev(np.stack([x for pr in prs for x in (pr["keys0"], pr["keys1"])]), torch.float64)
+    pc = ctx.dev(np.array([[2 * (i % len(prs)), 2 * (i % len(prs)) + 1] for i in range(Bx)], np.int32))
+    try:
+        eng = pipeline.YohooEngine(ctx, synth.random_weights("ET", 102), npass=npass, max_iter=H, ird=0.1, nn_mode=args.nn_mode)
+        for w in range(2):
+            eng.register(desc, fcgf, keys, pc, seed=w)
+        torch.cuda.synchronize()
+        steps = 5
+        marks = []
+        l0 = ctx.launches
+        for s_ in range(steps):
+            o = eng.register(desc, fcgf, keys, pc, seed=10 + s_, events=marks)
+        torch.cuda.synchronize()
+        per = len(marks) // steps
+        stage = {}
+        for s_ in range(steps):
+            m = marks[s_ * per:(s_ + 1) * per]
+            for (_, e0), (name, e1) in zip(m[:-1], m[1:]):
+                stage[name] = stage.get(name, 0.0) + e0.elapsed_time(e1) / steps
+        ms = marks[0][1].elapsed_time(marks[-1][1]) / steps
+        nh = float(o["n_hyp"].double().mean().item())
+        flops = Bx * nh * 2.0 * (13 * 128 * 256 * 60 + 13 * 256 * 512 * 13 + 13 * 512 * 256 + 256 * 512 + 512 * 128 + 128 * 4)
+        gt = np.stack([prs[i % len(prs)]["gt"] for i in range(Bx)])
+        err = float(np.abs(o["poses"].cpu().numpy()[:, :3] - gt).max())
+        ach = flops / (stage["et_network"] * 1e-3) / 1e12
+        out["workload_yohoo"] = {
+            "value": Bx / (ms * 1e-3), "unit": "pairs/s", "pairs_per_step": Bx, "steps": steps, "ms_per_step": ms, "stage_ms_per_step": stage,
+            "gpu_launches_per_step": (ctx.launches - l0) / steps, "hypotheses_per_pair": nh, "net_passes": npass, "max_abs_err_vs_gt": err,
+            "roofline": {"kernel": "gemm_tc_kernel (ET network: implicit group-conv GEMMs + FC head)", "bound": "tensor", "achieved": ach,
+                         "peak": tf32_peak * (1.0 if npass == 1 else 1.0 / 3.0), "unit": "TFLOP/s",
+                         "frac": ach / (tf32_peak * (1.0 if npass == 1 else 1.0 / 3.0)), "traffic": None,
+                         "note": "algorithmic flops = the pruned network (99.2 MFLOP per hypothesis: 60 group elements in layer 1, the 13 "
+                                 "neighbours of g = 0 in layer 2, g = 0 alone afterwards; the reference computes 483.8 MFLOP) x hypotheses / "
+                                 "CUDA-event time of the ET stage; peak = half the measured sustained dense bf16 rate (TF32), divided by the "
+                                 "number of passes"},
+            "note": "extra: yohoo estimator (ET network inside the timed region), inputs resident, random weights of the checkpoint shapes "
+                    "(ET head biased to the identity quaternion); the batch cycles over " + str(len(prs)) + " distinct pairs"}
+        del eng
+    except Exception as e:                                   # an extra block must never take the headline down
+        out["workload_yohoo"] = {"unavailable": repr(e)}
+    try:
+        pr = prs[0]
+        f0 = ctx.dev(pr["feats0"]); f1 = ctx.dev(pr["feats1"])
+        k0 = ctx.dev(pr["keys0"].astype(np.float32)); k1 = ctx.dev(pr["keys1"].astype(np.float32))
+        mo = matchot.MatchOT(ctx, synth.random_weights("RM", 104), npass=npass)
+        for w in range(2):
+            mo.forward(f1, f0, k1, k0)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        l0 = ctx.launches; steps = 3
+        e0.record()
+        for s_ in range(steps):
+            m0, s0 = mo.forward(f1, f0, k1, k0)                  # NOTE THE SWAP: the network's source side is cloud id1 (test/matcher.py:192-197)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out["workload_match_ot"] = {"value": 1e3 / ms, "unit": "pairs/s", "ms_per_pair": ms, "keypoints": n, "steps": steps, "net_passes": npass,
+                                    "gpu_launches_per_pair": (ctx.launches - l0) / steps, "matched": int((m0 >= 0).sum().item()),
+                                    "note": "extra: Match_ot.forward (--RM matcher: 2 graph blocks, 4 R-indicators, 100 Sinkhorn iterations, mutual "
+                                            "assignment) on one pair, inputs resident, random weights of the checkpoint shapes"}
+    except Exception as e:
+        out["workload_match_ot"] = {"unavailable": repr(e)}
+    return out
+
+
 def scene_e2e(args, ctx, rank, world, barrier):
     """The headline e2e: one whole synthetic scene per rank through scene.register_scene - descriptor files read from the cache
     directory, host->device copies, batched registration, the reference's per-pair files and pre.log written - timed from the call
@@ -344,8 +427,7 @@ def main():
     torch.cuda.set_device(local)
     ctx = ops.Context(local)
     ctx.set_corr_mode(args.corr_mode)
-    if args.score_mode:
-        ctx.set_score_mode(args.score_mode)
+    ctx.set_score_mode(args.score_mode)
     B, n, H = args.pairs_per_step, args.n, args.max_iter
     prs, desc_h, keys_h, pc_h = make_inputs(B, n, rank)
     old_affinity = bind_to_gpu_numa_node(local) if world > 1 else None
@@ -607,6 +689,8 @@ def main():
             line["value_only"] = True; line["e2e"]["note"] = "--value-only run: the e2e figures were not measured properly (tiny scene, one step)"
         if cb:
             line["cpu_baseline"] = cb
+        if args.extras and not args.value_only and world == 1:
+            line.update(extra_workloads(args, ctx, peaks))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

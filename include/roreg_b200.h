@@ -122,16 +122,21 @@ int roreg_kabsch3(roreg_ctx* ctx, const double* k0_sel, const double* k1_sel, co
 
 /* ---- a1-a3 / a22  group-convolution networks (GF: network/group_feat.py:26-45, ET: network/eqv_trans.py:119-138,
  * RD: network/rot_detect.py:43-55).  Activations are channel-last rows [(item*60+g)][C] split into tf32 hi/lo
- * parts; a group convolution is im2col over the 13 group neighbours (data_process, group_feat.py:20-24) followed
- * by the tcgen05 GEMM with a fused bias / residual / eval-BN / ReLU epilogue.                                      */
+ * parts; a group convolution gathers the 13 group neighbours (data_process, group_feat.py:20-24) inside the operand
+ * load of the tcgen05 GEMM, which has a fused bias / residual / eval-BN / ReLU epilogue.                           */
 /* descriptors [*,32,60] -> rows [(item*60+g)][n_src*32]; src_host / rows_host / permute_host are HOST arrays of
  * n_src device pointers / flags; flagged sources are read through P[pre_idx[item]] (eqv_trans.py:126-128).      */
 int roreg_pack_descriptors(roreg_ctx* ctx, int n_src, const float* const* src_host, const int32_t* const* rows_host,
                            const int32_t* permute_host, const int32_t* pre_idx, int n_items, const float* bn_scale,
                            const float* bn_shift, int relu, float* out_hi, float* out_lo, void* stream);
-/* out[(item*n_gout+j)][k*C+c] = act[(item*60 + N[gset[j]][k])][c]; gset NULL = all 60 group elements.            */
-int roreg_gconv_im2col(roreg_ctx* ctx, const float* act_hi, const float* act_lo, int n_items, int C,
-                       const int32_t* gset, int n_gout, float* out_hi, float* out_lo, void* stream);
+/* Group convolution as an IMPLICIT GEMM (data_process + Conv2d(C, O, (1,13)): network/group_feat.py:20-33, ops.py:45-51):
+ * out[(item*n_gout+j)][o] = sum_{k,c} act[(item*60 + N[gset[j]][k])][c] W[o][k*C+c] (+ epilogue as roreg_gemm); the
+ * 13-neighbour gather happens in the GEMM's operand load (TMA tile::gather4), nothing is materialised.  C % 32 == 0;
+ * gset NULL = all 60 group elements (n_gout = 60); act_lo / W_lo / out_lo may be NULL when npass == 1.              */
+int roreg_gconv_gemm(roreg_ctx* ctx, const float* act_hi, const float* act_lo, int n_items, int C, const int32_t* gset,
+                     int n_gout, const float* W_hi, const float* W_lo, int w_rows, int O, int NT, int npass,
+                     const float* bias, const float* residual, int res_ld, float* raw_out, int raw_ld, float* out_hi,
+                     float* out_lo, int out_ld, const float* bn_scale, const float* bn_shift, int relu, void* stream);
 /* out[r][o] = sum_c A[r][c] W[o][c]; v = out + bias (+ residual[r*res_ld+o]); raw_out = v; act = relu?(v*bn_scale
  * + bn_shift) split hi/lo.  Kdim % 32 == 0; W has w_rows >= ceil(O/NT)*NT rows; npass 1 (TF32) or 3 (3xTF32).    */
 int roreg_gemm(roreg_ctx* ctx, const float* A_hi, const float* A_lo, int R, int Kdim, const float* W_hi,

@@ -42,7 +42,7 @@ SIGNATURES = {
     "roreg_refine_once": (_i, [_p, _p, _p, _p, _i, _i, _p, _d, _p, _p, _p]),
     "roreg_kabsch3": (_i, [_p, _p, _p, _p, _i, _p, _p]),
     "roreg_pack_descriptors": (_i, [_p, _i, _p, _p, _p, _p, _i, _p, _p, _i, _p, _p, _p]),
-    "roreg_gconv_im2col": (_i, [_p, _p, _p, _i, _i, _p, _i, _p, _p, _p]),
+    "roreg_gconv_gemm": (_i, [_p, _p, _p, _i, _i, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p, _i, _p]),
     "roreg_gemm": (_i, [_p, _p, _p, _i, _i, _p, _p, _i, _i, _i, _i, _p, _p, _i, _p, _i, _p, _p, _i, _p, _p, _i, _p]),
     "roreg_gf_finalize": (_i, [_p, _p, _p, _i, _p, _p]),
     "roreg_rd_finalize": (_i, [_p, _p, _i, _p, _p]),

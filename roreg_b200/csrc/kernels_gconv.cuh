@@ -4,9 +4,11 @@
 //
 // Activations live channel-LAST: act[(item*60 + g)][c], split into tf32 hi / lo parts by the producing
 // epilogue.  A group convolution  out[o,g] = b[o] + sum_{c,k} W[o,c,k] act[c, N[g,k]]  is the GEMM of
-//   A[(item, g)][(k, c)] = act[(item*60 + N[g,k])][c]        (im2col over the 13 group neighbours)
-// with W_flat[o][(k,c)].  Only the output group elements a later stage needs are gathered (`gset`), which
-// is how ET's "only g = 0 of the head is used" (network/eqv_trans.py:136) prunes the two last layers.
+//   A[(item, g)][(k, c)] = act[(item*60 + N[g,k])][c]        (the 13 group neighbours of g)
+// with W_flat[o][(k,c)].  A is IMPLICIT: the GEMM's producer warp gathers the activation rows with
+// cp.async.bulk.tensor tile::gather4 (kernels_gemm_tc.cuh, GemmArgs.g_*) - round 1 materialised it with an im2col
+// pass (13x the activation bytes written and read back).  Only the output group elements a later stage needs are
+// computed (`gset`), which is how ET's "only g = 0 of the head is used" (network/eqv_trans.py:136) prunes the two last layers.
 #pragma once
 #include "common.cuh"
 
@@ -42,26 +44,6 @@ __global__ void __launch_bounds__(256) pack_desc_kernel(PackArgs a) {
     const long long o = ((long long)item * 60 + g) * C + oc;
     a.out_hi[o] = hi;
     if (a.out_lo) a.out_lo[o] = y - hi;
-  }
-}
-
-// ---- im2col over the group neighbourhood --------------------------------------------------------------------
-// out[(item*n_gout + j)][k*C + c] = act[(item*60 + nei[gset[j]][k])][c]      (float4 granularity, C % 4 == 0)
-__global__ void __launch_bounds__(256) gconv_im2col_kernel(const float* __restrict__ act_hi, const float* __restrict__ act_lo,
-                                                           int n_items, int C, const int32_t* __restrict__ nei,
-                                                           const int32_t* __restrict__ gset, int n_gout,
-                                                           float* __restrict__ out_hi, float* __restrict__ out_lo) {
-  const int c4 = C >> 2;
-  const long long per_row = 13LL * c4;
-  const long long total = (long long)n_items * n_gout * per_row;
-  for (long long e = blockIdx.x * 256LL + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
-    const long long r = e / per_row; const int w = (int)(e % per_row);
-    const int k = w / c4, q = w % c4;
-    const int item = (int)(r / n_gout), j = (int)(r % n_gout);
-    const int g = gset ? gset[j] : j;
-    const long long srow = (long long)item * 60 + nei[g * 13 + k];
-    reinterpret_cast<float4*>(out_hi)[e] = reinterpret_cast<const float4*>(act_hi)[srow * c4 + q];
-    if (out_lo) reinterpret_cast<float4*>(out_lo)[e] = reinterpret_cast<const float4*>(act_lo)[srow * c4 + q];
   }
 }
 

@@ -2,26 +2,38 @@
 //
 //   out[r][o] = sum_c A[r][c] * W[o][c]         A: [R][Kdim] activations (rows = (item, group element)),
 //                                                W: [O][Kdim] weights, both K-major float32 in HBM.
-// A group convolution (network/ops.py:11-20) is this GEMM on the im2col-gathered activation matrix
-// (Kdim = 13*Cin, see kernels_gconv.cuh); the 1x1 FC head of ET_test (network/eqv_trans.py:93-101) is it
+// A group convolution (network/ops.py:11-20) is this GEMM on the neighbour-gathered activation matrix, gathered by the
+// producer warp itself (Kdim = 13*Cin, GemmArgs.g_*, see kernels_gconv.cuh); the 1x1 FC head of ET_test (network/eqv_trans.py:93-101) is it
 // directly.  Precision: npass = 1 -> one TF32 pass (what the reference's own cuDNN path does on Ampere+,
 // torch.backends.cudnn.allow_tf32 defaults to True), npass = 3 -> hi/lo split of both operands, three
 // passes (hi.hi + lo.hi + hi.lo) into the same accumulator: float32-class, used for parity with the oracle.
 // Fused epilogue (one thread per output row, TMEM -> registers):
 //   v = acc + bias[o] (+ residual[r][o]);  raw_out[r][o] = v;  y = v*bn_scale[o] + bn_shift[o];  relu;
 //   act_hi[r][o] = tf32(y), act_lo[r][o] = y - tf32(y)      (the next layer's operands)
-// Pipeline: warp 0 TMA producer (SWIZZLE_128B boxes), warp 1 MMA issuer, warps 2-5 epilogue; 4 smem stages;
-// two TMEM accumulators of up to 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Pipeline: warp 0 TMA producer (SWIZZLE_128B boxes, or tile::gather4 row gathers for the implicit group convolution),
+// warp 1 MMA issuer, warps 2-5 epilogue; every operand image of a k-chunk is loaded ONCE per stage and all passes run from
+// it; two TMEM accumulators of up to 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
 #pragma once
 #include "kernels_nn_tc.cuh"
 
 namespace roreg {
 
-constexpr int GM_BM = 128, GM_KC = 32, GM_STAGES = 4;
+constexpr int GM_BM = 128, GM_KC = 32;
 constexpr int GM_A_BYTES = GM_BM * GM_KC * 4;            // 16 KB
 constexpr int GM_W_BYTES = 256 * GM_KC * 4;              // up to 32 KB (NT <= 256 weight rows)
-constexpr int GM_STAGE_BYTES = GM_A_BYTES + GM_W_BYTES;  // 48 KB
-constexpr int GM_SMEM_BYTES = GM_STAGES * GM_STAGE_BYTES + 1024 + 256;
+// One stage holds EVERY operand image the passes of a k-chunk need, so each image is read from L2 once per k-chunk
+// (round 1 re-loaded A_hi and W_hi for the second / third pass: 144 KB per k-chunk against the ~42 B/clk/SM the L2 delivers):
+//   1 pass : A | W                 48 KB x 4 stages
+//   3 pass : A_hi | A_lo | W_hi | W_lo   96 KB x 2 stages (a stage is 12 MMAs = ~1500 tensor clocks: two are enough to prefetch)
+template <int NPASS> struct GemmCfg {
+  static constexpr int STAGES = NPASS == 3 ? 2 : 4;
+  static constexpr int A_IMAGES = NPASS == 3 ? 2 : 1;
+  static constexpr int STAGE_BYTES = A_IMAGES * (GM_A_BYTES + GM_W_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int OFF_ALO = GM_A_BYTES;                         // 3-pass only
+  static constexpr int OFF_WHI = A_IMAGES * GM_A_BYTES;
+  static constexpr int OFF_WLO = OFF_WHI + GM_W_BYTES;               // 3-pass only
+};
 
 struct GemmArgs {
   int R, Kdim, O, NT;          // rows, contraction length (multiple of 32), valid output channels, N tile (16..256, %16 == 0)
@@ -36,23 +48,45 @@ struct GemmArgs {
   // a_cols[g] - a permutation applied by the TMA coordinate alone, no data movement.
   const int32_t* a_cols;       // [Kdim/32] A column (element) coordinate per k-chunk, or NULL = kc*32
   uint8_t* amax_arg; int amax_id;   // if set: raw_out / amax_arg hold a running (max, argmax id) instead of being overwritten
+  // IMPLICIT GROUP CONVOLUTION (network/group_feat.py:20-24 data_process folded into the operand load): when g_C > 0 the A
+  // operand is never materialised.  The tensor maps describe the channel-last ACTIVATION [n_items*60][g_C]; GEMM row
+  // r = item * g_ng + j (output group element g = g_set ? g_set[j] : j) and k-chunk kc (tap k = kc*32 / g_C, channels
+  // c0 = kc*32 % g_C) read activation row item*60 + g_nei[g][k], columns c0..c0+31 - fetched four rows per instruction with
+  // cp.async.bulk.tensor ... tile::gather4 straight into the SWIZZLE_128B operand tile (Kdim = 13 * g_C).
+  int g_C, g_ng; const int32_t* g_nei; const int32_t* g_set;
 };
 
+// four rows of a 2-D tensor (box = 32 columns x 1 row) -> 4 x 128 B at dst, swizzled on the absolute shared-memory address
+// exactly like a 4-row box (scripts/gather4_test.cu, profiles/r02_gather4_test.txt)
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map, int col, int r0, int r1, int r2, int r3, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];"
+               ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
+}
+
+template <int NPASS>
 __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
+  using Cfg = GemmCfg<NPASS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GM_STAGES * GM_STAGE_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   // barriers: 0..3 full, 4..7 empty, 8..9 tmem_full, 10..11 tmem_empty
   __shared__ uint32_t tmem_base_s;
   __shared__ int32_t acols_s[256];
+  __shared__ int32_t nei_s[60 * 13];
+  __shared__ int32_t gset_s[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
+  const bool gather = a.g_C > 0;
   for (int i = threadIdx.x; i < a.Kdim / GM_KC && i < 256; i += blockDim.x) acols_s[i] = a.a_cols ? a.a_cols[i] : i * GM_KC;
+  if (gather) {
+    for (int i = threadIdx.x; i < 60 * 13; i += blockDim.x) nei_s[i] = a.g_nei[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) gset_s[i] = (a.g_set && i < a.g_ng) ? a.g_set[i] : i;
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < GM_STAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -68,24 +102,46 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const int n_tiles = n_mt * a.n_ntiles;
   const int n_kc = a.Kdim / GM_KC;
-  const int n_k = n_kc * a.npass;
-  const uint32_t stage_tx = GM_A_BYTES + (uint32_t)a.NT * GM_KC * 4;
+  const uint32_t w_bytes = (uint32_t)a.NT * GM_KC * 4;
+  const uint32_t stage_tx = Cfg::A_IMAGES * (GM_A_BYTES + w_bytes);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
 
   if (warp == 0) {
-    if (lane == 0) {
-      uint32_t it = 0;
-      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
-        for (int k = 0; k < n_k; ++k, ++it) {
-          const int pass = k / n_kc, kc = k % n_kc;
-          const int st = it % GM_STAGES; const uint32_t ph = (it / GM_STAGES) & 1;
-          mbar_wait(BAR(4 + st), ph ^ 1);
+    // ===================== producer: the whole warp (gather mode: lane l fetches rows 4l..4l+3 of the tile) =====================
+    const int cpk = gather ? a.g_C / GM_KC : 1;          // k-chunks per tap
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+      const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
+      int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
+      if (gather) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          int r = mt * GM_BM + 4 * lane + i;
+          if (r >= a.R) r = a.R - 1;                     // rows past the end: any valid row (their outputs are masked)
+          const int item = r / a.g_ng, j = r - item * a.g_ng;
+          base[i] = item * 60; tap0[i] = gset_s[j] * 13;
+        }
+      }
+      int k_tap = 0, k_sub = 0;                          // kc = k_tap * cpk + k_sub
+      for (int kc = 0; kc < n_kc; ++kc, ++it) {
+        const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
+        mbar_wait(BAR(4 + st), ph ^ 1);
+        const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
+        if (lane == 0) {
           mbar_expect_tx(BAR(st), stage_tx);
-          uint8_t* sb = smem + st * GM_STAGE_BYTES;
-          // pass 0: A_hi.W_hi   pass 1: A_lo.W_hi   pass 2: A_hi.W_lo
-          tma_load_2d(smem_u32(sb), (pass == 1) ? &mapAlo : &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
-          tma_load_2d(smem_u32(sb + GM_A_BYTES), (pass == 2) ? &mapWlo : &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
+          tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
+          if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
+        }
+        if (gather) {
+          const int c0 = k_sub * GM_KC;
+          const int r0 = base[0] + nei_s[tap0[0] + k_tap], r1 = base[1] + nei_s[tap0[1] + k_tap];
+          const int r2 = base[2] + nei_s[tap0[2] + k_tap], r3 = base[3] + nei_s[tap0[3] + k_tap];
+          tma_gather4(sb + lane * 512, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
+          if (NPASS == 3) tma_gather4(sb + Cfg::OFF_ALO + lane * 512, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
+          if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
+        } else if (lane == 0) {
+          tma_load_2d(sb, &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
+          if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, acols_s[kc], mt * GM_BM, BAR(st));
         }
       }
     }
@@ -97,14 +153,24 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
         mbar_wait(BAR(10 + acc), tph ^ 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * 256;
-        for (int k = 0; k < n_k; ++k, ++it) {
-          const int st = it % GM_STAGES; const uint32_t ph = (it / GM_STAGES) & 1;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(BAR(st), ph);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t sa = smem_u32(smem + st * GM_STAGE_BYTES), sw = sa + GM_A_BYTES;
+          const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          const uint32_t whi = sa + Cfg::OFF_WHI;
 #pragma unroll
-          for (int kk = 0; kk < GM_KC / 8; ++kk)
-            umma_tf32(d_tmem, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(sw + kk * 32), idesc, (k | kk) ? 1u : 0u);
+          for (int kk = 0; kk < GM_KC / 8; ++kk)          // A_hi . W_hi
+            umma_tf32(d_tmem, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(whi + kk * 32), idesc, (kc | kk) ? 1u : 0u);
+          if (NPASS == 3) {
+            const uint32_t alo = sa + Cfg::OFF_ALO, wlo = sa + Cfg::OFF_WLO;
+#pragma unroll
+            for (int kk = 0; kk < GM_KC / 8; ++kk)        // A_lo . W_hi
+              umma_tf32(d_tmem, umma_desc_sw128(alo + kk * 32), umma_desc_sw128(whi + kk * 32), idesc, 1u);
+#pragma unroll
+            for (int kk = 0; kk < GM_KC / 8; ++kk)        // A_hi . W_lo
+              umma_tf32(d_tmem, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(wlo + kk * 32), idesc, 1u);
+          }
           umma_commit(BAR(4 + st));
         }
         umma_commit(BAR(8 + acc));
@@ -194,7 +260,7 @@ static inline int gemm_make_map(roreg_ctx* c, CUtensorMap* m, const float* base,
   }
   const cuuint64_t dims[2] = {(cuuint64_t)kdim, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)kdim * sizeof(float)};
-  const cuuint32_t box[2] = {(cuuint32_t)GM_KC, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)GM_KC, (cuuint32_t)box_rows};      // box_rows = 1: tile::gather4 source (rows chosen per instruction)
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -202,28 +268,41 @@ static inline int gemm_make_map(roreg_ctx* c, CUtensorMap* m, const float* base,
   return ROREG_OK;
 }
 
-// A_hi/A_lo: [R][Kdim]; W_hi/W_lo: [Opad][Kdim] with Opad = n_ntiles*NT rows allocated (rows >= O may be anything finite: masked).
+// A_hi/A_lo: [R][Kdim] - or, in gather mode (a.g_C > 0), the channel-last activation [n_act_rows][g_C];
+// W_hi/W_lo: [Opad][Kdim] with Opad = n_ntiles*NT rows allocated (rows >= O may be anything finite: masked).
 static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A_lo, const float* W_hi, const float* W_lo,
-                                 long long w_rows, GemmArgs a, cudaStream_t st) {
+                                 long long w_rows, GemmArgs a, cudaStream_t st, long long n_act_rows = 0) {
   if (a.R <= 0) return ROREG_OK;
   if (a.Kdim / GM_KC > 256 || a.Kdim % GM_KC || a.NT % 16 || a.NT < 16 || a.NT > 256 || (a.npass != 1 && a.npass != 3) || (a.npass == 3 && (!A_lo || !W_lo))) {
     snprintf(c->err, sizeof(c->err), "gemm_tc_launch: unsupported shape Kdim=%d NT=%d npass=%d", a.Kdim, a.NT, a.npass);
     return ROREG_ERR_UNSUPPORTED;
   }
+  const bool gather = a.g_C > 0;
+  if (gather && (a.g_C % GM_KC || a.Kdim != 13 * a.g_C || a.g_ng < 1 || a.g_ng > 60 || !a.g_nei || a.a_cols || n_act_rows < 60)) {
+    snprintf(c->err, sizeof(c->err), "gemm_tc_launch: unsupported implicit group convolution C=%d Kdim=%d n_g=%d", a.g_C, a.Kdim, a.g_ng);
+    return ROREG_ERR_UNSUPPORTED;
+  }
   CUtensorMap mAh, mAl, mWh, mWl;
   int rc;
-  if ((rc = gemm_make_map(c, &mAh, A_hi, a.R, a.Kdim, GM_BM))) return rc;
-  if ((rc = gemm_make_map(c, &mAl, A_lo ? A_lo : A_hi, a.R, a.Kdim, GM_BM))) return rc;
+  if (gather) {
+    if ((rc = gemm_make_map(c, &mAh, A_hi, n_act_rows, a.g_C, 1))) return rc;
+    if ((rc = gemm_make_map(c, &mAl, A_lo ? A_lo : A_hi, n_act_rows, a.g_C, 1))) return rc;
+  } else {
+    if ((rc = gemm_make_map(c, &mAh, A_hi, a.R, a.Kdim, GM_BM))) return rc;
+    if ((rc = gemm_make_map(c, &mAl, A_lo ? A_lo : A_hi, a.R, a.Kdim, GM_BM))) return rc;
+  }
   if ((rc = gemm_make_map(c, &mWh, W_hi, w_rows, a.Kdim, a.NT))) return rc;
   if ((rc = gemm_make_map(c, &mWl, W_lo ? W_lo : W_hi, w_rows, a.Kdim, a.NT))) return rc;
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GM_SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
   }
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const long long tiles = (long long)n_mt * a.n_ntiles;
   const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
-  gemm_tc_kernel<<<grid, 192, GM_SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  if (a.npass == 3) gemm_tc_kernel<3><<<grid, 192, GemmCfg<3>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  else gemm_tc_kernel<1><<<grid, 192, GemmCfg<1>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

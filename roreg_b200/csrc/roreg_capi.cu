@@ -237,7 +237,11 @@ static int score_and_select(roreg_ctx* c, const MatchView& mv, int cap, const do
     const int hx = (H + 255) / 256;
     const long long items = (long long)hx * tiles * B;
     long long grid = items;
-    if (const char* e = getenv("ROREG_SCORE_CTAS_PER_SM")) { const long long cap = (long long)atoi(e) * c->sm_count; if (cap >= 1 && cap < grid) grid = cap; }
+    // resident CTAs of the persistent scoring kernel: 2 per SM by default (run c1/c2: 24.9 k pairs/s against 24.1 k uncapped
+    // and 24.2 / 24.4 k at 1 / 3 - it leaves room for the pooling kernel that co-runs in the pipelined schedule); 0 = uncapped
+    long long per_sm = 2;
+    if (const char* e = getenv("ROREG_SCORE_CTAS_PER_SM")) per_sm = atoi(e);
+    if (per_sm >= 1 && per_sm * c->sm_count < grid) grid = per_sm * c->sm_count;
     if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     ransac_score_pre_kernel<<<(unsigned)grid, 256, 0, st>>>(sa, hx, items);
   } else ransac_score_kernel<<<dim3((H + 255) / 256, tiles, B), 256, 0, st>>>(sa);
@@ -298,7 +302,7 @@ int roreg_kabsch3(roreg_ctx* c, const double* k0s, const double* k1s, const int3
 }
 
 // ------------------------------------------------------------------------------------------------
-// group-convolution networks (GF / ET / RD): pack, im2col, GEMM, tails
+// group-convolution networks (GF / ET / RD): pack, implicit group-convolution GEMM, dense GEMM, tails
 // ------------------------------------------------------------------------------------------------
 int roreg_pack_descriptors(roreg_ctx* c, int n_src, const float* const* src_host, const int32_t* const* rows_host,
                            const int32_t* permute_host, const int32_t* pre_idx, int n_items, const float* bn_scale,
@@ -317,19 +321,6 @@ int roreg_pack_descriptors(roreg_ctx* c, int n_src, const float* const* src_host
   return ROREG_OK;
 }
 
-int roreg_gconv_im2col(roreg_ctx* c, const float* act_hi, const float* act_lo, int n_items, int C, const int32_t* gset,
-                       int n_gout, float* out_hi, float* out_lo, void* stream) {
-  RR_ARG(c, act_hi && out_hi && n_items >= 0 && C >= 4 && (C % 4) == 0 && n_gout >= 1 && n_gout <= 60);
-  RR_ARG(c, (out_lo == nullptr) || (act_lo != nullptr));
-  if (n_items == 0) return ROREG_OK;
-  const long long total = (long long)n_items * n_gout * 13 * (C / 4);
-  long long blocks = (total + 255) / 256;
-  if (blocks > (long long)c->sm_count * 32) blocks = (long long)c->sm_count * 32;
-  gconv_im2col_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(act_hi, act_lo, n_items, C, c->d_nei, gset, n_gout, out_hi, out_lo);
-  RR_LAUNCH_CHECK(c);
-  return ROREG_OK;
-}
-
 int roreg_gemm(roreg_ctx* c, const float* A_hi, const float* A_lo, int R, int Kdim, const float* W_hi, const float* W_lo,
                int w_rows, int O, int NT, int npass, const float* bias, const float* residual, int res_ld, float* raw_out,
                int raw_ld, float* act_hi, float* act_lo, int act_ld, const float* bn_scale, const float* bn_shift, int relu,
@@ -342,6 +333,23 @@ int roreg_gemm(roreg_ctx* c, const float* A_hi, const float* A_lo, int R, int Kd
   a.act_hi = act_hi; a.act_lo = act_lo; a.act_ld = act_ld; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.relu = relu;
   RR_ARG(c, (bn_scale == nullptr) == (bn_shift == nullptr));
   return gemm_tc_launch(c, A_hi, A_lo, W_hi, W_lo, w_rows, a, (cudaStream_t)stream);
+}
+
+int roreg_gconv_gemm(roreg_ctx* c, const float* act_hi, const float* act_lo, int n_items, int C, const int32_t* gset, int n_gout,
+                     const float* W_hi, const float* W_lo, int w_rows, int O, int NT, int npass, const float* bias,
+                     const float* residual, int res_ld, float* raw_out, int raw_ld, float* out_hi, float* out_lo, int out_ld,
+                     const float* bn_scale, const float* bn_shift, int relu, void* stream) {
+  RR_ARG(c, act_hi && W_hi && n_items >= 0 && C >= 32 && (C % 32) == 0 && n_gout >= 1 && n_gout <= 60 && O >= 1 && NT >= 16 && w_rows >= NT);
+  RR_ARG(c, (raw_out || out_hi) && (long long)n_items * 60 < (1LL << 31));
+  if (n_items == 0) return ROREG_OK;
+  GemmArgs a{};
+  a.R = n_items * n_gout; a.Kdim = 13 * C; a.O = O; a.NT = NT; a.n_ntiles = (O + NT - 1) / NT; a.npass = npass;
+  RR_ARG(c, (long long)a.n_ntiles * NT <= w_rows);
+  a.bias = bias; a.residual = residual; a.res_ld = res_ld; a.raw_out = raw_out; a.raw_ld = raw_ld;
+  a.act_hi = out_hi; a.act_lo = out_lo; a.act_ld = out_ld; a.bn_scale = bn_scale; a.bn_shift = bn_shift; a.relu = relu;
+  RR_ARG(c, (bn_scale == nullptr) == (bn_shift == nullptr));
+  a.g_C = C; a.g_ng = n_gout; a.g_nei = c->d_nei; a.g_set = gset;
+  return gemm_tc_launch(c, act_hi, act_lo, W_hi, W_lo, w_rows, a, (cudaStream_t)stream, (long long)n_items * 60);
 }
 
 int roreg_gf_finalize(roreg_ctx* c, const float* conv_out, const float* x, int n, float* eqv_out, void* stream) {

@@ -2,7 +2,7 @@
 (network/eqv_trans.py:78-138) and the RD detector (network/rot_detect.py:35-55), inference only.
 
 Host side = weight packing (once per checkpoint) and the layer schedule; every FLOP runs in
-libroreg_b200.so (pack / im2col / tcgen05 GEMM with fused bias+residual+BN+ReLU epilogue / tails).
+libroreg_b200.so (pack / implicit group-convolution tcgen05 GEMM with fused bias+residual+BN+ReLU epilogue / tails).
 State-dict key names are the reference checkpoints' (checkpoints/FCGF/{GF,ET,RD}/model_best.pth)."""
 import ctypes as C
 import numpy as np
@@ -35,7 +35,7 @@ class Layer:
         W = np.asarray(W, np.float32)
         O, Cin = W.shape[0], W.shape[1]
         k = W.shape[3] if W.ndim == 4 else 1
-        flat = W.reshape(O, Cin, -1).transpose(0, 2, 1).reshape(O, k * Cin)      # [(k, c)] order of the im2col rows
+        flat = W.reshape(O, Cin, -1).transpose(0, 2, 1).reshape(O, k * Cin)      # [(k, c)] order of the gathered operand rows
         self.O, self.Kdim = O, k * Cin
         self.NT = min(256, -(-O // 16) * 16)
         self.rows = -(-O // self.NT) * self.NT
@@ -69,12 +69,23 @@ class GroupNets:
         _lib.check(self.ctx.h, rc, "roreg_pack_descriptors")
         return hi, lo
 
-    def im2col(self, act, n_items, Cch, gset=None):
+    def gconv(self, act, n_items, Cch, L, gset=None, residual=None, res_ld=0, want_raw=False, bn=None, relu=False, want_act=True):
+        """Group convolution of the channel-last activation `act` = (hi, lo) [n_items*60][Cch] with layer L as an implicit GEMM
+        (roreg_gconv_gemm): rows (item, g) for g in gset (all 60 when None); same epilogue options as gemm()."""
         n_g = 60 if gset is None else int(gset.shape[0])
-        hi = self._buf(n_items * n_g, 13 * Cch); lo = self._buf(n_items * n_g, 13 * Cch) if self.npass == 3 else None
-        rc = self.lib.roreg_gconv_im2col(self.ctx.h, _ptr(act[0]), _ptr(act[1]), n_items, Cch, _ptr(gset), n_g, _ptr(hi), _ptr(lo), _stream())
-        _lib.check(self.ctx.h, rc, "roreg_gconv_im2col")
-        return hi, lo
+        R = n_items * n_g
+        raw = self._buf(R, L.O) if want_raw else None
+        ahi = self._buf(R, L.O) if want_act else None
+        alo = self._buf(R, L.O) if (want_act and self.npass == 3) else None
+        sc = sh = None
+        if bn is not None:
+            sc, sh = self.ctx.dev(bn[0]), self.ctx.dev(bn[1])
+        assert L.Kdim == 13 * Cch
+        rc = self.lib.roreg_gconv_gemm(self.ctx.h, _ptr(act[0]), _ptr(act[1]), n_items, Cch, _ptr(gset), n_g, _ptr(L.hi), _ptr(L.lo), L.rows,
+                                       L.O, L.NT, self.npass, _ptr(L.bias), _ptr(residual), res_ld, _ptr(raw), L.O, _ptr(ahi), _ptr(alo), L.O,
+                                       _ptr(sc), _ptr(sh), int(relu), _stream())
+        _lib.check(self.ctx.h, rc, "roreg_gconv_gemm")
+        return raw, (ahi, alo)
 
     def gemm(self, A, R, L, residual=None, res_ld=0, want_raw=False, bn=None, relu=False, want_act=True):
         raw = self._buf(R, L.O) if want_raw else None
@@ -109,10 +120,10 @@ class GFNet(GroupNets):
         for s in range(0, n, self.chunk):
             xs = x[s:s + self.chunk].contiguous(); m = xs.shape[0]; R = m * 60
             a0 = self.pack([xs], [None], [0], None, m)                                  # Conv_in has no BN/ReLU (group_feat.py:16)
-            raw0, act1 = self.gemm(self.im2col(a0, m, 32), R, self.L_in, want_raw=True, bn=self.bn_a, relu=True)
-            _, act2 = self.gemm(self.im2col(act1, m, 256), R, self.L_a, bn=self.bn_b, relu=True)
-            _, act3 = self.gemm(self.im2col(act2, m, 512), R, self.L_b, residual=raw0, res_ld=256, bn=self.bn_c, relu=True)   # identity shortcut (ops.py:60-63)
-            raw3, _ = self.gemm(self.im2col(act3, m, 256), R, self.L_out, want_raw=True, want_act=False)
+            raw0, act1 = self.gconv(a0, m, 32, self.L_in, want_raw=True, bn=self.bn_a, relu=True)
+            _, act2 = self.gconv(act1, m, 256, self.L_a, bn=self.bn_b, relu=True)
+            _, act3 = self.gconv(act2, m, 512, self.L_b, residual=raw0, res_ld=256, bn=self.bn_c, relu=True)   # identity shortcut (ops.py:60-63)
+            raw3, _ = self.gconv(act3, m, 256, self.L_out, want_raw=True, want_act=False)
             rc = self.lib.roreg_gf_finalize(self.ctx.h, _ptr(raw3), _ptr(xs), m, _ptr(out[s:s + m]), _stream())
             _lib.check(self.ctx.h, rc, "roreg_gf_finalize")
         return out
@@ -144,10 +155,10 @@ class ETNet(GroupNets):
             sl = lambda t: t[s:e].contiguous()
             a0 = self.pack([before0, before1, after0, after1], [sl(rows_b0), sl(rows_b1), sl(rows_a0), sl(rows_a1)], [1, 0, 1, 0],
                            sl(pre_idx), m, bn=self.bn0, relu=True)
-            raw0, act1 = self.gemm(self.im2col(a0, m, 128), m * 60, self.L0, want_raw=True, bn=self.bn_a, relu=True)
-            _, act2 = self.gemm(self.im2col(act1, m, 256, self.g13), m * 13, self.L_a, bn=self.bn_b, relu=True)
-            # rows (item, j) of act2 are the 13 inputs of output g = 0 in tap order: [m, 13*512] IS the im2col row
-            A2 = (act2[0].view(m, 13 * 512), act2[1].view(m, 13 * 512))
+            raw0, act1 = self.gconv(a0, m, 128, self.L0, want_raw=True, bn=self.bn_a, relu=True)
+            _, act2 = self.gconv(act1, m, 256, self.L_a, gset=self.g13, bn=self.bn_b, relu=True)
+            # rows (item, j) of act2 are the 13 inputs of output g = 0 in tap order: [m, 13*512] IS the gathered operand row
+            A2 = (act2[0].view(m, 13 * 512), act2[1].view(m, 13 * 512) if act2[1] is not None else None)
             _, f = self.gemm(A2, m, self.L_b, residual=raw0, res_ld=60 * 256)          # + shortcut at g = 0; FC input is the raw sum
             _, f = self.gemm(f, m, self.F0, bn=self.bnf1, relu=True)
             _, f = self.gemm(f, m, self.F3, bn=self.bnf4, relu=True)
@@ -174,10 +185,10 @@ class RDNet(GroupNets):
         for s in range(0, n, self.chunk):
             xs = x[s:s + self.chunk].contiguous(); m = xs.shape[0]; R = m * 60
             a_sc = self.pack([xs], [None], [0], None, m, bn=self.bn_sc, relu=True)
-            raw_sc, _ = self.gemm(self.im2col(a_sc, m, 32), R, self.L_sc, want_raw=True, want_act=False)
+            raw_sc, _ = self.gconv(a_sc, m, 32, self.L_sc, want_raw=True, want_act=False)
             a_in = self.pack([xs], [None], [0], None, m, bn=self.bn_in, relu=True)
-            _, act1 = self.gemm(self.im2col(a_in, m, 32), R, self.L_in, bn=self.bn_out, relu=True)
-            raw, _ = self.gemm(self.im2col(act1, m, 64), R, self.L_out, residual=raw_sc, res_ld=16, want_raw=True, want_act=False)
+            _, act1 = self.gconv(a_in, m, 32, self.L_in, bn=self.bn_out, relu=True)
+            raw, _ = self.gconv(act1, m, 64, self.L_out, residual=raw_sc, res_ld=16, want_raw=True, want_act=False)
             feat = torch.empty((m, 32, 60), dtype=torch.float32, device=self.ctx.device)
             rc = self.lib.roreg_rd_finalize(self.ctx.h, _ptr(raw), m, _ptr(feat), _stream())
             _lib.check(self.ctx.h, rc, "roreg_rd_finalize")

@@ -17,14 +17,20 @@ class YohooEngine:
         self.ctx, self.max_iter, self.ird, self.nn_mode = ctx, max_iter, ird, nn_mode
         self.et = nets.ETNet(ctx, et_state_dict, npass=npass, chunk=et_chunk)
 
-    def register(self, desc, fcgf, keys, pair_cloud, order=None, seed=0):
+    def register(self, desc, fcgf, keys, pair_cloud, order=None, seed=0, events=None):
         """desc / fcgf [n_clouds,n,32,60] f32 (GF-out / FCGF-in descriptors), keys [n_clouds,n,3] f64, pair_cloud [B,2] int32.
         order (optional) [B,H] int64: hypothesis j of pair b is match order[b,j] (parity tests); default = device shuffle.
+        events (optional list): receives (name, torch.cuda.Event) marks on the current stream after each stage (bench.py).
         Returns the register_batch output dict (poses, recall = index in the scored order, ...)."""
+        def mark(name):
+            if events is not None:
+                e = torch.cuda.Event(enable_timing=True); e.record(); events.append((name, e))
+        mark("start")
         ctx = self.ctx
         n_clouds, n = desc.shape[0], desc.shape[1]
         B = pair_cloud.shape[0]; H = self.max_iter
         out = ctx.register_batch(desc, keys, pair_cloud, max_iter=H, ird=self.ird, nn_mode=self.nn_mode, estimator=2)
+        mark("matcher+des2r")
         K = out["n_matches"].to(torch.int64)                                     # [B]
         S = out["matches"].shape[1]
         if order is None:
@@ -44,10 +50,13 @@ class YohooEngine:
         pre = torch.gather(out["dr_index"].to(torch.int64), 1, order).reshape(-1).to(torch.int32).contiguous()
         d2 = desc.reshape(n_clouds * n, 32, 60); f2 = fcgf.reshape(n_clouds * n, 32, 60)
         # side 0 of the network = cloud id1 (test/estimator.py:293-306)
+        mark("select")
         quat = self.et.forward(f2, row1, f2, row0, d2, row1, d2, row0, pre)
+        mark("et_network")
         k2 = keys.reshape(n_clouds * n, 3)
         k0m = k2.index_select(0, row0.to(torch.int64)).contiguous(); k1m = k2.index_select(0, row1.to(torch.int64)).contiguous()
         hyps = ctx.hypotheses_from_quat(quat, pre, k0m, k1m).reshape(B, H, 3, 4)
         ctx.estimate_batch(out, hyps, n_hyp)
+        mark("hypotheses+ransac+refine")
         out["order"] = order; out["n_hyp"] = n_hyp; out["hyps"] = hyps
         return out

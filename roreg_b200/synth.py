@@ -153,3 +153,76 @@ class SynthScene:
         os.makedirs(d_out, exist_ok=True)
         for cid in self.pc_ids:
             np.save(f"{d_out}/{cid}.npy", self.feats[int(cid)])
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# Random-initialised networks with the parameter names and shapes of the reference's checkpoints (checkpoints/FCGF/{GF,ET,RD,RM}/
+# model_best.pth, key `network_state_dict`): the GPU box has neither the checkpoints nor a network, and BASELINE asks for
+# "random-init weights of that architecture" in the bench.  Layer tables: network/group_feat.py:7-18, network/ops.py:11-63,
+# network/eqv_trans.py:78-101, network/rot_detect.py:35-42, network/rot_coh_match.py:14-32,95-104,123-131,176-186,214-274,323-337.
+def _gconv_block(prefix, cin, mid, cout):
+    """Residual_Comb_Conv: (BN, conv 1x13) x 2 and a (BN, conv) shortcut when the widths differ."""
+    spec = [("bn", f"{prefix}.comb_layer_in.0", cin), ("conv", f"{prefix}.comb_layer_in.2", mid, cin, 13),
+            ("bn", f"{prefix}.comb_layer_out.0", mid), ("conv", f"{prefix}.comb_layer_out.2", cout, mid, 13)]
+    if cin != cout:
+        spec += [("bn", f"{prefix}.short_cut_layer.0", cin), ("conv", f"{prefix}.short_cut_layer.2", cout, cin, 13)]
+    return spec
+
+
+def _mlp2(prefix, cin, mid, cout):
+    spec = [("conv", f"{prefix}.net.0", mid, cin, 1), ("conv", f"{prefix}.net.3", cout, mid, 1)]
+    return spec + ([("conv", f"{prefix}.res", cout, cin, 1)] if cin != cout else [])
+
+
+def _attention(prefix):
+    return [("conv", f"{prefix}.merge", 32, 32, 1)] + [("conv", f"{prefix}.proj.{i}", 32, 32, 1) for i in range(3)]
+
+
+def _network_spec(kind):
+    if kind == "GF":
+        return ([("conv", "PartI_net.Conv_in.0", 256, 32, 13)] + _gconv_block("PartI_net.SO3_Conv_layers.0", 256, 512, 256)
+                + [("bn", "PartI_net.Conv_out.comb_layer.0", 256), ("conv", "PartI_net.Conv_out.comb_layer.2", 32, 256, 13)])
+    if kind == "ET":
+        return ([("bn", "Conv_init.comb_layer.0", 128), ("conv", "Conv_init.comb_layer.2", 256, 128, 13)]
+                + _gconv_block("PartII_SO3_Conv_layers.0", 256, 512, 256)
+                + [("conv", "PartII_To_R_FC.0", 512, 256, 1), ("bn", "PartII_To_R_FC.1", 512), ("conv", "PartII_To_R_FC.3", 128, 512, 1),
+                   ("bn", "PartII_To_R_FC.4", 128), ("conv", "PartII_To_R_FC.6", 4, 128, 1)])
+    if kind == "RD":
+        return _gconv_block("eqv_encoder.0", 32, 64, 16)
+    if kind == "RM":
+        spec = []
+        for b in range(2):
+            for side in ("s2t", "t2s"):
+                q = f"Graph.merge_blocks.{b}.cross_graph_{side}"
+                spec += _attention(q + ".cross_attn") + _mlp2(q + ".merge", 96, 64, 32)
+            for side in ("s", "t"):
+                q = f"Graph.merge_blocks.{b}.self_graph_{side}"
+                spec += (_attention(q + ".self_attn") + _mlp2(q + ".pos_en", 3, 64, 32) + _mlp2(q + ".ambiguity", 120, 128, 32)
+                         + _mlp2(q + ".val_en", 96, 64, 32) + _mlp2(q + ".merge", 96, 64, 32))
+        return spec + _mlp2("final_mlp", 64, 64, 32)
+    raise KeyError(kind)
+
+
+def random_weights(kind, seed):
+    """state-dict-like {name: float32 array} for kind in GF / ET / RD / RM: fan-in-scaled normal weights, small biases, eval-mode
+    BatchNorm statistics near (0, 1).  ET's last layer is biased towards the identity quaternion so that its hypotheses
+    quat2mat(q) @ Rgroup[coarse] land near a synthetic pair's planted pose (a random head never registers anything)."""
+    rng = np.random.default_rng(seed)
+    sd = {}
+    for entry in _network_spec(kind):
+        if entry[0] == "conv":
+            _, name, cout, cin, taps = entry
+            sd[name + ".weight"] = (rng.standard_normal((cout, cin, 1, taps)) / np.sqrt(cin * taps)).astype(np.float32)
+            sd[name + ".bias"] = (0.1 * rng.standard_normal(cout)).astype(np.float32)
+        else:
+            _, name, c = entry
+            sd[name + ".weight"] = (1 + 0.1 * rng.standard_normal(c)).astype(np.float32)
+            sd[name + ".bias"] = (0.1 * rng.standard_normal(c)).astype(np.float32)
+            sd[name + ".running_mean"] = (0.1 * rng.standard_normal(c)).astype(np.float32)
+            sd[name + ".running_var"] = (1 + 0.2 * rng.random(c)).astype(np.float32)
+    if kind == "ET":
+        sd["PartII_To_R_FC.6.weight"] *= np.float32(0.05)
+        sd["PartII_To_R_FC.6.bias"] = (np.array([3.0, 0, 0, 0]) + 0.02 * rng.standard_normal(4)).astype(np.float32)
+    if kind == "RM":
+        sd["ot_layer.bin_score"] = np.array(1.0, np.float32)
+    return sd

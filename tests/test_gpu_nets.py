@@ -1,4 +1,4 @@
-"""Group-convolution networks (tcgen05 GEMM + pack / im2col / tails) against the oracle on seeded random
+"""Group-convolution networks (tcgen05 GEMM with the implicit 13-neighbour gather + pack / tails) against the oracle on seeded random
 weights, and against files the UNMODIFIED reference wrote (tests/golden/s256.npz: gf_eqv_*, det_score_*, trans_pre_*)."""
 import os
 import types
