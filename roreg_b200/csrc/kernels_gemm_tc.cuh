@@ -10,8 +10,8 @@
 // Fused epilogue (one thread per output row, TMEM -> registers):
 //   v = acc + bias[o] (+ residual[r][o]);  raw_out[r][o] = v;  y = v*bn_scale[o] + bn_shift[o];  relu;
 //   act_hi[r][o] = tf32(y), act_lo[r][o] = y - tf32(y)      (the next layer's operands)
-// Pipeline: warp 0 TMA producer (SWIZZLE_128B boxes, or tile::gather4 row gathers for the implicit group convolution),
-// warp 1 MMA issuer, warps 2-5 epilogue; every operand image of a k-chunk is loaded ONCE per stage and all passes run from
+// Pipeline: warps 0-3 TMA producers (SWIZZLE_128B boxes, or tile::gather4 row gathers for the implicit group convolution),
+// warp 4 MMA issuer, warps 5-8 epilogue; every operand image of a k-chunk is loaded ONCE per stage and all passes run from
 // it; two TMEM accumulators of up to 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
 #pragma once
 #include "kernels_nn_tc.cuh"
@@ -63,8 +63,11 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 
+constexpr int GM_PRODUCERS = 4;                          // producer warps 0..3, MMA warp 4, epilogue warps 5..8
+constexpr int GM_THREADS = (GM_PRODUCERS + 1 + 4) * 32;  // 288
+
 template <int NPASS>
-__global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
   using Cfg = GemmCfg<NPASS>;
@@ -90,7 +93,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {
+  if (warp == GM_PRODUCERS) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -106,46 +109,58 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
   const uint32_t stage_tx = Cfg::A_IMAGES * (GM_A_BYTES + w_bytes);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
 
-  if (warp == 0) {
-    // ===================== producer: the whole warp (gather mode: lane l fetches rows 4l..4l+3 of the tile) =====================
+  if (warp < GM_PRODUCERS) {
+    // ===================== producers =====================
+    // Plain mode: lane 0 of warp 0 issues two (four) box loads per stage, the other producer warps have nothing to do.
+    // Gather mode: a tile::gather4 instruction takes its four row coordinates from uniform registers, so the compiler
+    // serialises lanes that hold different rows (ELECT + 6 x R2UR + UTMALDG per lane: run c5 - one warp issuing all 32 gathers
+    // of a stage took ~1300 clk per k-chunk and made GF slower than the im2col version).  The 32 gathers of a stage are
+    // therefore spread over FOUR warps: warp w, lanes 0..7 fetch rows 32 w + 4 l .. + 3 of the tile (8 serialised issues per warp).
     const int cpk = gather ? a.g_C / GM_KC : 1;          // k-chunks per tap
-    uint32_t it = 0;
-    for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-      const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
-      int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
-      if (gather) {
+    if (gather || warp == 0) {
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
+        int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
+        if (gather && lane < 8) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          int r = mt * GM_BM + 4 * lane + i;
-          if (r >= a.R) r = a.R - 1;                     // rows past the end: any valid row (their outputs are masked)
-          const int item = r / a.g_ng, j = r - item * a.g_ng;
-          base[i] = item * 60; tap0[i] = gset_s[j] * 13;
+          for (int i = 0; i < 4; ++i) {
+            int r = mt * GM_BM + 32 * warp + 4 * lane + i;
+            if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
+            const int item = r / a.g_ng, j = r - item * a.g_ng;
+            base[i] = item * 60; tap0[i] = gset_s[j] * 13;
+          }
         }
-      }
-      int k_tap = 0, k_sub = 0;                          // kc = k_tap * cpk + k_sub
-      for (int kc = 0; kc < n_kc; ++kc, ++it) {
-        const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
-        mbar_wait(BAR(4 + st), ph ^ 1);
-        const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
-        if (lane == 0) {
-          mbar_expect_tx(BAR(st), stage_tx);
-          tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
-          if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
-        }
-        if (gather) {
-          const int c0 = k_sub * GM_KC;
-          const int r0 = base[0] + nei_s[tap0[0] + k_tap], r1 = base[1] + nei_s[tap0[1] + k_tap];
-          const int r2 = base[2] + nei_s[tap0[2] + k_tap], r3 = base[3] + nei_s[tap0[3] + k_tap];
-          tma_gather4(sb + lane * 512, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
-          if (NPASS == 3) tma_gather4(sb + Cfg::OFF_ALO + lane * 512, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
-          if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
-        } else if (lane == 0) {
-          tma_load_2d(sb, &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
-          if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, acols_s[kc], mt * GM_BM, BAR(st));
+        int k_tap = 0, k_sub = 0;                        // kc = k_tap * cpk + k_sub
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
+          if (lane == 0) mbar_wait(BAR(4 + st), ph ^ 1);  // one poller per warp
+          __syncwarp();
+          const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          if (warp == 0 && lane == 0) {
+            mbar_expect_tx(BAR(st), stage_tx);
+            tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
+            if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
+            if (!gather) {
+              tma_load_2d(sb, &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
+              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, acols_s[kc], mt * GM_BM, BAR(st));
+            }
+          }
+          if (gather) {
+            if (lane < 8) {
+              const int c0 = k_sub * GM_KC;
+              const int r0 = base[0] + nei_s[tap0[0] + k_tap], r1 = base[1] + nei_s[tap0[1] + k_tap];
+              const int r2 = base[2] + nei_s[tap0[2] + k_tap], r3 = base[3] + nei_s[tap0[3] + k_tap];
+              const uint32_t dst = sb + (warp * 8 + lane) * 512;
+              tma_gather4(dst, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
+              if (NPASS == 3) tma_gather4(dst + Cfg::OFF_ALO, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
+            }
+            if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
+          }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == GM_PRODUCERS) {
     if (lane == 0) {
       uint32_t it = 0, it_t = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it_t) {
@@ -247,7 +262,7 @@ __global__ void __launch_bounds__(192, 1) gemm_tc_kernel(const __grid_constant__
     }
   }
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  if (warp == GM_PRODUCERS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 static inline int gemm_make_map(roreg_ctx* c, CUtensorMap* m, const float* base, long long rows, int kdim, int box_rows) {
@@ -301,8 +316,8 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const long long tiles = (long long)n_mt * a.n_ntiles;
   const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
-  if (a.npass == 3) gemm_tc_kernel<3><<<grid, 192, GemmCfg<3>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
-  else gemm_tc_kernel<1><<<grid, 192, GemmCfg<1>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  if (a.npass == 3) gemm_tc_kernel<3><<<grid, GM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  else gemm_tc_kernel<1><<<grid, GM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

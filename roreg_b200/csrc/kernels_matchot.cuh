@@ -225,6 +225,175 @@ __global__ void __launch_bounds__(1024) sinkhorn_cols_kernel(SinkArgs a) {
   }
 }
 
+// ---- Sinkhorn + final assignment as ONE persistent kernel ------------------------------------------------
+// Round 1 ran the 100 iterations as 200 launches, each streaming S from HBM.  Here the grid is one CTA per SM, launched
+// cooperatively; CTA c OWNS a block of consecutive rows of Z for the whole run:
+//   row pass     u[i] = log_mu - LSE_j(Z[i][j] + v[j]) for its rows (v staged in shared memory);
+//   column pass  for every column j the partial LSE over ITS rows of Z[i][j] + u[i] (its own, just computed u: no global read)
+//                -> part[c][j] = (max, sum); grid barrier; CTA c merges the partials of ITS columns in CTA order -> v[j]; barrier.
+// S (100 MB at 5000 x 5000) is read twice per iteration from L2 - it fits the 126 MB L2 - in the same float32 online
+// max / sum arithmetic as before; per iteration two grid barriers instead of two launches.  The assignment
+// (rot_coh_match.py:369-379) reuses the ownership: row argmax locally, column argmax through the same partial / merge step.
+struct SinkFusedArgs {
+  const float* S; int m, n, ld; float alpha, norm; int iters;
+  float* u; float* v;             // [m+1], [n+1]
+  float2* part;                   // [gridDim.x][n+1] column partials (max, sum) / (best value, row index bits)
+  int32_t* idx0; float* max0; int32_t* idx1; int32_t* matches0; float* mscores0;
+};
+
+__device__ __forceinline__ void sink_grid_sync(unsigned int* bar, unsigned int& gen) {
+  // sense-free generation barrier on a global counter: every CTA is resident (cooperative launch, one CTA per SM)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    ++gen;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned int target = gen * gridDim.x;
+    unsigned int spins = 0;
+    while (*reinterpret_cast<volatile unsigned int*>(bar) < target)
+      if (++spins > (1u << 24)) { printf("roreg: sinkhorn grid barrier timed out (block %d, generation %u)\n", blockIdx.x, gen); __trap(); }   // never hang the GPU
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a, unsigned int* bar) {
+  extern __shared__ float vs[];                         // [n+1] current v (row pass) / v for the assignment
+  __shared__ float us[64];                              // u of the rows this CTA owns
+  __shared__ float rmx[32], rsm[32]; __shared__ int rix[32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int G = gridDim.x, c = blockIdx.x;
+  const int rpc = (a.m + 1 + G - 1) / G;                // rows per CTA (<= 64, checked by the launcher)
+  const int r0 = c * rpc, r1 = min(r0 + rpc, a.m + 1);
+  const int cpc = (a.n + 1 + G - 1) / G;                // columns per CTA in the merge step
+  const int c0 = c * cpc, c1 = min(c0 + cpc, a.n + 1);
+  unsigned int gen = 0;
+  const float log_mu_bin = logf((float)a.n) + a.norm, log_nu_bin = logf((float)a.m) + a.norm;
+  for (int j = tid; j <= a.n; j += 1024) vs[j] = 0.f;  // v = 0 (rot_coh_match.py:302)
+  __syncthreads();
+  for (int it = 0; it < a.iters; ++it) {
+    // ---------------- row pass: 4 rows at a time, 256 threads per row ----------------
+    for (int rb = r0; rb < r1; rb += 4) {
+      const int i = rb + (tid >> 8), p = tid & 255;
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+      if (i < r1) {
+        const float* row = a.S + (long long)i * a.ld;
+        for (int j0 = p; j0 <= a.n; j0 += 1024) {
+          float t[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = j0 + 256 * q;
+            t[q] = -INFINITY;
+            if (j <= a.n) t[q] = ((i < a.m && j < a.n) ? __ldg(row + j) : a.alpha) + vs[j];
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (t[q] > mx[q]) { sm[q] = sm[q] * expf(mx[q] - t[q]) + 1.f; mx[q] = t[q]; }
+            else if (t[q] > -INFINITY) sm[q] += expf(t[q] - mx[q]);
+          }
+        }
+      }
+      lse_merge(mx[0], sm[0], mx[1], sm[1]); lse_merge(mx[2], sm[2], mx[3], sm[3]); lse_merge(mx[0], sm[0], mx[2], sm[2]);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx[0], o), os = __shfl_xor_sync(0xffffffffu, sm[0], o); lse_merge(mx[0], sm[0], om, os); }
+      if (lane == 0) { rmx[warp] = mx[0]; rsm[warp] = sm[0]; }
+      __syncthreads();
+      if (p == 0 && i < r1) {
+        float m0 = rmx[warp], s0 = rsm[warp];
+        for (int w = 1; w < 8; ++w) lse_merge(m0, s0, rmx[warp + w], rsm[warp + w]);
+        const float uu = ((i < a.m) ? a.norm : log_mu_bin) - (m0 + logf(s0));
+        us[i - r0] = uu; a.u[i] = uu;
+      }
+      __syncthreads();
+    }
+    // ---------------- column pass over the rows this CTA owns ----------------
+    for (int j = tid; j <= a.n; j += 1024) {
+      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i0 = r0; i0 < r1; i0 += 4) {
+        float t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int i = i0 + q;
+          t[q] = -INFINITY;
+          if (i < r1) t[q] = ((i < a.m && j < a.n) ? __ldg(a.S + (long long)i * a.ld + j) : a.alpha) + us[i - r0];
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (t[q] > mx[q]) { sm[q] = sm[q] * expf(mx[q] - t[q]) + 1.f; mx[q] = t[q]; }
+          else if (t[q] > -INFINITY) sm[q] += expf(t[q] - mx[q]);
+        }
+      }
+      lse_merge(mx[0], sm[0], mx[1], sm[1]); lse_merge(mx[2], sm[2], mx[3], sm[3]); lse_merge(mx[0], sm[0], mx[2], sm[2]);
+      a.part[(long long)c * (a.n + 1) + j] = make_float2(mx[0], sm[0]);
+    }
+    sink_grid_sync(bar, gen);
+    // ---------------- merge the partials of this CTA's columns (fixed order: lane l takes CTAs l, l+32, ...) ----------------
+    for (int j = c0 + warp; j < c1; j += 32) {
+      float mx = -INFINITY, sm = 0.f;
+      for (int k = lane; k < G; k += 32) { const float2 pr = __ldcg(a.part + (long long)k * (a.n + 1) + j); lse_merge(mx, sm, pr.x, pr.y); }   // written by other SMs: L2 loads
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o); lse_merge(mx, sm, om, os); }
+      if (lane == 0) a.v[j] = ((j < a.n) ? a.norm : log_nu_bin) - (mx + logf(sm));
+    }
+    sink_grid_sync(bar, gen);
+    for (int j = tid; j <= a.n; j += 1024) vs[j] = __ldcg(a.v + j);
+    __syncthreads();
+  }
+  if (a.iters == 0) {                                   // u = v = 0
+    for (int i = r0 + tid; i < r1; i += 1024) { us[i - r0] = 0.f; a.u[i] = 0.f; }
+    for (int j = c0 + tid; j < c1; j += 1024) a.v[j] = 0.f;
+    __syncthreads();
+  }
+  // ---------------- assignment: row argmax (own rows), column argmax partials, merge, mutual check ----------------
+  for (int rb = r0; rb < min(r1, a.m); rb += 4) {
+    const int i = rb + (tid >> 8), p = tid & 255;
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    if (i < min(r1, a.m)) {
+      const float* row = a.S + (long long)i * a.ld; const float ui = us[i - r0];
+      for (int j = p; j < a.n; j += 256) { const float t = __ldg(row + j) + ui + vs[j] - a.norm; if (t > bv) { bv = t; bi = j; } }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float vo = __shfl_xor_sync(0xffffffffu, bv, o); const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (vo > bv || (vo == bv && io < bi)) { bv = vo; bi = io; }
+    }
+    if (lane == 0) { rmx[warp] = bv; rix[warp] = bi; }
+    __syncthreads();
+    if (p == 0 && i < min(r1, a.m)) {
+      float v0 = rmx[warp]; int i0 = rix[warp];
+      for (int w = 1; w < 8; ++w) if (rmx[warp + w] > v0 || (rmx[warp + w] == v0 && rix[warp + w] < i0)) { v0 = rmx[warp + w]; i0 = rix[warp + w]; }
+      a.idx0[i] = i0; a.max0[i] = v0;
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < a.n; j += 1024) {               // first maximal row of this CTA's block (rows ascend, strict >)
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int i = r0; i < min(r1, a.m); ++i) { const float t = __ldg(a.S + (long long)i * a.ld + j) + us[i - r0] + vs[j] - a.norm; if (t > bv) { bv = t; bi = i; } }
+    a.part[(long long)c * (a.n + 1) + j] = make_float2(bv, __int_as_float(bi));
+  }
+  sink_grid_sync(bar, gen);
+  for (int j = c0 + warp; j < min(c1, a.n); j += 32) {
+    float bv = -INFINITY; int bi = 0x7fffffff;
+    for (int k = lane; k < G; k += 32) {
+      const float2 pr = __ldcg(a.part + (long long)k * (a.n + 1) + j); const int ri = __float_as_int(pr.y);
+      if (pr.x > bv || (pr.x == bv && ri < bi)) { bv = pr.x; bi = ri; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float vo = __shfl_xor_sync(0xffffffffu, bv, o); const int io = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (vo > bv || (vo == bv && io < bi)) { bv = vo; bi = io; }
+    }
+    if (lane == 0) a.idx1[j] = bi;
+  }
+  sink_grid_sync(bar, gen);
+  for (int i = r0 + tid; i < min(r1, a.m); i += 1024) {  // matches0 / matching_scores0 (rot_coh_match.py:371-378)
+    const int j = a.idx0[i];
+    const bool mutual = (__ldcg(a.idx1 + j) == i);
+    a.matches0[i] = mutual ? j : -1;
+    a.mscores0[i] = mutual ? expf(a.max0[i]) : 0.f;
+  }
+}
+
 // final assignment (rot_coh_match.py:369-379): row / column argmax of Z + u + v - norm on the inner [m][n] block
 __global__ void __launch_bounds__(256) ot_row_argmax_kernel(SinkArgs a, int32_t* __restrict__ idx0, float* __restrict__ max0) {
   __shared__ float sv[8]; __shared__ int si[8];

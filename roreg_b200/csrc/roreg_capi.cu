@@ -508,10 +508,28 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
                          int32_t* matches0, float* mscores0, void* stream) {
   RR_ARG(c, S && u && v && matches0 && mscores0 && m >= 1 && n >= 1 && ld >= n && iters >= 0);
   cudaStream_t st = (cudaStream_t)stream;
-  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * m) + rr_align(sizeof(float) * m) + rr_align(sizeof(int32_t) * n) + 4096);
+  const int G = c->sm_count;
+  const bool fused = ((m + G) / G <= 64) && ((size_t)(n + 1) * sizeof(float) <= 200 * 1024) && !getenv("ROREG_SINKHORN_LAUNCHES");
+  int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * m) + rr_align(sizeof(float) * m) + rr_align(sizeof(int32_t) * n) +
+                            (fused ? rr_align(sizeof(float2) * (size_t)G * (n + 1)) + rr_align(256) : 0) + 4096);
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
   int32_t* idx0 = ar.take<int32_t>(m); float* max0 = ar.take<float>(m); int32_t* idx1 = ar.take<int32_t>(n);
+  if (fused) {
+    // one persistent cooperative kernel: 100 iterations + the assignment (kernels_matchot.cuh, sinkhorn_fused_kernel)
+    float2* part = ar.take<float2>((size_t)G * (n + 1));
+    unsigned int* bar = ar.take<unsigned int>(64);
+    RR_CUDA(c, cudaMemsetAsync(bar, 0, 256, st));
+    SinkFusedArgs fa{S, m, n, ld, alpha, -logf((float)(m + n)), iters, u, v, part, idx0, max0, idx1, matches0, mscores0};
+    const size_t smem = (size_t)(n + 1) * sizeof(float);
+    static unsigned long long attr_mask = 0;
+    if (rr_first_use_on_device(&attr_mask, c->device))
+      RR_CUDA(c, cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    void* args[] = {&fa, &bar};
+    RR_CUDA(c, cudaLaunchCooperativeKernel((const void*)sinkhorn_fused_kernel, dim3(G), dim3(1024), args, smem, st));
+    c->launches += 1;
+    return ROREG_OK;
+  }
   RR_CUDA(c, cudaMemsetAsync(u, 0, sizeof(float) * (m + 1), st));
   RR_CUDA(c, cudaMemsetAsync(v, 0, sizeof(float) * (n + 1), st));
   SinkArgs a{S, m, n, ld, alpha, -logf((float)(m + n)), u, v};

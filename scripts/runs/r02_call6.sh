@@ -1,0 +1,37 @@
+#!/bin/bash
+# Round 2, GPU call 6: four producer warps for the gather GEMM; persistent cooperative Sinkhorn + assignment kernel.
+set -x
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests/test_gpu_nets.py tests/test_gpu_matchot.py -x -q -m gpu > gpurun_out/c6_pytest_nets.txt 2>&1
+tail -6 gpurun_out/c6_pytest_nets.txt
+timeout 900 python scripts/time_nets.py > gpurun_out/c6_nets_timing.txt 2> gpurun_out/c6_nets_timing.err; cat gpurun_out/c6_nets_timing.txt; tail -3 gpurun_out/c6_nets_timing.err
+ROREG_SINKHORN_LAUNCHES=1 timeout 300 python - > gpurun_out/c6_matchot_old_sinkhorn.txt 2>&1 <<'PY'
+import sys, numpy as np, torch
+sys.path.insert(0, ".")
+from roreg_b200 import ops, synth, matchot
+ctx = ops.Context(0)
+pr = synth.make_pair(2, n=5000)
+f0 = ctx.dev(pr["feats0"]); f1 = ctx.dev(pr["feats1"]); k0 = ctx.dev(pr["keys0"].astype(np.float32)); k1 = ctx.dev(pr["keys1"].astype(np.float32))
+mo = matchot.MatchOT(ctx, synth.random_weights("RM", 104), npass=1)
+mo.forward(f1, f0, k1, k0); torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+l0 = ctx.launches; e0.record(); m0, s0 = mo.forward(f1, f0, k1, k0); e1.record(); torch.cuda.synchronize()
+print("Match_ot with the 200-launch Sinkhorn:", e0.elapsed_time(e1), "ms", ctx.launches - l0, "launches", int((m0 >= 0).sum()))
+PY
+cat gpurun_out/c6_matchot_old_sinkhorn.txt
+# launch list of the networks (per-kernel durations)
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/c6_nets_launches.csv python scripts/time_nets.py > /dev/null 2>&1
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(open("gpurun_out/c6_nets_launches.csv")))
+hdr = [i for i, r in enumerate(rows) if r and r[0] == "ID"]
+agg = collections.OrderedDict()
+if hdr:
+    h = rows[hdr[0]]; kn = h.index("Kernel Name"); mv = h.index("Metric Value")
+    for r in rows[hdr[0] + 1:]:
+        if len(r) > mv:
+            try: v = float(r[mv].replace(",", ""))
+            except ValueError: continue
+            a = agg.setdefault(r[kn][:60], [0, 0.0]); a[0] += 1; a[1] += v
+    for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]: print(f"{t/1e3:10.1f} us total {n:5d} launches {t/n/1e3:9.1f} us avg  {k}")
+PY
