@@ -15,11 +15,16 @@
 //     cute/atom/mma_traits_sm100.hpp, Major-MN / SWIZZLE_128B, in 16-byte units ((8,n),(8,k)):((1,LBO),(8,SBO))):
 //     8 f-rows x 128 B (64 h) atoms, chunk16 ^= f % 8, SBO = 1024 B between 8-f groups, LBO = 4096 B between the two
 //     matches stacked along M (resp. N).
-// Shared-memory traffic per match: 16 KB (operand writes) + 24 KB (MMA reads) + 30 KB (Gram transpose) = 70 KB.
+// Shared-memory traffic per match: 16 KB (operand writes) + 24 KB (MMA reads) + 30 KB (Gram store + diagonal reads) = 70 KB.
+// Round 2 (runs c2-c4): the Gram is stored ROW-wise with its columns at coset slots so that both the stores and the table-
+// addressed diagonal reads are bank-conflict-free (round 1: 2.3 wavefronts per read); the read table lives in shared memory
+// (ptxas had spilled 40 pre-extracted offsets: 40 local loads per item on the epilogue's critical chain); the item walk goes
+// pair by pair without per-item count loads.  0.975 -> 0.835 ms per 64 pairs; the kernel is now l1tex-pipe bound (73 %).
 //
 //   warps 0-10   loaders    a pool over the row tasks {X m0, X m1, Y m0, Y m1} of every item: LDG row -> regs -> fp16 hi / lo' -> STS.64
 //   warp 11      MMA        6 x tcgen05.mma kind::f16 (M = N = 128, K = 16, A/B MN-major), 2 x (D1 | D2) in TMEM
-//   warps 12-19  epilogue   (two sets of 4 warps alternating over the items)  tcgen05.ld D1, D2 -> FFMA combine -> smem transpose -> 60 generalised-diagonal sums -> argmax
+//   warps 12-19  epilogue   (two sets of 4 warps alternating over the items)  tcgen05.ld D1, D2 -> FFMA combine -> row-wise 16-byte stores
+//                           at the coset slots of icosa_cosets.cuh -> 60 conflict-free loads per generalised diagonal -> argmax
 #pragma once
 #include <cuda_fp16.h>
 #include "kernels_corr_tc.cuh"
@@ -30,7 +35,8 @@ namespace roreg {
 
 constexpr int C3_GROUPS = 3;                              // operand-tile sets (items in flight between the loaders and the tensor pipe)
 // Warp roles are template parameters: LOADERS loader warps (a pool that takes the (item, row) tasks round-robin), one MMA warp,
-// ESETS epilogue sets of 4 warps.  Default <11, 2> = 640 threads; <11, 3> = 768 threads adds a third epilogue set at 80 registers per thread (registers are allocated per 4 warps: 21-24 warps cost the same).
+// ESETS epilogue sets of 4 warps.  Instantiated: <11, 2> = 640 threads, 96 registers per thread.  (<11, 3> = 768 threads leaves 80
+// registers per thread - registers are allocated per 4 warps, 21-24 warps cost the same - and ran slower, see the launcher.)
 __host__ __device__ constexpr int c3_threads(int loaders, int esets) { return (loaders + 1 + 4 * esets) * 32; }
 constexpr int C3_OP_BYTES = 32 * 128;                     // one match's operand tile: 32 f-rows x 64 h fp16 = 4 KB
 constexpr int C3_BUF_BYTES = 8 * C3_OP_BYTES;             // Xhi m0|m1, Xlo m0|m1, Yhi m0|m1, Ylo m0|m1 = 32 KB
@@ -336,15 +342,13 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
   const bool v2 = (a.tab == c->d_permT8);               // variant 2 (R-indicator convention): its own coset layout
   RR_ARG(c, (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(Y) & 15) == 0);
   a.X = X; a.Y = Y; a.trace = nullptr;
-  static int sets = 0;                                   // role layout: ROREG_CORR_SETS=3 -> <11 loaders, 3 epilogue sets>, default <11, 2>
-  if (!sets) { const char* e = getenv("ROREG_CORR_SETS"); sets = (e && atoi(e) == 3) ? 3 : 2; }
+  // role layout <11 loaders, 2 epilogue sets>.  A third epilogue set (<11, 3>, 768 threads) was measured in run c4: 80 registers
+  // per thread force spills in the loaders and the epilogue, Des2R 1.07 ms against 0.835 ms - not instantiated.
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
     RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<true, 1, 11, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(2)));
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 1, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(3)));
-    RR_CUDA(c, cudaFuncSetAttribute(group_corr_tc3_kernel<false, 2, 11, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, c3_smem_bytes(3)));
   }
   const long long items = (long long)a.B * ((a.K + 1) / 2);
   RR_ARG(c, items < (1LL << 31));
@@ -374,13 +378,8 @@ static inline int group_corr_tc3_launch(roreg_ctx* c, const float* X, const floa
     free(h); cudaFree(a.trace);
     return ROREG_OK;
   }
-  if (sets == 3) {
-    if (v2) group_corr_tc3_kernel<false, 2, 11, 3><<<grid, c3_threads(11, 3), c3_smem_bytes(3), st>>>(a);
-    else group_corr_tc3_kernel<false, 1, 11, 3><<<grid, c3_threads(11, 3), c3_smem_bytes(3), st>>>(a);
-  } else {
-    if (v2) group_corr_tc3_kernel<false, 2, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
-    else group_corr_tc3_kernel<false, 1, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
-  }
+  if (v2) group_corr_tc3_kernel<false, 2, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
+  else group_corr_tc3_kernel<false, 1, 11, 2><<<grid, c3_threads(11, 2), c3_smem_bytes(2), st>>>(a);
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

@@ -69,7 +69,14 @@ __global__ void __launch_bounds__(256) chan_stats_kernel(const float* __restrict
   for (long long r = (long long)blockIdx.x * rpb + rl; r < P; r += (long long)gridDim.x * rpb) {
     const double v = x[r * C + c]; s += v; ss += v * v;
   }
-  atomicAdd(&acc[2 * c], s); atomicAdd(&acc[2 * c + 1], ss);
+  // one atomic pair per channel and CTA (run c6: 256 contended double atomics per CTA made this 85 us per call)
+  __shared__ double sh[256][2];
+  sh[threadIdx.x][0] = s; sh[threadIdx.x][1] = ss;
+  __syncthreads();
+  if (rl == 0) {
+    for (int k = 1; k < rpb; ++k) { s += sh[k * C + c][0]; ss += sh[k * C + c][1]; }
+    atomicAdd(&acc[2 * c], s); atomicAdd(&acc[2 * c + 1], ss);
+  }
 }
 __global__ void chan_stats_finish_kernel(const double* __restrict__ acc, long long P, int C, float* __restrict__ mean, float* __restrict__ rstd) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -234,6 +241,17 @@ __global__ void __launch_bounds__(1024) sinkhorn_cols_kernel(SinkArgs a) {
 // S (100 MB at 5000 x 5000) is read twice per iteration from L2 - it fits the 126 MB L2 - in the same float32 online
 // max / sum arithmetic as before; per iteration two grid barriers instead of two launches.  The assignment
 // (rot_coh_match.py:369-379) reuses the ownership: row argmax locally, column argmax through the same partial / merge step.
+// Four more terms of an online logsumexp, branch-free: one rescale of the running sum per group and ex2.approx exponentials
+// (run c6: with expf and a data-dependent branch per element the passes were ARITHMETIC-bound - 97 us per pass, whether launched
+// 200 times or run from one persistent kernel; 5 MUFU per 4 elements put a pass at the L2 streaming time instead).
+__device__ __forceinline__ void lse_acc4(float& mx, float& sm, const float (&t)[4]) {
+  const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+  if (m4 == -INFINITY) return;
+  const float nm = fmaxf(mx, m4);
+  sm = sm * __expf(mx - nm) + ((__expf(t[0] - nm) + __expf(t[1] - nm)) + (__expf(t[2] - nm) + __expf(t[3] - nm)));
+  mx = nm;
+}
+
 struct SinkFusedArgs {
   const float* S; int m, n, ld; float alpha, norm; int iters;
   float* u; float* v;             // [m+1], [n+1]
@@ -275,7 +293,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
     // ---------------- row pass: 4 rows at a time, 256 threads per row ----------------
     for (int rb = r0; rb < r1; rb += 4) {
       const int i = rb + (tid >> 8), p = tid & 255;
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+      float mx = -INFINITY, sm = 0.f;
       if (i < r1) {
         const float* row = a.S + (long long)i * a.ld;
         for (int j0 = p; j0 <= a.n; j0 += 1024) {
@@ -286,17 +304,12 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
             t[q] = -INFINITY;
             if (j <= a.n) t[q] = ((i < a.m && j < a.n) ? __ldg(row + j) : a.alpha) + vs[j];
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (t[q] > mx[q]) { sm[q] = sm[q] * expf(mx[q] - t[q]) + 1.f; mx[q] = t[q]; }
-            else if (t[q] > -INFINITY) sm[q] += expf(t[q] - mx[q]);
-          }
+          lse_acc4(mx, sm, t);
         }
       }
-      lse_merge(mx[0], sm[0], mx[1], sm[1]); lse_merge(mx[2], sm[2], mx[3], sm[3]); lse_merge(mx[0], sm[0], mx[2], sm[2]);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx[0], o), os = __shfl_xor_sync(0xffffffffu, sm[0], o); lse_merge(mx[0], sm[0], om, os); }
-      if (lane == 0) { rmx[warp] = mx[0]; rsm[warp] = sm[0]; }
+      for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o); lse_merge(mx, sm, om, os); }
+      if (lane == 0) { rmx[warp] = mx; rsm[warp] = sm; }
       __syncthreads();
       if (p == 0 && i < r1) {
         float m0 = rmx[warp], s0 = rsm[warp];
@@ -308,7 +321,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
     }
     // ---------------- column pass over the rows this CTA owns ----------------
     for (int j = tid; j <= a.n; j += 1024) {
-      float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY}, sm[4] = {0.f, 0.f, 0.f, 0.f};
+      float mx = -INFINITY, sm = 0.f;
       for (int i0 = r0; i0 < r1; i0 += 4) {
         float t[4];
 #pragma unroll
@@ -317,14 +330,9 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
           t[q] = -INFINITY;
           if (i < r1) t[q] = ((i < a.m && j < a.n) ? __ldg(a.S + (long long)i * a.ld + j) : a.alpha) + us[i - r0];
         }
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          if (t[q] > mx[q]) { sm[q] = sm[q] * expf(mx[q] - t[q]) + 1.f; mx[q] = t[q]; }
-          else if (t[q] > -INFINITY) sm[q] += expf(t[q] - mx[q]);
-        }
+        lse_acc4(mx, sm, t);
       }
-      lse_merge(mx[0], sm[0], mx[1], sm[1]); lse_merge(mx[2], sm[2], mx[3], sm[3]); lse_merge(mx[0], sm[0], mx[2], sm[2]);
-      a.part[(long long)c * (a.n + 1) + j] = make_float2(mx[0], sm[0]);
+      a.part[(long long)c * (a.n + 1) + j] = make_float2(mx, sm);
     }
     sink_grid_sync(bar, gen);
     // ---------------- merge the partials of this CTA's columns (fixed order: lane l takes CTAs l, l+32, ...) ----------------
