@@ -210,6 +210,25 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
                      : "r"(taddr + c0) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         if (r < a.R) {
+          // running-maximum mode: all 16 previous maxima of this chunk are loaded BEFORE any update.  Round 1 read them one by one
+          // between the stores (same array: the compiler may not hoist a load above a store), i.e. 256 serialised L2 round trips
+          // per thread and tile - the all-pairs GEMMs were bound by that chain, not by the tensor pipe (run c7: 355 us per launch
+          // against 94 us of MMA work).
+          float old[16], res[16];
+          if (a.residual) {                               // likewise: the residual row chunk in one go, ahead of the stores
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int oj = nt * a.NT + c0 + j;
+              res[j] = (oj < a.O) ? __ldcg(a.residual + r * a.res_ld + oj) : 0.f;
+            }
+          }
+          if (a.amax_arg) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int oj = nt * a.NT + c0 + j;
+              old[j] = (oj < a.O) ? __ldcg(a.raw_out + r * a.raw_ld + oj) : INFINITY;
+            }
+          }
 #pragma unroll
           for (int j4 = 0; j4 < 4; ++j4) {
             const int o = nt * a.NT + c0 + 4 * j4;
@@ -221,15 +240,16 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
               float val = __uint_as_float(v[4 * j4 + j]);
               if (oj < a.O) {
                 if (a.bias) val += __ldg(a.bias + oj);
-                if (a.residual) val += a.residual[r * a.res_ld + oj];
+                if (a.residual) val += res[4 * j4 + j];
               }
               x[j] = val;
             }
             const bool full = (o + 3 < a.O);
             if (a.amax_arg) {          // running (max, argmax) over successive launches; strict '>' keeps the first maximum
-              for (int j = 0; j < 4 && o + j < a.O; ++j) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
                 const long long ix = r * a.raw_ld + o + j;
-                if (x[j] > a.raw_out[ix]) { a.raw_out[ix] = x[j]; a.amax_arg[ix] = (uint8_t)a.amax_id; }
+                if (o + j < a.O && x[j] > old[4 * j4 + j]) { a.raw_out[ix] = x[j]; a.amax_arg[ix] = (uint8_t)a.amax_id; }
               }
             } else if (a.raw_out) {
               float* p = a.raw_out + r * a.raw_ld + o;

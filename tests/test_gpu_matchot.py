@@ -123,7 +123,7 @@ def test_match_ot_forward_against_oracle_larger(ctx, tables, capsys):
     _adjudicate_forward(ctx, tables, 59, 1100, capsys)
 
 
-def test_yoho_mat_plugin_reproduces_reference_files(tmp_path):
+def test_yoho_mat_plugin_reproduces_reference_files(tmp_path, capsys):
     import roreg_b200.test as rt
     z, n, keynum, _, seeds = load_golden("rm300")
     ds = synth.SynthDataset(seeds, n=n, name="synth/rm", with_fcgf=False)
@@ -139,6 +139,15 @@ def test_yoho_mat_plugin_reproduces_reference_files(tmp_path):
         m = np.load(f"{cache}/synth/rm/match_{keynum}/{id0}-{id1}.npy"); s = np.load(f"{cache}/synth/rm/match_{keynum}/scores/{id0}-{id1}.npy")
         ref = z[f"match_{id0}-{id1}"]
         a = {tuple(r) for r in m.tolist()}; b = {tuple(r) for r in ref.tolist()}
+        with capsys.disabled():
+            print(f"\n[yoho_mat vs reference file {id0}-{id1}] {len(b)} reference matches, {len(a ^ b)} in the symmetric difference")
+        # The reference file comes from torch on the CPU, the plugin from the 3xTF32 GEMMs: a neighbour list decided inside the
+        # float32 near-tie band (test_match_ot_forward_against_oracle counts them: 0-2 rows of 8 n) changes that row's features and
+        # with them a handful of assignments.  The teacher-forced test above is the exact one; here the bound is a few matches.
         assert len(a ^ b) <= max(2, len(b) // 50), (len(a), len(b), len(a ^ b))
-        if np.array_equal(m, ref):
-            assert np.abs(s - z[f"scores_{id0}-{id1}"]).max() < 1e-3
+        common = sorted(a & b)
+        if common:
+            ia = {tuple(r): i for i, r in enumerate(m.tolist())}; ib = {tuple(r): i for i, r in enumerate(ref.tolist())}
+            sa = np.array([s[ia[r]] for r in common]); sb = np.array([z[f"scores_{id0}-{id1}"][ib[r]] for r in common])
+            if len(a ^ b) == 0:
+                assert np.abs(sa - sb).max() < 1e-3
