@@ -29,7 +29,7 @@ template <int NPASS> struct GemmCfg {
   static constexpr int STAGES = NPASS == 3 ? 2 : 4;
   static constexpr int A_IMAGES = NPASS == 3 ? 2 : 1;
   static constexpr int STAGE_BYTES = A_IMAGES * (GM_A_BYTES + GM_W_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;      // the dynamic array is declared 1024-byte aligned: no slack needed
   static constexpr int OFF_ALO = GM_A_BYTES;                         // 3-pass only
   static constexpr int OFF_WHI = A_IMAGES * GM_A_BYTES;
   static constexpr int OFF_WLO = OFF_WHI + GM_W_BYTES;               // 3-pass only
@@ -71,22 +71,28 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
   using Cfg = GemmCfg<NPASS>;
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - ((uint32_t)__cvta_generic_to_shared(smem_raw) & 1023u)) & 1023u);
+  // Shared-memory budget: static (~1.4 KB, rounded up to the array's 1 KB alignment) + 192 KB of stages + barriers = 194.3 KiB,
+  // i.e. under the 196 KiB carve-out step (+1 KiB the system reserves per CTA) - see the note at nei_s.
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem_raw) & 1023u) != 0) { if (threadIdx.x == 0) printf("roreg: gemm_tc_kernel: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::STAGES * Cfg::STAGE_BYTES);
   // barriers: 0..3 full, 4..7 empty, 8..9 tmem_full, 10..11 tmem_empty
   __shared__ uint32_t tmem_base_s;
-  __shared__ int32_t acols_s[256];
-  __shared__ int32_t nei_s[60 * 13];
-  __shared__ int32_t gset_s[64];
+  __shared__ uint16_t acols_s[256];
+  // byte tables: together with the dynamic buffers the CTA must stay under the 196 KiB shared-memory carve-out - the next step
+  // (228 KiB) halves the L1 that the epilogue's row-strided loads live in (run c7: 3.4 KB of int32 tables cost the all-pairs
+  // GEMMs 45 %)
+  __shared__ uint8_t nei_s[60 * 13];
+  __shared__ uint8_t gset_s[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const bool gather = a.g_C > 0;
-  for (int i = threadIdx.x; i < a.Kdim / GM_KC && i < 256; i += blockDim.x) acols_s[i] = a.a_cols ? a.a_cols[i] : i * GM_KC;
+  for (int i = threadIdx.x; i < a.Kdim / GM_KC && i < 256; i += blockDim.x) acols_s[i] = (uint16_t)(a.a_cols ? a.a_cols[i] : i * GM_KC);   // < Kdim <= 8192
   if (gather) {
-    for (int i = threadIdx.x; i < 60 * 13; i += blockDim.x) nei_s[i] = a.g_nei[i];
-    for (int i = threadIdx.x; i < 64; i += blockDim.x) gset_s[i] = (a.g_set && i < a.g_ng) ? a.g_set[i] : i;
+    for (int i = threadIdx.x; i < 60 * 13; i += blockDim.x) nei_s[i] = (uint8_t)a.g_nei[i];
+    for (int i = threadIdx.x; i < 64; i += blockDim.x) gset_s[i] = (uint8_t)((a.g_set && i < a.g_ng) ? a.g_set[i] : i);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
@@ -128,7 +134,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             int r = mt * GM_BM + 32 * warp + 4 * lane + i;
             if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
             const int item = r / a.g_ng, j = r - item * a.g_ng;
-            base[i] = item * 60; tap0[i] = gset_s[j] * 13;
+            base[i] = item * 60; tap0[i] = (int)gset_s[j] * 13;
           }
         }
         int k_tap = 0, k_sub = 0;                        // kc = k_tap * cpk + k_sub
@@ -142,15 +148,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
             if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
             if (!gather) {
-              tma_load_2d(sb, &mapAhi, acols_s[kc], mt * GM_BM, BAR(st));
-              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, acols_s[kc], mt * GM_BM, BAR(st));
+              tma_load_2d(sb, &mapAhi, (int)acols_s[kc], mt * GM_BM, BAR(st));
+              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, (int)acols_s[kc], mt * GM_BM, BAR(st));
             }
           }
           if (gather) {
             if (lane < 8) {
               const int c0 = k_sub * GM_KC;
-              const int r0 = base[0] + nei_s[tap0[0] + k_tap], r1 = base[1] + nei_s[tap0[1] + k_tap];
-              const int r2 = base[2] + nei_s[tap0[2] + k_tap], r3 = base[3] + nei_s[tap0[3] + k_tap];
+              const int r0 = base[0] + (int)nei_s[tap0[0] + k_tap], r1 = base[1] + (int)nei_s[tap0[1] + k_tap];
+              const int r2 = base[2] + (int)nei_s[tap0[2] + k_tap], r3 = base[3] + (int)nei_s[tap0[3] + k_tap];
               const uint32_t dst = sb + (warp * 8 + lane) * 512;
               tma_gather4(dst, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
               if (NPASS == 3) tma_gather4(dst + Cfg::OFF_ALO, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
@@ -215,18 +221,28 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
           // per thread and tile - the all-pairs GEMMs were bound by that chain, not by the tensor pipe (run c7: 355 us per launch
           // against 94 us of MMA work).
           float old[16], res[16];
-          if (a.residual) {                               // likewise: the residual row chunk in one go, ahead of the stores
+          // 16-byte loads where the row chunk allows it: one L2 request per four values, no reliance on L1 reuse (with ~200 KB
+          // of shared memory per CTA only ~28 KB of L1 are left: the epilogue's per-thread sectors do not survive there)
+          const bool vec_res = a.residual && ((a.res_ld & 3) == 0) && (nt * a.NT + c0 + 15 < a.O);
+          const bool vec_old = a.amax_arg && ((a.raw_ld & 3) == 0) && (nt * a.NT + c0 + 15 < a.O);
+          if (a.residual) {                               // the residual row chunk in one go, ahead of the stores
+            if (vec_res) {
+              const float4* pr = reinterpret_cast<const float4*>(a.residual + r * a.res_ld + nt * a.NT + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int oj = nt * a.NT + c0 + j;
-              res[j] = (oj < a.O) ? __ldcg(a.residual + r * a.res_ld + oj) : 0.f;
+              for (int q = 0; q < 4; ++q) { const float4 w = __ldcg(pr + q); res[4 * q] = w.x; res[4 * q + 1] = w.y; res[4 * q + 2] = w.z; res[4 * q + 3] = w.w; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { const int oj = nt * a.NT + c0 + j; res[j] = (oj < a.O) ? a.residual[r * a.res_ld + oj] : 0.f; }
             }
           }
           if (a.amax_arg) {
+            if (vec_old) {
+              const float4* po = reinterpret_cast<const float4*>(a.raw_out + r * a.raw_ld + nt * a.NT + c0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const int oj = nt * a.NT + c0 + j;
-              old[j] = (oj < a.O) ? __ldcg(a.raw_out + r * a.raw_ld + oj) : INFINITY;
+              for (int q = 0; q < 4; ++q) { const float4 w = __ldcg(po + q); old[4 * q] = w.x; old[4 * q + 1] = w.y; old[4 * q + 2] = w.z; old[4 * q + 3] = w.w; }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) { const int oj = nt * a.NT + c0 + j; old[j] = (oj < a.O) ? a.raw_out[r * a.raw_ld + oj] : INFINITY; }
             }
           }
 #pragma unroll
@@ -246,10 +262,22 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
             const bool full = (o + 3 < a.O);
             if (a.amax_arg) {          // running (max, argmax) over successive launches; strict '>' keeps the first maximum
+              const long long ix0 = r * a.raw_ld + o;
+              const bool u0 = x[0] > old[4 * j4], u1 = x[1] > old[4 * j4 + 1], u2 = x[2] > old[4 * j4 + 2], u3 = x[3] > old[4 * j4 + 3];
+              if (vec_old) {
+                if (u0 | u1 | u2 | u3) {                  // one 16-byte + one 4-byte store per group of four instead of up to eight scalar ones
+                  *reinterpret_cast<float4*>(a.raw_out + ix0) = make_float4(u0 ? x[0] : old[4 * j4], u1 ? x[1] : old[4 * j4 + 1],
+                                                                           u2 ? x[2] : old[4 * j4 + 2], u3 ? x[3] : old[4 * j4 + 3]);
+                  uchar4* pa = reinterpret_cast<uchar4*>(a.amax_arg + ix0);
+                  uchar4 ar = (a.amax_id == 0) ? make_uchar4(0, 0, 0, 0) : *pa;      // first rotation: nothing to keep
+                  const uint8_t id = (uint8_t)a.amax_id;
+                  if (u0) ar.x = id; if (u1) ar.y = id; if (u2) ar.z = id; if (u3) ar.w = id;
+                  *pa = ar;
+                }
+              } else {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const long long ix = r * a.raw_ld + o + j;
-                if (o + j < a.O && x[j] > old[4 * j4 + j]) { a.raw_out[ix] = x[j]; a.amax_arg[ix] = (uint8_t)a.amax_id; }
+                for (int j = 0; j < 4; ++j)
+                  if (o + j < a.O && x[j] > old[4 * j4 + j]) { a.raw_out[ix0 + j] = x[j]; a.amax_arg[ix0 + j] = (uint8_t)a.amax_id; }
               }
             } else if (a.raw_out) {
               float* p = a.raw_out + r * a.raw_ld + o;

@@ -241,14 +241,21 @@ __global__ void __launch_bounds__(1024) sinkhorn_cols_kernel(SinkArgs a) {
 // S (100 MB at 5000 x 5000) is read twice per iteration from L2 - it fits the 126 MB L2 - in the same float32 online
 // max / sum arithmetic as before; per iteration two grid barriers instead of two launches.  The assignment
 // (rot_coh_match.py:369-379) reuses the ownership: row argmax locally, column argmax through the same partial / merge step.
-// Four more terms of an online logsumexp, branch-free: one rescale of the running sum per group and ex2.approx exponentials
-// (run c6: with expf and a data-dependent branch per element the passes were ARITHMETIC-bound - 97 us per pass, whether launched
-// 200 times or run from one persistent kernel; 5 MUFU per 4 elements put a pass at the L2 streaming time instead).
-__device__ __forceinline__ void lse_acc4(float& mx, float& sm, const float (&t)[4]) {
-  const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
-  if (m4 == -INFINITY) return;
-  const float nm = fmaxf(mx, m4);
-  sm = sm * __expf(mx - nm) + ((__expf(t[0] - nm) + __expf(t[1] - nm)) + (__expf(t[2] - nm) + __expf(t[3] - nm)));
+// N more terms of an online logsumexp, branch-free: one rescale of the running sum per group, exponentials as ex2.approx of
+// an FFMA (runs c6-c8: with expf and a data-dependent branch per element the passes were arithmetic-bound; with four loads in
+// flight per thread they were L2-LATENCY-bound - lts throughput 7 % - so the passes below keep 8 / 16 loads in flight).
+template <int N>
+__device__ __forceinline__ void lse_acc(float& mx, float& sm, const float (&t)[N]) {
+  constexpr float L2E = 1.4426950408889634f;
+  float mN = t[0];
+#pragma unroll
+  for (int q = 1; q < N; ++q) mN = fmaxf(mN, t[q]);
+  if (mN == -INFINITY) return;
+  const float nm = fmaxf(mx, mN), nml = nm * L2E;
+  float acc = 0.f;
+#pragma unroll
+  for (int q = 0; q < N; ++q) acc += exp2f(fmaf(t[q], L2E, -nml));     // -inf terms give 0
+  sm = sm * exp2f(fmaf(mx, L2E, -nml)) + acc;
   mx = nm;
 }
 
@@ -296,15 +303,15 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
       float mx = -INFINITY, sm = 0.f;
       if (i < r1) {
         const float* row = a.S + (long long)i * a.ld;
-        for (int j0 = p; j0 <= a.n; j0 += 1024) {
-          float t[4];
+        for (int j0 = p; j0 <= a.n; j0 += 2048) {
+          float t[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
+          for (int q = 0; q < 8; ++q) {
             const int j = j0 + 256 * q;
             t[q] = -INFINITY;
             if (j <= a.n) t[q] = ((i < a.m && j < a.n) ? __ldg(row + j) : a.alpha) + vs[j];
           }
-          lse_acc4(mx, sm, t);
+          lse_acc<8>(mx, sm, t);
         }
       }
 #pragma unroll
@@ -322,15 +329,15 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
     // ---------------- column pass over the rows this CTA owns ----------------
     for (int j = tid; j <= a.n; j += 1024) {
       float mx = -INFINITY, sm = 0.f;
-      for (int i0 = r0; i0 < r1; i0 += 4) {
-        float t[4];
+      for (int i0 = r0; i0 < r1; i0 += 16) {
+        float t[16];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
+        for (int q = 0; q < 16; ++q) {
           const int i = i0 + q;
           t[q] = -INFINITY;
           if (i < r1) t[q] = ((i < a.m && j < a.n) ? __ldg(a.S + (long long)i * a.ld + j) : a.alpha) + us[i - r0];
         }
-        lse_acc4(mx, sm, t);
+        lse_acc<16>(mx, sm, t);
       }
       a.part[(long long)c * (a.n + 1) + j] = make_float2(mx, sm);
     }
