@@ -283,7 +283,7 @@ __device__ __forceinline__ void sink_grid_sync(unsigned int* bar, unsigned int& 
 }
 
 __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a, unsigned int* bar) {
-  extern __shared__ float vs[];                         // [n+1] current v (row pass) / v for the assignment
+  extern __shared__ __align__(16) float vs[];           // [n+1] current v (row pass) / v for the assignment
   __shared__ float us[64];                              // u of the rows this CTA owns
   __shared__ float rmx[32], rsm[32]; __shared__ int rix[32];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -297,22 +297,38 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
   for (int j = tid; j <= a.n; j += 1024) vs[j] = 0.f;  // v = 0 (rot_coh_match.py:302)
   __syncthreads();
   for (int it = 0; it < a.iters; ++it) {
-    // ---------------- row pass: 4 rows at a time, 256 threads per row ----------------
+    // ---------------- row pass: 4 rows at a time, 256 threads per row, 16-byte loads ----------------
+    // (run c9: 36 instructions per element - 64-bit index arithmetic, bounds predicates and the dustbin select on every load -
+    // made the passes issue-bound at ~50 us per iteration; the interior [m][n] block is now read as float4 / float2 without
+    // predicates and the dustbin row / column are added as separate terms.  Requires n % 4 == 0, ld % 4 == 0: the launcher checks.)
+    const int nq = a.n >> 2;                             // float4 per interior row
     for (int rb = r0; rb < r1; rb += 4) {
       const int i = rb + (tid >> 8), p = tid & 255;
       float mx = -INFINITY, sm = 0.f;
       if (i < r1) {
-        const float* row = a.S + (long long)i * a.ld;
-        for (int j0 = p; j0 <= a.n; j0 += 2048) {
-          float t[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const int j = j0 + 256 * q;
-            t[q] = -INFINITY;
-            if (j <= a.n) t[q] = ((i < a.m && j < a.n) ? __ldg(row + j) : a.alpha) + vs[j];
+        const float4* vq = reinterpret_cast<const float4*>(vs);
+        if (i < a.m) {
+          const float4* row = reinterpret_cast<const float4*>(a.S + (long long)i * a.ld);
+          int j4 = p;
+          for (; j4 + 256 < nq; j4 += 512) {             // two float4 in flight
+            const float4 s0 = __ldg(row + j4), s1 = __ldg(row + j4 + 256);
+            const float4 v0 = vq[j4], v1 = vq[j4 + 256];
+            const float t[8] = {s0.x + v0.x, s0.y + v0.y, s0.z + v0.z, s0.w + v0.w, s1.x + v1.x, s1.y + v1.y, s1.z + v1.z, s1.w + v1.w};
+            lse_acc<8>(mx, sm, t);
           }
-          lse_acc<8>(mx, sm, t);
+          if (j4 < nq) {
+            const float4 s0 = __ldg(row + j4); const float4 v0 = vq[j4];
+            const float t[4] = {s0.x + v0.x, s0.y + v0.y, s0.z + v0.z, s0.w + v0.w};
+            lse_acc<4>(mx, sm, t);
+          }
+        } else {                                          // the dustbin row: Z = alpha everywhere
+          for (int j4 = p; j4 < nq; j4 += 256) {
+            const float4 v0 = vq[j4];
+            const float t[4] = {a.alpha + v0.x, a.alpha + v0.y, a.alpha + v0.z, a.alpha + v0.w};
+            lse_acc<4>(mx, sm, t);
+          }
         }
+        if (p == 0) { const float t[1] = {a.alpha + vs[a.n]}; lse_acc<1>(mx, sm, t); }     // the dustbin column
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o); lse_merge(mx, sm, om, os); }
@@ -326,20 +342,35 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
       }
       __syncthreads();
     }
-    // ---------------- column pass over the rows this CTA owns ----------------
-    for (int j = tid; j <= a.n; j += 1024) {
-      float mx = -INFINITY, sm = 0.f;
-      for (int i0 = r0; i0 < r1; i0 += 16) {
-        float t[16];
+    // ---------------- column pass over the rows this CTA owns: a thread takes column PAIRS, 16 rows in flight ----------------
+    {
+      const int ri1 = min(r1, a.m);                       // interior rows of this CTA
+      const bool owns_bin = (r1 == a.m + 1) && (r0 <= a.m);
+      for (int jp = tid; jp < (a.n >> 1); jp += 1024) {
+        float mx0 = -INFINITY, sm0 = 0.f, mx1 = -INFINITY, sm1 = 0.f;
+        const float2* col = reinterpret_cast<const float2*>(a.S + (long long)r0 * a.ld) + jp;
+        const int ldp = a.ld >> 1;
+        int i = r0;
+        for (; i + 8 <= ri1; i += 8) {
+          float t0[8], t1[8];
 #pragma unroll
-        for (int q = 0; q < 16; ++q) {
-          const int i = i0 + q;
-          t[q] = -INFINITY;
-          if (i < r1) t[q] = ((i < a.m && j < a.n) ? __ldg(a.S + (long long)i * a.ld + j) : a.alpha) + us[i - r0];
+          for (int q = 0; q < 8; ++q) { const float2 z = __ldg(col + (long long)(i - r0 + q) * ldp); const float uu = us[i - r0 + q]; t0[q] = z.x + uu; t1[q] = z.y + uu; }
+          lse_acc<8>(mx0, sm0, t0); lse_acc<8>(mx1, sm1, t1);
         }
-        lse_acc<16>(mx, sm, t);
+        for (; i < ri1; ++i) {
+          const float2 z = __ldg(col + (long long)(i - r0) * ldp); const float uu = us[i - r0];
+          const float t0[1] = {z.x + uu}, t1[1] = {z.y + uu};
+          lse_acc<1>(mx0, sm0, t0); lse_acc<1>(mx1, sm1, t1);
+        }
+        if (owns_bin) { const float t[1] = {a.alpha + us[a.m - r0]}; lse_acc<1>(mx0, sm0, t); lse_acc<1>(mx1, sm1, t); }
+        float2* pp = a.part + (long long)c * (a.n + 1) + 2 * jp;
+        pp[0] = make_float2(mx0, sm0); pp[1] = make_float2(mx1, sm1);
       }
-      a.part[(long long)c * (a.n + 1) + j] = make_float2(mx, sm);
+      if (tid == 0) {                                     // the dustbin column: alpha + u over all own rows
+        float mx = -INFINITY, sm = 0.f;
+        for (int i = r0; i < r1; ++i) { const float t[1] = {a.alpha + us[i - r0]}; lse_acc<1>(mx, sm, t); }
+        a.part[(long long)c * (a.n + 1) + a.n] = make_float2(mx, sm);
+      }
     }
     sink_grid_sync(bar, gen);
     // ---------------- merge the partials of this CTA's columns (fixed order: lane l takes CTAs l, l+32, ...) ----------------

@@ -509,7 +509,9 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
   RR_ARG(c, S && u && v && matches0 && mscores0 && m >= 1 && n >= 1 && ld >= n && iters >= 0);
   cudaStream_t st = (cudaStream_t)stream;
   const int G = c->sm_count;
-  const bool fused = ((m + G) / G <= 64) && ((size_t)(n + 1) * sizeof(float) <= 200 * 1024) && !getenv("ROREG_SINKHORN_LAUNCHES");
+  // the persistent kernel reads the interior block with 16 / 8-byte loads: n, ld multiples of 4 and a 16-byte aligned S
+  const bool fused = ((m + G) / G <= 64) && ((size_t)(n + 4) * sizeof(float) <= 200 * 1024) && (n % 4 == 0) && (ld % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(S) & 15) == 0) && !getenv("ROREG_SINKHORN_LAUNCHES");
   int rc = rr_ws_reserve(c, rr_align(sizeof(int32_t) * m) + rr_align(sizeof(float) * m) + rr_align(sizeof(int32_t) * n) +
                             (fused ? rr_align(sizeof(float2) * (size_t)G * (n + 1)) + rr_align(256) : 0) + 4096);
   if (rc) return rc;
@@ -521,7 +523,7 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
     unsigned int* bar = ar.take<unsigned int>(64);
     RR_CUDA(c, cudaMemsetAsync(bar, 0, 256, st));
     SinkFusedArgs fa{S, m, n, ld, alpha, -logf((float)(m + n)), iters, u, v, part, idx0, max0, idx1, matches0, mscores0};
-    const size_t smem = (size_t)(n + 1) * sizeof(float);
+    const size_t smem = (size_t)(n + 4) * sizeof(float);
     static unsigned long long attr_mask = 0;
     if (rr_first_use_on_device(&attr_mask, c->device))
       RR_CUDA(c, cudaFuncSetAttribute(sinkhorn_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
