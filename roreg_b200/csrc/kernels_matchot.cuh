@@ -309,17 +309,20 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
         const float4* vq = reinterpret_cast<const float4*>(vs);
         if (i < a.m) {
           const float4* row = reinterpret_cast<const float4*>(a.S + (long long)i * a.ld);
-          int j4 = p;
-          for (; j4 + 256 < nq; j4 += 512) {             // two float4 in flight
-            const float4 s0 = __ldg(row + j4), s1 = __ldg(row + j4 + 256);
-            const float4 v0 = vq[j4], v1 = vq[j4 + 256];
-            const float t[8] = {s0.x + v0.x, s0.y + v0.y, s0.z + v0.z, s0.w + v0.w, s1.x + v1.x, s1.y + v1.y, s1.z + v1.z, s1.w + v1.w};
-            lse_acc<8>(mx, sm, t);
-          }
-          if (j4 < nq) {
-            const float4 s0 = __ldg(row + j4); const float4 v0 = vq[j4];
-            const float t[4] = {s0.x + v0.x, s0.y + v0.y, s0.z + v0.z, s0.w + v0.w};
-            lse_acc<4>(mx, sm, t);
+          // up to five float4 per thread in flight: at n = 5000 the whole row is ONE wait per group of four rows
+          for (int j0 = p; j0 < nq; j0 += 5 * 256) {
+            float4 sv[5];
+#pragma unroll
+            for (int q = 0; q < 5; ++q) { const int j4 = j0 + 256 * q; sv[q] = (j4 < nq) ? __ldg(row + j4) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY); }
+#pragma unroll
+            for (int q = 0; q < 5; ++q) {
+              const int j4 = j0 + 256 * q;
+              if (j4 < nq) {
+                const float4 v0 = vq[j4];
+                const float t[4] = {sv[q].x + v0.x, sv[q].y + v0.y, sv[q].z + v0.z, sv[q].w + v0.w};
+                lse_acc<4>(mx, sm, t);
+              }
+            }
           }
         } else {                                          // the dustbin row: Z = alpha everywhere
           for (int j4 = p; j4 < nq; j4 += 256) {
