@@ -63,14 +63,16 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 
-constexpr int GM_PRODUCERS = 4;                          // producer warps 0..3, MMA warp 4, epilogue warps 5..8
-constexpr int GM_THREADS = (GM_PRODUCERS + 1 + 4) * 32;  // 288
+// Warp roles: NPROD producer warps, then the MMA warp, then four epilogue warps.  NPROD is a template parameter because the gather
+// issue is serialised per lane (see the producer section): 4 / 8 / 16 producer warps issue 8 / 4 / 2 gathers each per k-chunk.
+__host__ __device__ constexpr int gm_threads(int nprod) { return (nprod + 1 + 4) * 32; }
 
-template <int NPASS>
-__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+template <int NPASS, int NPROD>
+__global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
   using Cfg = GemmCfg<NPASS>;
+  constexpr int GM_PRODUCERS = NPROD, LANES = 32 / NPROD;     // gather lanes per producer warp
   // Shared-memory budget: static (~1.4 KB, rounded up to the array's 1 KB alignment) + 192 KB of stages + barriers = 194.3 KiB,
   // i.e. under the 196 KiB carve-out step (+1 KiB the system reserves per CTA) - see the note at nei_s.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -121,17 +123,19 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     // Gather mode: a tile::gather4 instruction takes its four row coordinates from uniform registers, so the compiler
     // serialises lanes that hold different rows (ELECT + 6 x R2UR + UTMALDG per lane: run c5 - one warp issuing all 32 gathers
     // of a stage took ~1300 clk per k-chunk and made GF slower than the im2col version).  The 32 gathers of a stage are
-    // therefore spread over FOUR warps: warp w, lanes 0..7 fetch rows 32 w + 4 l .. + 3 of the tile (8 serialised issues per warp).
+    // therefore spread over NPROD warps: warp w, lanes 0..LANES-1 fetch the row groups w * LANES + l of the tile.  Run c11 (4 warps
+    // x 8 lanes): ~2000 clk per k-chunk in the issue loop (ELECT, 6 x R2UR.BROADCAST, UTMALDG, branch: ~250 clk per gather)
+    // against 512 clk of MMA work - the producers, not the tensor pipe or L2, paced the gather layers (tensor pipe 33 % active).
     const int cpk = gather ? a.g_C / GM_KC : 1;          // k-chunks per tap
     if (gather || warp == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
         int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
-        if (gather && lane < 8) {
+        if (gather && lane < LANES) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            int r = mt * GM_BM + 32 * warp + 4 * lane + i;
+            int r = mt * GM_BM + 4 * (warp * LANES + lane) + i;
             if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
             const int item = r / a.g_ng, j = r - item * a.g_ng;
             base[i] = item * 60; tap0[i] = (int)gset_s[j] * 13;
@@ -153,11 +157,11 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             }
           }
           if (gather) {
-            if (lane < 8) {
+            if (lane < LANES) {
               const int c0 = k_sub * GM_KC;
               const int r0 = base[0] + (int)nei_s[tap0[0] + k_tap], r1 = base[1] + (int)nei_s[tap0[1] + k_tap];
               const int r2 = base[2] + (int)nei_s[tap0[2] + k_tap], r3 = base[3] + (int)nei_s[tap0[3] + k_tap];
-              const uint32_t dst = sb + (warp * 8 + lane) * 512;
+              const uint32_t dst = sb + (warp * LANES + lane) * 512;
               tma_gather4(dst, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
               if (NPASS == 3) tma_gather4(dst + Cfg::OFF_ALO, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
             }
@@ -358,14 +362,24 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   if ((rc = gemm_make_map(c, &mWl, W_lo ? W_lo : W_hi, w_rows, a.Kdim, a.NT))) return rc;
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
   }
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const long long tiles = (long long)n_mt * a.n_ntiles;
   const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
-  if (a.npass == 3) gemm_tc_kernel<3><<<grid, GM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
-  else gemm_tc_kernel<1><<<grid, GM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  // producer warps: plain mode needs one issuing lane (4 = the smallest instantiation); gather mode: ROREG_GEMM_PRODUCERS = 4 | 8 | 16
+  static int gprod = 0;
+  if (!gprod) { const char* e = getenv("ROREG_GEMM_PRODUCERS"); const int v = e ? atoi(e) : 8; gprod = (v == 4 || v == 16) ? v : 8; }
+  const int nprod = gather ? gprod : 4;
+#define GM_LAUNCH(NP, NPR) gemm_tc_kernel<NP, NPR><<<grid, gm_threads(NPR), GemmCfg<NP>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a)
+  if (a.npass == 3) { if (nprod == 4) GM_LAUNCH(3, 4); else if (nprod == 8) GM_LAUNCH(3, 8); else GM_LAUNCH(3, 16); }
+  else              { if (nprod == 4) GM_LAUNCH(1, 4); else if (nprod == 8) GM_LAUNCH(1, 8); else GM_LAUNCH(1, 16); }
+#undef GM_LAUNCH
   RR_LAUNCH_CHECK(c);
   return ROREG_OK;
 }

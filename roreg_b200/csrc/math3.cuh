@@ -68,6 +68,33 @@ RR_HD int svd3_complete_u(const double A[9], const double V[9], const double S[3
     const double inv = (S[j] > 0) ? 1.0 / S[j] : 0.0;
     for (int i = 0; i < 3; ++i) U[3 * i + j] = A[3 * i + j] * inv;
   }
+  // rank <= 1 (a triplet with a repeated match: 3-point draws are WITH replacement, test/estimator.py:228): two singular values
+  // vanish and the cross-product completion below would return zero columns - i.e. a projector, not a rotation.  Complete U with
+  // an orthonormal basis instead, as LAPACK's SVD does for the reference (which basis is arbitrary there too).
+  {
+    int jmax = 0;
+    if (S[1] > S[jmax]) jmax = 1;
+    if (S[2] > S[jmax]) jmax = 2;
+    int nsig = 0;
+    for (int j = 0; j < 3; ++j) nsig += (S[j] > 1e-10 * smax) ? 1 : 0;
+    if (smax <= 0.0 || nsig <= 1) {
+      if (smax <= 0.0) { for (int i = 0; i < 9; ++i) U[i] = (i % 4 == 0) ? 1.0 : 0.0; return jmin; }
+      const double u0 = U[0 + jmax], u1 = U[3 + jmax], u2 = U[6 + jmax];
+      int e = 0;
+      if (fabs(u1) < fabs(u0)) e = 1;
+      if (fabs(u2) < fabs(e == 0 ? u0 : u1)) e = 2;
+      const double ex = (e == 0), ey = (e == 1), ez = (e == 2);
+      double v0 = u1 * ez - u2 * ey, v1 = u2 * ex - u0 * ez, v2 = u0 * ey - u1 * ex;        // u x e
+      const double nv = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+      v0 /= nv; v1 /= nv; v2 /= nv;
+      const double w0 = u1 * v2 - u2 * v1, w1 = u2 * v0 - u0 * v2, w2 = u0 * v1 - u1 * v0;  // u x v: (u, v, w) right-handed
+      const int ja = (jmax + 1) % 3, jb = (jmax + 2) % 3;
+      U[0 + ja] = v0; U[3 + ja] = v1; U[6 + ja] = v2;
+      U[0 + jb] = w0; U[3 + jb] = w1; U[6 + jb] = w2;
+      if (jmin == jmax) jmin = ja;
+      return jmin;
+    }
+  }
   const int a = (jmin + 1) % 3, b = (jmin + 2) % 3;
   double c0 = U[3 + a] * U[6 + b] - U[6 + a] * U[3 + b];
   double c1 = U[6 + a] * U[0 + b] - U[0 + a] * U[6 + b];

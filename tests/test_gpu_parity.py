@@ -303,6 +303,19 @@ def test_kabsch3_proper_branch(ctx, pair):
 
 
 # ---------------------------------------------------------------------------------------- batched engine
+def test_kabsch3_repeated_matches_still_give_rotations(ctx, pair):
+    """Triplets are drawn with replacement (test/estimator.py:228): a repeated match makes the cross-covariance rank 1 or 0.  The
+    device Kabsch must still return a proper rotation (as LAPACK does for the reference), never a projector / zero matrix."""
+    k0, k1 = _matched(pair)
+    trip = np.array([[5, 5, 9], [7, 7, 7], [3, 11, 3], [1, 2, 3]], np.int32)
+    got = _np(ctx.kabsch3(ctx.dev(k0, torch.float64), ctx.dev(k1, torch.float64), ctx.dev(trip)))
+    for h in range(4):
+        R = got[h][:, :3]
+        assert np.isfinite(got[h]).all() and np.abs(R @ R.T - np.eye(3)).max() < 1e-9 and abs(np.linalg.det(R) - 1) < 1e-9
+        t = trip[h]
+        assert np.abs(k1[t].mean(0) @ R.T + got[h][:, 3] - k0[t].mean(0)).max() < 1e-9
+
+
 def _oracle_pipeline(pr, tables, hyp=None, trip=None, ird=0.1):
     pps, sc = O.mutual_run(pr["feats0"], pr["feats1"])
     dr = O.rindex(pr["feats0"], pr["feats1"], pps, tables.perm)

@@ -61,6 +61,28 @@ def test_three_point_transform_arbitrary_triplets():
     assert nproper > 1000
 
 
+def test_three_point_transform_repeated_points_is_still_a_rotation():
+    """Triplets drawn WITH replacement (test/estimator.py:228) repeat a match: the cross-covariance has rank 1 (two equal
+    points) or 0 (three equal points).  LAPACK returns an orthogonal matrix for the reference; the device arithmetic must also
+    return a proper rotation (round 1 returned a rank-1 projector / the zero matrix) that maps the distinct points correctly."""
+    L = _lib(); rng = np.random.default_rng(9)
+    for i in range(300):
+        k1 = rng.random((3, 3)) * 3; k0 = rng.random((3, 3)) * 3 + rng.uniform(-2, 2, 3)
+        kind = i % 3
+        if kind == 0: k1[2] = k1[1]; k0[2] = k0[1]                     # rank 1
+        elif kind == 1: k1[1] = k1[0]; k1[2] = k1[0]; k0[1] = k0[0]; k0[2] = k0[0]      # rank 0
+        else: k1[2] = k1[0]; k0[2] = k0[0]
+        k0 = np.ascontiguousarray(k0); k1 = np.ascontiguousarray(k1)
+        T = np.zeros((3, 4)); L.rr_host_three_point_transform(k0.ctypes.data_as(dp), k1.ctypes.data_as(dp), T.ctypes.data_as(dp))
+        R = T[:, :3]
+        assert np.isfinite(T).all() and np.abs(R @ R.T - np.eye(3)).max() < 1e-9 and abs(np.linalg.det(R) - 1) < 1e-9
+        # centroids map onto each other, and for rank 1 the direction between the two distinct points is preserved
+        assert np.abs(k1.mean(0) @ R.T + T[:, 3] - k0.mean(0)).max() < 1e-9
+        if kind != 1:
+            d1 = k1[1] - k1[0]; d0 = k0[1] - k0[0]
+            assert np.abs(R @ (d1 / np.linalg.norm(d1)) - d0 / np.linalg.norm(d0)).max() < 1e-7
+
+
 def test_quat_times_anchor_bit_exact(tables):
     L = _lib(); rng = np.random.default_rng(2)
     for i in range(300):
