@@ -31,7 +31,8 @@ typedef enum {
   ROREG_ERR_ARG = -1,        /* bad argument                                     */
   ROREG_ERR_CUDA = -2,       /* CUDA runtime error (see roreg_last_error)        */
   ROREG_ERR_NOMEM = -3,      /* workspace allocation failed                      */
-  ROREG_ERR_UNSUPPORTED = -4 /* size outside the compiled limits                 */
+  ROREG_ERR_UNSUPPORTED = -4,/* size outside the compiled limits                 */
+  ROREG_ERR_IO = -5          /* a result file could not be written               */
 } roreg_status;
 
 typedef struct roreg_ctx roreg_ctx;
@@ -246,6 +247,17 @@ int roreg_set_overlap(roreg_ctx* ctx, int enable);
  * and repeated in float64 otherwise; decisions and sums are identical to mode 0 by construction.                      */
 int roreg_set_score_mode(roreg_ctx* ctx, int mode);
 int roreg_get_stage_ms(roreg_ctx* ctx, float* ms_host);
+
+/* ---- stage I/O: the four per-pair files the reference's plugins leave for its evaluator, written from C
+ * so that writer threads run without the Python GIL (no GPU involved; any path may be NULL = skip that file):
+ *   match_path     int64 [K,2]  .npy   (test/matcher.py:108, np.save of match_pps)
+ *   scores_path    float64 [K]  .npy   = ones (test/matcher.py:109)
+ *   dr_index_path  int64 [K]    .npy   (test/estimator.py:111)
+ *   npz_path       np.savez(trans = pose [4,4] float64, recalltime = int64 scalar)   (test/estimator.py:242)
+ * NPY format 1.0 / ZIP of stored members: exactly what np.load reads back.                                              */
+int roreg_write_pair_files(const char* match_path, const char* scores_path, const char* dr_index_path, const char* npz_path,
+                           const int64_t* matches, const int64_t* dr_index, int K, const double* pose4x4,
+                           long long recalltime);
 
 #ifdef __cplusplus
 }

@@ -65,6 +65,7 @@ SIGNATURES = {
     "roreg_set_overlap": (_i, [_p, _i]),
     "roreg_set_score_mode": (_i, [_p, _i]),
     "roreg_get_stage_ms": (_i, [_p, C.POINTER(C.c_float)]),
+    "roreg_write_pair_files": (_i, [C.c_char_p, C.c_char_p, C.c_char_p, C.c_char_p, _p, _p, _i, _p, C.c_longlong]),
 }
 
 _lib = None

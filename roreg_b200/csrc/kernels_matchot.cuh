@@ -264,20 +264,22 @@ struct SinkFusedArgs {
   float* u; float* v;             // [m+1], [n+1]
   float2* part;                   // [gridDim.x][n+1] column partials (max, sum) / (best value, row index bits)
   int32_t* idx0; float* max0; int32_t* idx1; int32_t* matches0; float* mscores0;
+  int dbg;                        // ROREG_DEBUG_SINK (bottleneck experiments only, results then WRONG): 1 = no grid barriers, 2 = barriers without fences
 };
 
-__device__ __forceinline__ void sink_grid_sync(unsigned int* bar, unsigned int& gen) {
+__device__ __forceinline__ void sink_grid_sync(unsigned int* bar, unsigned int& gen, int dbg = 0) {
   // sense-free generation barrier on a global counter: every CTA is resident (cooperative launch, one CTA per SM)
   __syncthreads();
+  if (dbg == 1) return;
   if (threadIdx.x == 0) {
     ++gen;
-    __threadfence();
+    if (dbg != 2) __threadfence();
     atomicAdd(bar, 1u);
     const unsigned int target = gen * gridDim.x;
     unsigned int spins = 0;
     while (*reinterpret_cast<volatile unsigned int*>(bar) < target)
       if (++spins > (1u << 24)) { printf("roreg: sinkhorn grid barrier timed out (block %d, generation %u)\n", blockIdx.x, gen); __trap(); }   // never hang the GPU
-    __threadfence();
+    if (dbg != 2) __threadfence();
   }
   __syncthreads();
 }
@@ -375,7 +377,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
         a.part[(long long)c * (a.n + 1) + a.n] = make_float2(mx, sm);
       }
     }
-    sink_grid_sync(bar, gen);
+    sink_grid_sync(bar, gen, a.dbg);
     // ---------------- merge the partials of this CTA's columns (fixed order: lane l takes CTAs l, l+32, ...) ----------------
     for (int j = c0 + warp; j < c1; j += 32) {
       float mx = -INFINITY, sm = 0.f;
@@ -384,7 +386,7 @@ __global__ void __launch_bounds__(1024, 1) sinkhorn_fused_kernel(SinkFusedArgs a
       for (int o = 16; o > 0; o >>= 1) { const float om = __shfl_xor_sync(0xffffffffu, mx, o), os = __shfl_xor_sync(0xffffffffu, sm, o); lse_merge(mx, sm, om, os); }
       if (lane == 0) a.v[j] = ((j < a.n) ? a.norm : log_nu_bin) - (mx + logf(sm));
     }
-    sink_grid_sync(bar, gen);
+    sink_grid_sync(bar, gen, a.dbg);
     for (int j = tid; j <= a.n; j += 1024) vs[j] = __ldcg(a.v + j);
     __syncthreads();
   }

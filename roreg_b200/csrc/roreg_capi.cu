@@ -11,6 +11,7 @@
 #include "kernels_gemm_tc.cuh"
 #include "kernels_gconv.cuh"
 #include "kernels_matchot.cuh"
+#include "host_io.inl"
 
 using namespace roreg;
 
@@ -522,7 +523,8 @@ int roreg_sinkhorn_match(roreg_ctx* c, const float* S, int m, int n, int ld, flo
     float2* part = ar.take<float2>((size_t)G * (n + 1));
     unsigned int* bar = ar.take<unsigned int>(64);
     RR_CUDA(c, cudaMemsetAsync(bar, 0, 256, st));
-    SinkFusedArgs fa{S, m, n, ld, alpha, -logf((float)(m + n)), iters, u, v, part, idx0, max0, idx1, matches0, mscores0};
+    SinkFusedArgs fa{S, m, n, ld, alpha, -logf((float)(m + n)), iters, u, v, part, idx0, max0, idx1, matches0, mscores0, 0};
+    if (const char* e = getenv("ROREG_DEBUG_SINK")) fa.dbg = atoi(e);
     const size_t smem = (size_t)(n + 4) * sizeof(float);
     static unsigned long long attr_mask = 0;
     if (rr_first_use_on_device(&attr_mask, c->device))

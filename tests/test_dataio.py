@@ -72,3 +72,28 @@ def test_reference_demo_scene():
     sub = pc0[::8].astype(np.float32)
     d = np.array([np.sqrt(((sub - p.astype(np.float32)) ** 2).sum(1).min()) for p in moved[::25]])
     assert np.mean(d < 0.05) > 0.5, np.mean(d < 0.05)
+
+
+def test_pair_file_writer_matches_numpy(tmp_path):
+    """roreg_write_pair_files (plain C, used by the scene driver's writer threads): the .npy files are byte-identical to np.save
+    of the same arrays, the .npz is read back by np.load with the keys / dtypes / shapes np.savez(trans=..., recalltime=...)
+    produces (test/matcher.py:108-109, test/estimator.py:111,242).  No GPU involved."""
+    from roreg_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for K in (0, 1, 7, 3400):
+        m = rng.integers(0, 5000, (K, 2)).astype(np.int64); dr = rng.integers(0, 60, K).astype(np.int64); T = rng.random((4, 4))
+        f = {k: str(tmp_path / f"{k}{K}") for k in ("m.npy", "s.npy", "d.npy", "r.npz")}
+        rc = lib.roreg_write_pair_files(f["m.npy"].encode(), f["s.npy"].encode(), f["d.npy"].encode(), f["r.npz"].encode(),
+                                        m.ctypes.data, dr.ctypes.data, K, T.ctypes.data, 50000)
+        assert rc == 0
+        for name, ref in (("m.npy", m), ("s.npy", np.ones(K)), ("d.npy", dr)):
+            np.save(str(tmp_path / "ref.npy"), ref)
+            assert open(f[name], "rb").read() == open(str(tmp_path / "ref.npy"), "rb").read(), (name, K)
+        z = np.load(f["r.npz"], allow_pickle=True)
+        np.savez(str(tmp_path / "ref.npz"), trans=T, recalltime=50000)
+        zr = np.load(str(tmp_path / "ref.npz"))
+        assert sorted(z.files) == sorted(zr.files) == ["recalltime", "trans"]
+        for k in z.files:
+            assert z[k].dtype == zr[k].dtype and z[k].shape == zr[k].shape and np.array_equal(z[k], zr[k])
+    assert lib.roreg_write_pair_files(str(tmp_path / "no_such_dir" / "x.npy").encode(), None, None, None, m.ctypes.data, dr.ctypes.data, K, T.ctypes.data, 1) == -5
