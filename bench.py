@@ -647,8 +647,9 @@ def main():
         ach = amount / dur / 1e12; peak = tc_peak; unit = "TFLOP/s"
     traffic = None
     try:       # dram__bytes_read+write of the dominant stage's main kernel from the committed ncu --set full capture, scaled to B pairs
-        tj = json.load(open(os.path.join(REPO, "profiles", "r01_traffic.json")))["kernels"]
-        kname = {"nn": "nn_tc4_kernel", "group_corr": "group_corr_tc3_kernel", "score_select": "ransac_score_kernel",
+        tj = json.load(open(os.path.join(REPO, "profiles", "r02_traffic.json")))["kernels"]
+        kname = {"nn": "nn_tc4_kernel", "group_corr": "group_corr_tc3_kernel",
+                 "score_select": "ransac_score_pre_kernel" if args.score_mode == 1 else "ransac_score_kernel",
                  "inv_pool": "inv_pool_t4_kernel"}.get(dom)
         if kname in tj:
             traffic = tj[kname]["dram_bytes_per_launch"] / tj[kname]["pairs_per_launch"] * B
@@ -663,9 +664,11 @@ def main():
                                "hbm_frac_overlapped": B * (2 * n * 7680 + 2 * n * 128 + kavg * (2 * 7680 + 12)) / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak,
                                "survey_8d_bytes": B * 77.6e6 * (n / 5000.0),
                                "hbm_frac_survey_8d": B * 77.6e6 * (n / 5000.0) / (sum(stage_ms.values()) * 1e-3) / 1e9 / hbm_peak,
+                               "hbm_frac_survey_8d_timed": B * 77.6e6 * (n / 5000.0) / (ms_max / args.steps * 1e-3) / 1e9 / hbm_peak,
                                "note": "algorithmic_bytes = descriptors read by the pooling pass + the rows Des2R gathers for the K matches (two passes "
                                        "over HBM, DESIGN.md section 3); survey_8d_bytes = SURVEY.md 8(d)'s 77.6 MB per pair (every descriptor byte "
-                                       "counted once)"},
+                                       "counted once); ms = serial sum of the per-stage events, ms_overlapped / *_timed = the timed region's own "
+                                       "time per step (pipelined schedule: the tail of batch i-1 beside the pooling of batch i)"},
                 "note": "algorithmic bytes/flops per step (B pairs) / CUDA-event duration of that stage, events recorded by the library on the "
                         "launch stream in a replay of the timed steps with per-stage timing on (same serial schedule as the timed region unless "
                         "--pipelined 1; fused_step.ms_overlapped = the timed region's own ms per step, events included in neither)"}

@@ -9,6 +9,7 @@
 #include "kernels_nn_tc4.cuh"
 #include "kernels_corr_tc3.cuh"
 #include "kernels_gemm_tc.cuh"
+#include "kernels_allpairs_tc.cuh"
 #include "kernels_gconv.cuh"
 #include "kernels_matchot.cuh"
 #include "host_io.inl"
@@ -385,8 +386,9 @@ int roreg_quat_normalize(roreg_ctx* c, const float* q_in, int ld, int K, float* 
   return ROREG_OK;
 }
 
-// all-pairs 60-rotation correlation (north_star kernel 1): 60 K-permuted tcgen05 GEMMs with a
-// running (max, argmax) epilogue; X / Y are the channel-last tf32-split descriptors from roreg_pack_descriptors
+// all-pairs 60-rotation correlation (north_star kernel 1): ONE persistent tcgen05 kernel with the rotation
+// loop inside and the running (max, argmax) in registers (kernels_allpairs_tc.cuh); X / Y are the channel-last tf32-split
+// descriptors from roreg_pack_descriptors.  ROREG_ALLPAIRS_LAUNCHES=1 selects round 1's 60 K-permuted GEMM launches (A/B).
 int roreg_group_corr_allpairs(roreg_ctx* c, const float* X_hi, const float* X_lo, int N, const float* Y_hi, const float* Y_lo, int M,
                               int npass, float* best, uint8_t* best_a, int32_t* nn, int32_t* nn_a, float* nn_dist, void* stream) {
   RR_ARG(c, X_hi && Y_hi && best && best_a && N >= 1 && M >= 1 && (npass == 1 || (npass == 3 && X_lo && Y_lo)));
@@ -395,19 +397,23 @@ int roreg_group_corr_allpairs(roreg_ctx* c, const float* X_hi, const float* X_lo
   if (rc) return rc;
   rr_arena ar{(char*)c->ws, 0};
   int32_t* cols = ar.take<int32_t>(3600); float* nx = ar.take<float>(N); float* ny = ar.take<float>(M);
-  // column coordinate of k-chunk g for rotation a: P[a][g]*32   (cor_a = sum_g <X[:,P[a,g]], Y[:,g]>, test/estimator.py:85-89)
-  {
-    static int32_t h_cols[3600];
-    for (int i = 0; i < 3600; ++i) h_cols[i] = (int32_t)c->h_perm8[i] * 32;
-    RR_CUDA(c, cudaMemcpyAsync(cols, h_cols, sizeof(h_cols), cudaMemcpyHostToDevice, st));
-  }
-  fill_f32_kernel<<<rr_blocks(c, (long long)N * M, 256), 256, 0, st>>>(best, (long long)N * M, -INFINITY);
-  RR_LAUNCH_CHECK(c);
-  for (int a_id = 0; a_id < 60; ++a_id) {
-    GemmArgs g{};
-    g.R = N; g.Kdim = 1920; g.O = M; g.NT = M >= 256 ? 256 : ((M + 15) / 16) * 16; g.n_ntiles = (M + g.NT - 1) / g.NT; g.npass = npass;
-    g.raw_out = best; g.raw_ld = M; g.a_cols = cols + a_id * 60; g.amax_arg = best_a; g.amax_id = a_id;
-    if ((rc = gemm_tc_launch(c, X_hi, X_lo, Y_hi, Y_lo, M, g, st))) return rc;
+  if (!getenv("ROREG_ALLPAIRS_LAUNCHES")) {
+    if ((rc = allpairs_tc_launch(c, X_hi, X_lo, N, Y_hi, Y_lo, M, npass, best, best_a, st))) return rc;
+  } else {
+    // column coordinate of k-chunk g for rotation a: P[a][g]*32   (cor_a = sum_g <X[:,P[a,g]], Y[:,g]>, test/estimator.py:85-89)
+    {
+      static int32_t h_cols[3600];
+      for (int i = 0; i < 3600; ++i) h_cols[i] = (int32_t)c->h_perm8[i] * 32;
+      RR_CUDA(c, cudaMemcpyAsync(cols, h_cols, sizeof(h_cols), cudaMemcpyHostToDevice, st));
+    }
+    fill_f32_kernel<<<rr_blocks(c, (long long)N * M, 256), 256, 0, st>>>(best, (long long)N * M, -INFINITY);
+    RR_LAUNCH_CHECK(c);
+    for (int a_id = 0; a_id < 60; ++a_id) {
+      GemmArgs g{};
+      g.R = N; g.Kdim = 1920; g.O = M; g.NT = M >= 256 ? 256 : ((M + 15) / 16) * 16; g.n_ntiles = (M + g.NT - 1) / g.NT; g.npass = npass;
+      g.raw_out = best; g.raw_ld = M; g.a_cols = cols + a_id * 60; g.amax_arg = best_a; g.amax_id = a_id;
+      if ((rc = gemm_tc_launch(c, X_hi, X_lo, Y_hi, Y_lo, M, g, st))) return rc;
+    }
   }
   if (nn) {
     RR_ARG(c, nn_a && nn_dist);
