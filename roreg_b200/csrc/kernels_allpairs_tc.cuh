@@ -161,8 +161,13 @@ __global__ void __launch_bounds__(AP_THREADS, 1) allpairs_tc_kernel(const __grid
         if (vec) {
 #pragma unroll
           for (int c = 0; c < 128; c += 4) *reinterpret_cast<float4*>(pb + c) = make_float4(best[c], best[c + 1], best[c + 2], best[c + 3]);
+          if ((a.M & 15) == 0) {                          // byte rows: 16-byte stores only when the row pitch keeps them aligned
 #pragma unroll
-          for (int c = 0; c < 32; c += 4) *reinterpret_cast<uint4*>(pa + 4 * c) = make_uint4(argw[c], argw[c + 1], argw[c + 2], argw[c + 3]);
+            for (int c = 0; c < 32; c += 4) *reinterpret_cast<uint4*>(pa + 4 * c) = make_uint4(argw[c], argw[c + 1], argw[c + 2], argw[c + 3]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) *reinterpret_cast<uint32_t*>(pa + 4 * c) = argw[c];
+          }
         } else {
 #pragma unroll
           for (int c = 0; c < 128; ++c)

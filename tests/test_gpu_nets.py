@@ -185,6 +185,23 @@ def test_group_corr_allpairs(ctx, tables, npass, tol):
     ok = (part[:, 1] - part[:, 0]) > tol * 200
     assert (_np(nn)[ok] == dist.argmin(1)[ok]).all()
     assert np.abs(_np(nd) - dist.min(1))[ok].max() < tol * 200
+    # a size that takes the vectorised store path and several tiles in both directions (M % 4 == 0, M % 16 != 0: run c16's bug)
+    if True:
+        rng = np.random.default_rng(3)
+        X3 = rng.standard_normal((300, 32, 60)).astype(np.float32); Y3 = rng.standard_normal((520, 32, 60)).astype(np.float32)
+        X3 /= np.linalg.norm(X3, axis=1, keepdims=True); Y3 /= np.linalg.norm(Y3, axis=1, keepdims=True)
+        xh3, xl3 = g.pack([ctx.dev(X3)], [None], [0], None, 300); yh3, yl3 = g.pack([ctx.dev(Y3)], [None], [0], None, 520)
+        b3 = torch.empty((300, 520), dtype=torch.float32, device=ctx.device); a3 = torch.empty((300, 520), dtype=torch.uint8, device=ctx.device)
+        rc = ctx.lib.roreg_group_corr_allpairs(ctx.h, _ptr(xh3), _ptr(xl3), 300, _ptr(yh3), _ptr(yl3), 520, npass, _ptr(b3), _ptr(a3), None, None, None, _stream())
+        _lib.check(ctx.h, rc, "roreg_group_corr_allpairs")
+        torch.cuda.synchronize()
+        cor3 = np.einsum("nfag,mfg->nma", X3.astype(np.float64)[:, :, tables.perm], Y3.astype(np.float64))
+        assert (np.abs(_np(b3) - cor3.max(2)) / np.maximum(1.0, np.abs(cor3.max(2)))).max() < tol
+        t3 = np.sort(cor3, axis=2)[:, :, -2:]
+        clear3 = (t3[:, :, 1] - t3[:, :, 0]) > tol * 20
+        assert (_np(a3)[clear3] == cor3.argmax(2)[clear3]).all()
+        if npass == 3:
+            assert clear3.mean() > 0.9
     # planted rotation: Y rows that are group-permuted copies of X rows must be found with their rotation index
     a = 17
     Y2 = np.ascontiguousarray(X[:64][:, :, tables.perm[a]])
