@@ -54,6 +54,9 @@ struct GemmArgs {
   // c0 = kc*32 % g_C) read activation row item*60 + g_nei[g][k], columns c0..c0+31 - fetched four rows per instruction with
   // cp.async.bulk.tensor ... tile::gather4 straight into the SWIZZLE_128B operand tile (Kdim = 13 * g_C).
   int g_C, g_ng; const int32_t* g_nei; const int32_t* g_set;
+  // g_ldg != 0: the gathered operand is loaded by the producer warps with LDG.128 and stored into the swizzled tile with STS.128
+  // (needs the raw activation pointers and NPROD == 8); 0: TMA tile::gather4 through the tensor maps.
+  int g_ldg; const float* g_act_hi; const float* g_act_lo;
 };
 
 // four rows of a 2-D tensor (box = 32 columns x 1 row) -> 4 x 128 B at dst, swizzled on the absolute shared-memory address
@@ -97,7 +100,9 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
     for (int i = threadIdx.x; i < 64; i += blockDim.x) gset_s[i] = (uint8_t)((a.g_set && i < a.g_ng) ? a.g_set[i] : i);
   }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), 1); mbar_init(BAR(4 + s), 1); }
+    // full[st]: one arrival from the TMA-issuing lane (arrive.expect_tx); with the LDG loader also one per warp of the group that
+    // filled the stage's A tile (4)
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), (gather && a.g_ldg) ? 5 : 1); mbar_init(BAR(4 + s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -127,7 +132,70 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
     // x 8 lanes): ~2000 clk per k-chunk in the issue loop (ELECT, 6 x R2UR.BROADCAST, UTMALDG, branch: ~250 clk per gather)
     // against 512 clk of MMA work - the producers, not the tensor pipe or L2, paced the gather layers (tensor pipe 33 % active).
     const int cpk = gather ? a.g_C / GM_KC : 1;          // k-chunks per tap
-    if (gather || warp == 0) {
+    if (gather && a.g_ldg) {
+      // ---- LDG / STS loader (run c16: the plain-mode pipeline reaches 94 % tensor-pipe activity in the all-pairs kernel, so the
+      // gather layers' 33 % was the TMA gather itself).  Two groups of four warps take alternate stages.  In a group, thread
+      // (row lane rl = t / 8, chunk q = t % 8) loads the 16-byte chunk q of rows rl + 16 j (j = 0..7): a warp instruction covers
+      // four full 128-byte activation rows, and stores it at the SWIZZLE_128B position the MMA descriptor expects (row r at
+      // (r / 8) * 1024 + (r % 8) * 128, chunk q ^ (r % 8)): four rows = four distinct 128-byte lines per STS.128, conflict-free.
+      // One pass: the loads of the group's NEXT stage are issued before the current one is stored (registers, no barrier needed).
+      if (NPROD == 8) {
+        const int grp = warp >> 2, tg = (warp & 3) * 32 + lane;
+        const int q = tg & 7, rl = tg >> 3;
+        const uint32_t sw_off = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((q ^ (rl & 7)) << 4));     // + 2048 j
+        uint32_t it0 = 0;
+        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it0 += (uint32_t)n_kc) {
+          const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
+          int base[8], tap0[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            int r = mt * GM_BM + rl + 16 * j;
+            if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
+            const int item = r / a.g_ng, jj = r - item * a.g_ng;
+            base[j] = item * 60; tap0[j] = (int)gset_s[jj] * 13;
+          }
+          auto issue = [&](int kc, const float* act, float4 (&buf)[8]) {
+            const int k_tap = kc / cpk, c0 = (kc - k_tap * cpk) * GM_KC + 4 * q;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              buf[j] = __ldg(reinterpret_cast<const float4*>(act + (long long)(base[j] + (int)nei_s[tap0[j] + k_tap]) * a.g_C + c0));
+          };
+          const int first = (int)((grp - (int)(it0 & 1u)) & 1);
+          float4 cur[8], nxt[8], lo[8];
+          if (first < n_kc) issue(first, a.g_act_hi, cur);
+          for (int kc = first; kc < n_kc; kc += 2) {
+            if (NPASS == 1 && kc + 2 < n_kc) issue(kc + 2, a.g_act_hi, nxt);
+            if (NPASS == 3) issue(kc, a.g_act_lo, lo);
+            const uint32_t it = it0 + (uint32_t)kc;
+            const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
+            if (lane == 0) mbar_wait(BAR(4 + st), ph ^ 1);
+            __syncwarp();
+            uint8_t* sbp = smem + st * Cfg::STAGE_BYTES;
+            if ((warp & 3) == 0 && lane == 0) {
+              const uint32_t sb = smem_u32(sbp);
+              mbar_expect_tx(BAR(st), Cfg::A_IMAGES * w_bytes);
+              tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
+              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sbp + sw_off + 2048 * j) = cur[j];
+            if (NPASS == 3) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sbp + Cfg::OFF_ALO + sw_off + 2048 * j) = lo[j];
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05
+            __syncwarp();
+            if (lane == 0) mbar_arrive(BAR(st));
+            if (NPASS == 1) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+            } else if (kc + 2 < n_kc) {
+              issue(kc + 2, a.g_act_hi, cur);
+            }
+          }
+        }
+      }
+    } else if (gather || warp == 0) {
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
         const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
@@ -375,7 +443,11 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   // producer warps: plain mode needs one issuing lane (4 = the smallest instantiation); gather mode: ROREG_GEMM_PRODUCERS = 4 | 8 | 16
   static int gprod = 0;
   if (!gprod) { const char* e = getenv("ROREG_GEMM_PRODUCERS"); const int v = e ? atoi(e) : 8; gprod = (v == 4 || v == 16) ? v : 8; }
-  const int nprod = gather ? gprod : 4;
+  // gathered operand: ROREG_GEMM_GATHER=tma selects the TMA tile::gather4 producer, default = the LDG / STS loader (8 producer warps)
+  static int gldg = -1;
+  if (gldg < 0) { const char* e = getenv("ROREG_GEMM_GATHER"); gldg = (e && !strcmp(e, "tma")) ? 0 : 1; }
+  a.g_ldg = gather ? gldg : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
+  const int nprod = gather ? (a.g_ldg ? 8 : gprod) : 4;
 #define GM_LAUNCH(NP, NPR) gemm_tc_kernel<NP, NPR><<<grid, gm_threads(NPR), GemmCfg<NP>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a)
   if (a.npass == 3) { if (nprod == 4) GM_LAUNCH(3, 4); else if (nprod == 8) GM_LAUNCH(3, 8); else GM_LAUNCH(3, 16); }
   else              { if (nprod == 4) GM_LAUNCH(1, 4); else if (nprod == 8) GM_LAUNCH(1, 8); else GM_LAUNCH(1, 16); }
