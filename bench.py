@@ -368,6 +368,44 @@ def extra_workloads(args, ctx, peaks):
                                             "assignment) on one pair, inputs resident, random weights of the checkpoint shapes"}
     except Exception as e:
         out["workload_match_ot"] = {"unavailable": repr(e)}
+    try:
+        # all-pairs 60-rotation correlation (north_star kernel 1): max / argmax over the 60 rotations of the 1920-term correlation
+        # of EVERY (n, m) keypoint pair of one cloud pair - one persistent tcgen05 kernel, the rotation loop inside
+        from roreg_b200 import nets
+        from roreg_b200.ops import _ptr, _stream
+        pr = prs[0]
+        res = {}
+        for np_ in (1, 3):
+            g = nets.GroupNets(ctx, np_)
+            xh, xl = g.pack([ctx.dev(pr["feats1"])], [None], [0], None, n); yh, yl = g.pack([ctx.dev(pr["feats0"])], [None], [0], None, n)
+            best = torch.empty((n, n), dtype=torch.float32, device=ctx.device); ba = torch.empty((n, n), dtype=torch.uint8, device=ctx.device)
+            nn_ = torch.empty(n, dtype=torch.int32, device=ctx.device); nna = torch.empty(n, dtype=torch.int32, device=ctx.device)
+            nd = torch.empty(n, dtype=torch.float32, device=ctx.device)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+            for rep in range(3):
+                e0.record()
+                rc = ctx.lib.roreg_group_corr_allpairs(ctx.h, _ptr(xh), _ptr(xl), n, _ptr(yh), _ptr(yl), n, np_, _ptr(best), _ptr(ba), None, None, None, _stream())
+                e1.record(); torch.cuda.synchronize()
+                assert rc == 0
+            ms = e0.elapsed_time(e1)
+            rc = ctx.lib.roreg_group_corr_allpairs(ctx.h, _ptr(xh), _ptr(xl), n, _ptr(yh), _ptr(yl), n, np_, _ptr(best), _ptr(ba), _ptr(nn_), _ptr(nna), _ptr(nd), _stream())
+            torch.cuda.synchronize()
+            corr = pr["corr0"]; sel = np.where(corr >= 0)[0]
+            inv = np.full(n, -1); inv[corr[sel]] = sel; have = inv >= 0
+            res[np_] = (ms, float((nn_.cpu().numpy()[have] == inv[have]).mean()), float((nna.cpu().numpy()[have] == pr["a"]).mean()))
+        flops = 2.0 * n * n * 1920 * 60
+        peak1 = 0.5 * peaks.get("bf16_tflops", 1690.0)
+        out["workload_allpairs"] = {
+            "value": 1e3 / res[1][0], "unit": "pairs/s", "ms_per_pair_tf32": res[1][0], "ms_per_pair_3xtf32": res[3][0], "keypoints": n,
+            "nn_accuracy_vs_planted": res[1][1], "rotation_accuracy_vs_planted": res[1][2], "gpu_launches_per_pair": 1,
+            "roofline": {"kernel": "allpairs_tc_kernel<1>", "bound": "tensor", "achieved": flops / (res[1][0] * 1e-3) / 1e12, "peak": peak1, "unit": "TFLOP/s",
+                         "frac": flops / (res[1][0] * 1e-3) / 1e12 / peak1, "traffic": None,
+                         "note": "5.76 TFLOP (2 N M 1920 x 60 rotations) / CUDA-event time of the one launch; peak = half the measured BURST dense bf16 "
+                                 "rate (TF32, kernel timed alone); ncu: tensor pipe 94.5 % active (profiles/r02_allpairs.txt)"},
+            "note": "extra: 60-rotation correlation max / argmax for every keypoint pair of one cloud pair (a strict superset of what the reference "
+                    "evaluates), one persistent kernel"}
+    except Exception as e:
+        out["workload_allpairs"] = {"unavailable": repr(e)}
     return out
 
 

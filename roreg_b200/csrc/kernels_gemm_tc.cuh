@@ -57,6 +57,7 @@ struct GemmArgs {
   // g_ldg != 0: the gathered operand is loaded by the producer warps with LDG.128 and stored into the swizzled tile with STS.128
   // (needs the raw activation pointers and NPROD == 8); 0: TMA tile::gather4 through the tensor maps.
   int g_ldg; const float* g_act_hi; const float* g_act_lo;
+  int dbg;   // ROREG_DEBUG_GEMM (bottleneck experiments, results WRONG): 1 = epilogue without its global loads / stores, 2 = LDG loader without the loads
 };
 
 // four rows of a 2-D tensor (box = 32 columns x 1 row) -> 4 x 128 B at dst, swizzled on the absolute shared-memory address
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
             base[j] = item * 60; tap0[j] = (int)gset_s[jj] * 13;
           }
           auto issue = [&](int kc, const float* act, float4 (&buf)[8]) {
+            if (a.dbg == 2) return;
             const int k_tap = kc / cpk, c0 = (kc - k_tap * cpk) * GM_KC + 4 * q;
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -287,7 +289,7 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
                        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
                      : "r"(taddr + c0) : "memory");
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r < a.R) {
+        if (r < a.R && a.dbg != 1) {
           // running-maximum mode: all 16 previous maxima of this chunk are loaded BEFORE any update.  Round 1 read them one by one
           // between the stores (same array: the compiler may not hoist a load above a store), i.e. 256 serialised L2 round trips
           // per thread and tile - the all-pairs GEMMs were bound by that chain, not by the tensor pipe (run c7: 355 us per launch
@@ -447,6 +449,7 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   static int gldg = -1;
   if (gldg < 0) { const char* e = getenv("ROREG_GEMM_GATHER"); gldg = (e && !strcmp(e, "tma")) ? 0 : 1; }
   a.g_ldg = gather ? gldg : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
+  if (const char* e = getenv("ROREG_DEBUG_GEMM")) a.dbg = atoi(e);
   const int nprod = gather ? (a.g_ldg ? 8 : gprod) : 4;
 #define GM_LAUNCH(NP, NPR) gemm_tc_kernel<NP, NPR><<<grid, gm_threads(NPR), GemmCfg<NP>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a)
   if (a.npass == 3) { if (nprod == 4) GM_LAUNCH(3, 4); else if (nprod == 8) GM_LAUNCH(3, 8); else GM_LAUNCH(3, 16); }
