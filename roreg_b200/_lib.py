@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libroreg_b200.so")
+# ROREG_B200_LIB: another build of the same library (e.g. the -DROREG_GEMM_TRACE debugging build)
+LIB_PATH = os.environ.get("ROREG_B200_LIB") or os.path.join(_HERE, "csrc", "libroreg_b200.so")
 
 _p = C.c_void_p
 _i = C.c_int

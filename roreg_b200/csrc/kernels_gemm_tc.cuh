@@ -10,9 +10,10 @@
 // Fused epilogue (one thread per output row, TMEM -> registers):
 //   v = acc + bias[o] (+ residual[r][o]);  raw_out[r][o] = v;  y = v*bn_scale[o] + bn_shift[o];  relu;
 //   act_hi[r][o] = tf32(y), act_lo[r][o] = y - tf32(y)      (the next layer's operands)
-// Pipeline: warps 0-3 TMA producers (SWIZZLE_128B boxes, or tile::gather4 row gathers for the implicit group convolution),
-// warp 4 MMA issuer, warps 5-8 epilogue; every operand image of a k-chunk is loaded ONCE per stage and all passes run from
-// it; two TMEM accumulators of up to 256 columns so the epilogue of tile t overlaps the MMAs of tile t+1.
+// Pipeline: one box-producer lane (SWIZZLE_128B TMA boxes), eight loader warps that gather the implicit group convolution's
+// rows with cp.async, one MMA-issuing lane, eight epilogue warps (roles and register budgets at GM_LOADERS); every operand
+// image of a k-chunk is loaded ONCE per stage and all passes run from it; two TMEM accumulators of up to 256 columns so the
+// epilogue of tile t overlaps the MMAs of tile t+1.
 #pragma once
 #include "kernels_nn_tc.cuh"
 
@@ -54,10 +55,10 @@ struct GemmArgs {
   // c0 = kc*32 % g_C) read activation row item*60 + g_nei[g][k], columns c0..c0+31 - fetched four rows per instruction with
   // cp.async.bulk.tensor ... tile::gather4 straight into the SWIZZLE_128B operand tile (Kdim = 13 * g_C).
   int g_C, g_ng; const int32_t* g_nei; const int32_t* g_set;
-  // g_ldg != 0: the gathered operand is loaded by the producer warps with LDG.128 and stored into the swizzled tile with STS.128
-  // (needs the raw activation pointers and NPROD == 8); 0: TMA tile::gather4 through the tensor maps.
-  int g_ldg; const float* g_act_hi; const float* g_act_lo;
-  int dbg;   // ROREG_DEBUG_GEMM (bottleneck experiments, results WRONG): 1 = epilogue without its global loads / stores, 2 = LDG loader without the loads
+  // g_cpasync != 0: the gathered operand is copied by the producer warps with cp.async (16 bytes per thread and row, needs the raw
+  // activation pointers); 0: TMA tile::gather4 through the tensor maps.
+  int g_cpasync; const float* g_act_hi; const float* g_act_lo;
+  long long* trace;   // ROREG_DEBUG_GEMM_TRACE=<file>: clock64 stamps [1024 k-chunk iterations][8 events] of CTA 0 (one chosen launch)
 };
 
 // four rows of a 2-D tensor (box = 32 columns x 1 row) -> 4 x 128 B at dst, swizzled on the absolute shared-memory address
@@ -67,16 +68,24 @@ __device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar) : "memory");
 }
 
-// Warp roles: NPROD producer warps, then the MMA warp, then four epilogue warps.  NPROD is a template parameter because the gather
-// issue is serialised per lane (see the producer section): 4 / 8 / 16 producer warps issue 8 / 4 / 2 gathers each per k-chunk.
-__host__ __device__ constexpr int gm_threads(int nprod) { return (nprod + 1 + 4) * 32; }
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
 
-template <int NPASS, int NPROD>
-__global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
+// Warp roles, by warpgroup so that setmaxnreg can move registers to the epilogue (run c20: the same epilogue took 59 k clk per tile
+// at 128 registers per thread and 104 k clk at 96, where ptxas spills 324 bytes):
+//   warps 0-7   A loaders (implicit group convolution only; idle in plain mode)            40 registers
+//   warps 8-15  epilogue, two per TMEM lane quadrant (warp id % 4), alternate 16-column chunks   168 registers
+//   warp 16     MMA issuer (one lane); warp 17 box producer (one lane: W, and A in plain mode); 18-19 idle   56 registers
+constexpr int GM_LOADERS = 8, GM_EPI_WARPS = 8, GM_EPI0 = GM_LOADERS, GM_MMA_WARP = GM_LOADERS + GM_EPI_WARPS, GM_BOX_WARP = GM_MMA_WARP + 1;
+constexpr int GM_THREADS = (GM_LOADERS + GM_EPI_WARPS + 4) * 32;      // 640
+
+template <int NPASS>
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
                                                          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo,
                                                          GemmArgs a) {
   using Cfg = GemmCfg<NPASS>;
-  constexpr int GM_PRODUCERS = NPROD, LANES = 32 / NPROD;     // gather lanes per producer warp
+  constexpr int LANES = 32 / GM_LOADERS;                      // gather4 lanes per loader warp
   // Shared-memory budget: static (~1.4 KB, rounded up to the array's 1 KB alignment) + 192 KB of stages + barriers = 194.3 KiB,
   // i.e. under the 196 KiB carve-out step (+1 KiB the system reserves per CTA) - see the note at nei_s.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -95,19 +104,24 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   const bool gather = a.g_C > 0;
+#ifdef ROREG_GEMM_TRACE       // debugging builds only (nvcc -DROREG_GEMM_TRACE): the guard perturbs the MMA warp's code
+#define GM_TRACE(i, e) do { if (a.trace && blockIdx.x == 0 && (i) < 1024u) a.trace[(size_t)(i) * 8 + (e)] = clock64(); } while (0)
+#else
+#define GM_TRACE(i, e) do { } while (0)
+#endif
   for (int i = threadIdx.x; i < a.Kdim / GM_KC && i < 256; i += blockDim.x) acols_s[i] = (uint16_t)(a.a_cols ? a.a_cols[i] : i * GM_KC);   // < Kdim <= 8192
   if (gather) {
     for (int i = threadIdx.x; i < 60 * 13; i += blockDim.x) nei_s[i] = (uint8_t)a.g_nei[i];
     for (int i = threadIdx.x; i < 64; i += blockDim.x) gset_s[i] = (uint8_t)((a.g_set && i < a.g_ng) ? a.g_set[i] : i);
   }
   if (threadIdx.x == 0) {
-    // full[st]: one arrival from the TMA-issuing lane (arrive.expect_tx); with the LDG loader also one per warp of the group that
-    // filled the stage's A tile (4)
-    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), (gather && a.g_ldg) ? 5 : 1); mbar_init(BAR(4 + s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), 128); }
+    // full[st]: one arrival from the box producer (arrive.expect_tx); with the cp.async loader also one per loader thread
+    // (cp.async.mbarrier.arrive.noinc: the arrival is counted here, not added by the instruction)
+    for (int s = 0; s < Cfg::STAGES; ++s) { mbar_init(BAR(s), (gather && a.g_cpasync) ? GM_LOADERS * 32 + 1 : 1); mbar_init(BAR(4 + s), 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(BAR(8 + s), 1); mbar_init(BAR(10 + s), GM_EPI_WARPS * 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == GM_PRODUCERS) {
+  if (warp == GM_MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(512) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -120,137 +134,129 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
   const int n_tiles = n_mt * a.n_ntiles;
   const int n_kc = a.Kdim / GM_KC;
   const uint32_t w_bytes = (uint32_t)a.NT * GM_KC * 4;
-  const uint32_t stage_tx = Cfg::A_IMAGES * (GM_A_BYTES + w_bytes);
   const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(a.NT >> 3) << 17) | ((uint32_t)(GM_BM >> 4) << 24);
 
-  if (warp < GM_PRODUCERS) {
-    // ===================== producers =====================
-    // Plain mode: lane 0 of warp 0 issues two (four) box loads per stage, the other producer warps have nothing to do.
-    // Gather mode: a tile::gather4 instruction takes its four row coordinates from uniform registers, so the compiler
-    // serialises lanes that hold different rows (ELECT + 6 x R2UR + UTMALDG per lane: run c5 - one warp issuing all 32 gathers
-    // of a stage took ~1300 clk per k-chunk and made GF slower than the im2col version).  The 32 gathers of a stage are
-    // therefore spread over NPROD warps: warp w, lanes 0..LANES-1 fetch the row groups w * LANES + l of the tile.  Run c11 (4 warps
-    // x 8 lanes): ~2000 clk per k-chunk in the issue loop (ELECT, 6 x R2UR.BROADCAST, UTMALDG, branch: ~250 clk per gather)
-    // against 512 clk of MMA work - the producers, not the tensor pipe or L2, paced the gather layers (tensor pipe 33 % active).
+  if (warp < GM_LOADERS) {
+    // ===================== A loaders (implicit group convolution) =====================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     const int cpk = gather ? a.g_C / GM_KC : 1;          // k-chunks per tap
-    if (gather && a.g_ldg) {
-      // ---- LDG / STS loader (run c16: the plain-mode pipeline reaches 94 % tensor-pipe activity in the all-pairs kernel, so the
-      // gather layers' 33 % was the TMA gather itself).  Two groups of four warps take alternate stages.  In a group, thread
-      // (row lane rl = t / 8, chunk q = t % 8) loads the 16-byte chunk q of rows rl + 16 j (j = 0..7): a warp instruction covers
-      // four full 128-byte activation rows, and stores it at the SWIZZLE_128B position the MMA descriptor expects (row r at
-      // (r / 8) * 1024 + (r % 8) * 128, chunk q ^ (r % 8)): four rows = four distinct 128-byte lines per STS.128, conflict-free.
-      // One pass: the loads of the group's NEXT stage are issued before the current one is stored (registers, no barrier needed).
-      if (NPROD == 8) {
-        const int grp = warp >> 2, tg = (warp & 3) * 32 + lane;
-        const int q = tg & 7, rl = tg >> 3;
-        const uint32_t sw_off = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((q ^ (rl & 7)) << 4));     // + 2048 j
-        uint32_t it0 = 0;
-        for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, it0 += (uint32_t)n_kc) {
-          const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
-          int base[8], tap0[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            int r = mt * GM_BM + rl + 16 * j;
-            if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
-            const int item = r / a.g_ng, jj = r - item * a.g_ng;
-            base[j] = item * 60; tap0[j] = (int)gset_s[jj] * 13;
-          }
-          auto issue = [&](int kc, const float* act, float4 (&buf)[8]) {
-            if (a.dbg == 2) return;
-            const int k_tap = kc / cpk, c0 = (kc - k_tap * cpk) * GM_KC + 4 * q;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              buf[j] = __ldg(reinterpret_cast<const float4*>(act + (long long)(base[j] + (int)nei_s[tap0[j] + k_tap]) * a.g_C + c0));
-          };
-          const int first = (int)((grp - (int)(it0 & 1u)) & 1);
-          float4 cur[8], nxt[8], lo[8];
-          if (first < n_kc) issue(first, a.g_act_hi, cur);
-          for (int kc = first; kc < n_kc; kc += 2) {
-            if (NPASS == 1 && kc + 2 < n_kc) issue(kc + 2, a.g_act_hi, nxt);
-            if (NPASS == 3) issue(kc, a.g_act_lo, lo);
-            const uint32_t it = it0 + (uint32_t)kc;
-            const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
-            if (lane == 0) mbar_wait(BAR(4 + st), ph ^ 1);
-            __syncwarp();
-            uint8_t* sbp = smem + st * Cfg::STAGE_BYTES;
-            if ((warp & 3) == 0 && lane == 0) {
-              const uint32_t sb = smem_u32(sbp);
-              mbar_expect_tx(BAR(st), Cfg::A_IMAGES * w_bytes);
-              tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
-              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
-            }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sbp + sw_off + 2048 * j) = cur[j];
-            if (NPASS == 3) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) *reinterpret_cast<float4*>(sbp + Cfg::OFF_ALO + sw_off + 2048 * j) = lo[j];
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy writes -> visible to tcgen05
-            __syncwarp();
-            if (lane == 0) mbar_arrive(BAR(st));
-            if (NPASS == 1) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
-            } else if (kc + 2 < n_kc) {
-              issue(kc + 2, a.g_act_hi, cur);
-            }
-          }
-        }
-      }
-    } else if (gather || warp == 0) {
+    if (gather && a.g_cpasync) {
+      // ---- cp.async loader.  Timeline of run c19 (clock64 trace, profiles/r02_gemm_timeline.txt): a tile::gather4 stage
+      // completes ~4500 clk after its issue and the four stages in flight turn over every ~1400-1570 clk against ~800 clk of MMA
+      // work - the TMA unit spends ~35 clk per gather4 (4 rows) where a tiled box costs ~2 clk per row.  A register-staged
+      // LDG.128 -> STS.128 loader was slower still (its L2 round trip sits on the loader's critical path).  cp.async needs no
+      // registers and no waiting: every loader thread copies the 16-byte chunk q = t % 8 of rows t / 8 + 32 j straight to
+      // the SWIZZLE_128B position the MMA descriptor expects (row r at (r / 8) * 1024 + (r % 8) * 128, chunk q ^ (r % 8): a
+      // warp instruction reads four whole 128-byte activation rows and writes four distinct 128-byte lines), then posts
+      // cp.async.mbarrier.arrive.noinc on the stage's full barrier, which fires when its copies have landed.  The loaders run as
+      // far ahead as the empty barriers allow (4 / 2 stages).
+      constexpr int RSTEP = GM_LOADERS * 4, NJ = GM_BM / RSTEP;     // rows covered per pass of the loader threads; passes per tile
+      const int tg = warp * 32 + lane;
+      const int q = tg & 7, rl = tg >> 3;
+      const uint32_t sw_off = (uint32_t)((rl >> 3) * 1024 + (rl & 7) * 128 + ((q ^ (rl & 7)) << 4));     // + (RSTEP / 8) * 1024 * j
       uint32_t it = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
-        int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
-        if (gather && lane < LANES) {
+        const int mt = t / a.n_ntiles;
+        int base[NJ], tap0[NJ];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            int r = mt * GM_BM + 4 * (warp * LANES + lane) + i;
-            if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
-            const int item = r / a.g_ng, j = r - item * a.g_ng;
-            base[i] = item * 60; tap0[i] = (int)gset_s[j] * 13;
-          }
+        for (int j = 0; j < NJ; ++j) {
+          int r = mt * GM_BM + rl + RSTEP * j;
+          if (r >= a.R) r = a.R - 1;                   // rows past the end: any valid row (their outputs are masked)
+          const int item = r / a.g_ng, jj = r - item * a.g_ng;
+          base[j] = item * 60; tap0[j] = (int)gset_s[jj] * 13;
         }
         int k_tap = 0, k_sub = 0;                        // kc = k_tap * cpk + k_sub
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
           if (lane == 0) mbar_wait(BAR(4 + st), ph ^ 1);  // one poller per warp
           __syncwarp();
+          if (tg == 0) GM_TRACE(it, 0);
           const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
-          if (warp == 0 && lane == 0) {
-            mbar_expect_tx(BAR(st), stage_tx);
-            tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
-            if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
-            if (!gather) {
-              tma_load_2d(sb, &mapAhi, (int)acols_s[kc], mt * GM_BM, BAR(st));
-              if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, (int)acols_s[kc], mt * GM_BM, BAR(st));
-            }
+          const int c0 = k_sub * GM_KC + 4 * q;
+#pragma unroll
+          for (int j = 0; j < NJ; ++j) {
+            const long long off = (long long)(base[j] + (int)nei_s[tap0[j] + k_tap]) * a.g_C + c0;
+            const uint32_t dst = sb + sw_off + (uint32_t)(RSTEP / 8 * 1024 * j);
+            cp_async16(dst, a.g_act_hi + off);
+            if (NPASS == 3) cp_async16(dst + Cfg::OFF_ALO, a.g_act_lo + off);
           }
-          if (gather) {
-            if (lane < LANES) {
-              const int c0 = k_sub * GM_KC;
-              const int r0 = base[0] + (int)nei_s[tap0[0] + k_tap], r1 = base[1] + (int)nei_s[tap0[1] + k_tap];
-              const int r2 = base[2] + (int)nei_s[tap0[2] + k_tap], r3 = base[3] + (int)nei_s[tap0[3] + k_tap];
-              const uint32_t dst = sb + (warp * LANES + lane) * 512;
-              tma_gather4(dst, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
-              if (NPASS == 3) tma_gather4(dst + Cfg::OFF_ALO, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
-            }
-            if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(BAR(st)) : "memory");
+          if (tg == 0) GM_TRACE(it, 1);
+          if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
+        }
+      }
+    } else if (gather) {
+      // ---- TMA tile::gather4 loader (ROREG_GEMM_GATHER=tma, kept for A/B runs).  The instruction takes its four row coordinates
+      // from uniform registers, so the compiler serialises lanes that hold different rows (ELECT + 6 x R2UR + UTMALDG per lane):
+      // the 32 gathers of a stage are spread over the 8 loader warps, 4 lanes each.
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int mt = t / a.n_ntiles;
+        int base[4] = {0, 0, 0, 0}, tap0[4] = {0, 0, 0, 0};
+        if (lane < LANES) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            int r = mt * GM_BM + 4 * (warp * LANES + lane) + i;
+            if (r >= a.R) r = a.R - 1;
+            const int item = r / a.g_ng, j = r - item * a.g_ng;
+            base[i] = item * 60; tap0[i] = (int)gset_s[j] * 13;
           }
+        }
+        int k_tap = 0, k_sub = 0;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
+          if (lane == 0) mbar_wait(BAR(4 + st), ph ^ 1);
+          __syncwarp();
+          if (warp == 0 && lane == 0) GM_TRACE(it, 0);
+          const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          if (lane < LANES) {
+            const int c0 = k_sub * GM_KC;
+            const int r0 = base[0] + (int)nei_s[tap0[0] + k_tap], r1 = base[1] + (int)nei_s[tap0[1] + k_tap];
+            const int r2 = base[2] + (int)nei_s[tap0[2] + k_tap], r3 = base[3] + (int)nei_s[tap0[3] + k_tap];
+            const uint32_t dst = sb + (warp * LANES + lane) * 512;
+            tma_gather4(dst, &mapAhi, c0, r0, r1, r2, r3, BAR(st));
+            if (NPASS == 3) tma_gather4(dst + Cfg::OFF_ALO, &mapAlo, c0, r0, r1, r2, r3, BAR(st));
+          }
+          if (warp == 0 && lane == 0) GM_TRACE(it, 1);
+          if (++k_sub == cpk) { k_sub = 0; ++k_tap; }
         }
       }
     }
-  } else if (warp == GM_PRODUCERS) {
-    if (lane == 0) {
+  } else if (warp >= GM_MMA_WARP) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    if (warp == GM_BOX_WARP && lane == 0) {
+      // ===================== box producer: W every stage; A too in plain mode =====================
+      // expected bytes of a stage: everything that completes on the barrier by TMA (W; A unless cp.async brings it)
+      const uint32_t stage_tx = Cfg::A_IMAGES * (w_bytes + ((gather && a.g_cpasync) ? 0u : (uint32_t)GM_A_BYTES));
+      uint32_t it = 0;
+      for (int t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
+        for (int kc = 0; kc < n_kc; ++kc, ++it) {
+          const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
+          mbar_wait(BAR(4 + st), ph ^ 1);
+          const uint32_t sb = smem_u32(smem + st * Cfg::STAGE_BYTES);
+          mbar_expect_tx(BAR(st), stage_tx);
+          tma_load_2d(sb + Cfg::OFF_WHI, &mapWhi, kc * GM_KC, nt * a.NT, BAR(st));
+          if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_WLO, &mapWlo, kc * GM_KC, nt * a.NT, BAR(st));
+          if (!gather) {
+            tma_load_2d(sb, &mapAhi, (int)acols_s[kc], mt * GM_BM, BAR(st));
+            if (NPASS == 3) tma_load_2d(sb + Cfg::OFF_ALO, &mapAlo, (int)acols_s[kc], mt * GM_BM, BAR(st));
+          }
+        }
+      }
+    } else if (warp == GM_MMA_WARP && lane == 0) {
       uint32_t it = 0, it_t = 0;
       for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it_t) {
         const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
         mbar_wait(BAR(10 + acc), tph ^ 1);
+        GM_TRACE(it_t, 6);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + acc * 256;
         for (int kc = 0; kc < n_kc; ++kc, ++it) {
           const int st = it % Cfg::STAGES; const uint32_t ph = (it / Cfg::STAGES) & 1;
           mbar_wait(BAR(st), ph);
+          GM_TRACE(it, 2);
+          if (gather && a.g_cpasync) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) writes -> tcgen05 reads
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t sa = smem_u32(smem + st * Cfg::STAGE_BYTES);
           const uint32_t whi = sa + Cfg::OFF_WHI;
@@ -267,29 +273,28 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
               umma_tf32(d_tmem, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(wlo + kk * 32), idesc, 1u);
           }
           umma_commit(BAR(4 + st));
+          GM_TRACE(it, 3);
         }
         umma_commit(BAR(8 + acc));
       }
     }
   } else {
-    const int q = warp & 3;
+    // ===================== epilogue =====================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int q = warp & 3, half = (warp - GM_EPI0) >> 2;     // TMEM lane quadrant of this warp (warp id % 4); chunk parity
     const int row_in_tile = q * 32 + lane;
     uint32_t it_t = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it_t) {
       const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
       const int acc = it_t & 1; const uint32_t tph = (it_t >> 1) & 1;
       mbar_wait(BAR(8 + acc), tph);
+      if (warp == GM_EPI0 && lane == 0) GM_TRACE(it_t, 4);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const long long r = (long long)mt * GM_BM + row_in_tile;
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
-      for (int c0 = 0; c0 < a.NT; c0 += 16) {
-        uint32_t v[16];
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-                     : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                       "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                     : "r"(taddr + c0) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (r < a.R && a.dbg != 1) {
+      // one 16-column chunk of the accumulator row (v) -> bias / residual / running max / BN / ReLU / split -> global
+      auto process = [&](const uint32_t (&v)[16], const int c0) {
+        if (r < a.R) {
           // running-maximum mode: all 16 previous maxima of this chunk are loaded BEFORE any update.  Round 1 read them one by one
           // between the stores (same array: the compiler may not hoist a load above a store), i.e. 256 serialised L2 round trips
           // per thread and tile - the all-pairs GEMMs were bound by that chain, not by the tensor pipe (run c7: 355 us per launch
@@ -378,13 +383,37 @@ __global__ void __launch_bounds__(gm_threads(NPROD), 1) gemm_tc_kernel(const __g
             }
           }
         }
+      };
+      // The two warps of a lane quadrant take alternate chunks; the tcgen05.ld of a warp's next chunk is in flight while it works on
+      // the current one (run c19: 84 k clk of epilogue per 128 x 256 tile with four warps and serial loads - more than the tile's
+      // 78 k clk of MMA work in the 256-channel layers).
+#define GM_LDTM(V, C0) asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];" \
+                     : "=r"(V[0]), "=r"(V[1]), "=r"(V[2]), "=r"(V[3]), "=r"(V[4]), "=r"(V[5]), "=r"(V[6]), "=r"(V[7]), \
+                       "=r"(V[8]), "=r"(V[9]), "=r"(V[10]), "=r"(V[11]), "=r"(V[12]), "=r"(V[13]), "=r"(V[14]), "=r"(V[15]) \
+                     : "r"(taddr + (C0)) : "memory")
+      uint32_t va[16], vb[16];
+      int c0 = 16 * half;
+      if (c0 < a.NT) GM_LDTM(va, c0);
+      while (c0 < a.NT) {
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 < a.NT) GM_LDTM(vb, c0 + 32);
+        process(va, c0);
+        c0 += 32;
+        if (c0 >= a.NT) break;
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        if (c0 + 32 < a.NT) GM_LDTM(va, c0 + 32);
+        process(vb, c0);
+        c0 += 32;
       }
+#undef GM_LDTM
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(BAR(10 + acc));
+      if (warp == GM_EPI0 && lane == 0) GM_TRACE(it_t, 5);
     }
   }
+#undef GM_TRACE
   __syncthreads();
-  if (warp == GM_PRODUCERS) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
+  if (warp == GM_MMA_WARP) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(512) : "memory");
 }
 
 static inline int gemm_make_map(roreg_ctx* c, CUtensorMap* m, const float* base, long long rows, int kdim, int box_rows) {
@@ -432,30 +461,36 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   if ((rc = gemm_make_map(c, &mWl, W_lo ? W_lo : W_hi, w_rows, a.Kdim, a.NT))) return rc;
   static unsigned long long attr_mask = 0;
   if (rr_first_use_on_device(&attr_mask, c->device)) {
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
-    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<1>::SMEM_BYTES));
+    RR_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, GemmCfg<3>::SMEM_BYTES));
   }
   const int n_mt = (a.R + GM_BM - 1) / GM_BM;
   const long long tiles = (long long)n_mt * a.n_ntiles;
   const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
-  // producer warps: plain mode needs one issuing lane (4 = the smallest instantiation); gather mode: ROREG_GEMM_PRODUCERS = 4 | 8 | 16
-  static int gprod = 0;
-  if (!gprod) { const char* e = getenv("ROREG_GEMM_PRODUCERS"); const int v = e ? atoi(e) : 8; gprod = (v == 4 || v == 16) ? v : 8; }
-  // gathered operand: ROREG_GEMM_GATHER=tma selects the TMA tile::gather4 producer, default = the LDG / STS loader (8 producer warps)
-  static int gldg = -1;
-  if (gldg < 0) { const char* e = getenv("ROREG_GEMM_GATHER"); gldg = (e && !strcmp(e, "tma")) ? 0 : 1; }
-  a.g_ldg = gather ? gldg : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
-  if (const char* e = getenv("ROREG_DEBUG_GEMM")) a.dbg = atoi(e);
-  const int nprod = gather ? (a.g_ldg ? 8 : gprod) : 4;
-#define GM_LAUNCH(NP, NPR) gemm_tc_kernel<NP, NPR><<<grid, gm_threads(NPR), GemmCfg<NP>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a)
-  if (a.npass == 3) { if (nprod == 4) GM_LAUNCH(3, 4); else if (nprod == 8) GM_LAUNCH(3, 8); else GM_LAUNCH(3, 16); }
-  else              { if (nprod == 4) GM_LAUNCH(1, 4); else if (nprod == 8) GM_LAUNCH(1, 8); else GM_LAUNCH(1, 16); }
-#undef GM_LAUNCH
+  // gathered operand: cp.async loader by default; ROREG_GEMM_GATHER=tma selects the TMA tile::gather4 producer (A/B runs)
+  static int gcp = -1;
+  if (gcp < 0) { const char* e = getenv("ROREG_GEMM_GATHER"); gcp = (e && !strcmp(e, "tma")) ? 0 : 1; }
+  a.g_cpasync = gather ? gcp : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
+  // timeline of one gather launch (debugging only): ROREG_DEBUG_GEMM_TRACE=<file>, ROREG_DEBUG_GEMM_TRACE_LAUNCH=<index among the gather launches>
+  static int trace_seen = 0; long long* d_trace = nullptr; const char* trace_fn = getenv("ROREG_DEBUG_GEMM_TRACE");
+  if (trace_fn && gather) {
+    const char* e = getenv("ROREG_DEBUG_GEMM_TRACE_LAUNCH");
+    if (trace_seen++ == (e ? atoi(e) : 0)) { RR_CUDA(c, cudaMalloc(&d_trace, 1024 * 8 * sizeof(long long))); RR_CUDA(c, cudaMemset(d_trace, 0, 1024 * 8 * sizeof(long long))); }
+  }
+  a.trace = d_trace;
+  if (a.npass == 3) gemm_tc_kernel<3><<<grid, GM_THREADS, GemmCfg<3>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
+  else              gemm_tc_kernel<1><<<grid, GM_THREADS, GemmCfg<1>::SMEM_BYTES, st>>>(mAh, mAl, mWh, mWl, a);
   RR_LAUNCH_CHECK(c);
+  if (d_trace) {
+    RR_CUDA(c, cudaStreamSynchronize(st));
+    static long long h[1024 * 8];
+    RR_CUDA(c, cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost)); cudaFree(d_trace);
+    if (FILE* f = fopen(trace_fn, "w")) {
+      fprintf(f, "# R=%d Kdim=%d O=%d NT=%d npass=%d C=%d ng=%d cpasync=%d grid=%d\n", a.R, a.Kdim, a.O, a.NT, a.npass, a.g_C, a.g_ng, a.g_cpasync, grid);
+      for (int i = 0; i < 1024; ++i) { for (int e2 = 0; e2 < 8; ++e2) fprintf(f, "%lld ", h[i * 8 + e2]); fprintf(f, "\n"); }
+      fclose(f);
+    }
+  }
   return ROREG_OK;
 }
 

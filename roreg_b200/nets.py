@@ -104,7 +104,7 @@ class GroupNets:
 class GFNet(GroupNets):
     """Group_feat_network.forward (network/group_feat.py:26-45): [n,32,60] -> eqv [n,32,60]."""
 
-    def __init__(self, ctx, sd, prefix="PartI_net.", npass=3, chunk=500):
+    def __init__(self, ctx, sd, prefix="PartI_net.", npass=3, chunk=5000):
         super().__init__(ctx, npass)
         p = prefix
         self.chunk = chunk
@@ -133,7 +133,7 @@ class ETNet(GroupNets):
     """ET_test.forward (network/eqv_trans.py:119-138) -> unit quaternions [K,4].  Only group element 0 of the FC
     head is used (:136), so the last residual conv is evaluated at g = 0 and the middle one at its 13 neighbours."""
 
-    def __init__(self, ctx, sd, npass=3, chunk=1000):
+    def __init__(self, ctx, sd, npass=3, chunk=5000):
         super().__init__(ctx, npass)
         self.chunk = chunk
         self.bn0 = bn_fold(sd, "Conv_init.comb_layer.0"); self.L0 = Layer(ctx, sd["Conv_init.comb_layer.2.weight"], sd["Conv_init.comb_layer.2.bias"])
@@ -171,7 +171,7 @@ class ETNet(GroupNets):
 class RDNet(GroupNets):
     """detector_eqv_test.forward (network/rot_detect.py:43-55): GF-out descriptors [n,32,60] -> saliency [n]."""
 
-    def __init__(self, ctx, sd, npass=3, chunk=1000):
+    def __init__(self, ctx, sd, npass=3, chunk=5000):
         super().__init__(ctx, npass)
         self.chunk = chunk
         r = "eqv_encoder.0"

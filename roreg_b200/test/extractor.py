@@ -27,7 +27,7 @@ class yoho_des():
         self.net = None
 
     def _load_model(self):
-        self.net = nets.GFNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass, chunk=min(500, int(self.test_batch_size)))
+        self.net = nets.GFNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass, chunk=max(5000, int(self.test_batch_size)))   # bs_GF is the reference's memory knob; the output does not depend on the chunking (eval-mode BN)
 
     def run(self, dataset):
         self._load_model()

@@ -27,15 +27,15 @@ def timed(fn, reps=5, warm=2):
 x = rng.standard_normal((5000, 32, 60)).astype(np.float32); x /= np.linalg.norm(x, axis=1, keepdims=True)
 xd = ctx.dev(x)
 for npass in (1, 3):
-    gf = nets.GFNet(ctx, synth.random_weights("GF", 101), npass=npass, chunk=500)
+    gf = nets.GFNet(ctx, synth.random_weights("GF", 101), npass=npass)
     ms, ln = timed(lambda: gf.forward(xd))
     print(f"GF 5000 keypoints, npass {npass}: {ms:.2f} ms, {ln:.0f} launches, {2.17e12 / (ms * 1e-3) / 1e12:.0f} TFLOP/s algorithmic (434 MFLOP/keypoint)")
     K = 3400
     rows = ctx.dev(rng.integers(0, 5000, K).astype(np.int32)); pre = ctx.dev(rng.integers(0, 60, K).astype(np.int32))
-    et = nets.ETNet(ctx, synth.random_weights("ET", 102), npass=npass, chunk=1000)
+    et = nets.ETNet(ctx, synth.random_weights("ET", 102), npass=npass, chunk=4000)
     ms, ln = timed(lambda: et.forward(xd, rows, xd, rows, xd, rows, xd, rows, pre))
     print(f"ET {K} matches, npass {npass}: {ms:.2f} ms, {ln:.0f} launches, {K * 99.2e6 / (ms * 1e-3) / 1e12:.0f} TFLOP/s algorithmic (99.2 MFLOP/match pruned)")
-    rd = nets.RDNet(ctx, synth.random_weights("RD", 103), npass=npass, chunk=1000)
+    rd = nets.RDNet(ctx, synth.random_weights("RD", 103), npass=npass)
     ms, ln = timed(lambda: rd.forward(xd))
     print(f"RD 5000 keypoints, npass {npass}: {ms:.2f} ms, {ln:.0f} launches")
     pr = synth.make_pair(2, n=5000)
