@@ -283,6 +283,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int q = warp & 3, half = (warp - GM_EPI0) >> 2;     // TMEM lane quadrant of this warp (warp id % 4); chunk parity
     const int row_in_tile = q * 32 + lane;
+    // 16-byte accesses of whole chunks are possible when every row pitch is a multiple of 4 floats and every base is 16-byte aligned
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+    const bool vec_ok = !a.amax_arg && ((a.NT & 15) == 0) &&
+                        (!a.bias || al16(a.bias)) && (!a.residual || (al16(a.residual) && (a.res_ld & 3) == 0)) &&
+                        (!a.raw_out || (al16(a.raw_out) && (a.raw_ld & 3) == 0)) &&
+                        (!a.act_hi || (al16(a.act_hi) && (a.act_ld & 3) == 0 && (!a.act_lo || al16(a.act_lo)))) &&
+                        (!a.bn_scale || (al16(a.bn_scale) && al16(a.bn_shift)));
     uint32_t it_t = 0;
     for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it_t) {
       const int mt = t / a.n_ntiles, nt = t % a.n_ntiles;
@@ -294,7 +301,57 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * 256;
       // one 16-column chunk of the accumulator row (v) -> bias / residual / running max / BN / ReLU / split -> global
       auto process = [&](const uint32_t (&v)[16], const int c0) {
-        if (r < a.R) {
+        const int o0 = nt * a.NT + c0;
+        if (r < a.R && vec_ok && o0 + 16 <= a.O) {
+          // Fast path (whole chunk in range, 16-byte aligned rows, no running maximum): ~150 instructions.  The general path below
+          // tests every element and loads every bias / BN parameter on its own - 1840 instructions per chunk (ncu source view,
+          // run c23), which made the epilogue (60-76 k clk per tile) the limit of every layer with fewer than ~90 k-chunks.
+          float x[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+          if (a.bias) {
+            const float4* pb = reinterpret_cast<const float4*>(a.bias + o0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 w = __ldg(pb + k); x[4 * k] += w.x; x[4 * k + 1] += w.y; x[4 * k + 2] += w.z; x[4 * k + 3] += w.w; }
+          }
+          if (a.residual) {
+            const float4* pr = reinterpret_cast<const float4*>(a.residual + r * a.res_ld + o0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) { const float4 w = __ldcg(pr + k); x[4 * k] += w.x; x[4 * k + 1] += w.y; x[4 * k + 2] += w.z; x[4 * k + 3] += w.w; }
+          }
+          if (a.raw_out) {
+            float4* po = reinterpret_cast<float4*>(a.raw_out + r * a.raw_ld + o0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) po[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
+          }
+          if (a.act_hi) {
+            if (a.bn_scale) {
+              const float4* ps = reinterpret_cast<const float4*>(a.bn_scale + o0);
+              const float4* pt = reinterpret_cast<const float4*>(a.bn_shift + o0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const float4 sc = __ldg(ps + k), sh = __ldg(pt + k);
+                x[4 * k] = fmaf(x[4 * k], sc.x, sh.x); x[4 * k + 1] = fmaf(x[4 * k + 1], sc.y, sh.y);
+                x[4 * k + 2] = fmaf(x[4 * k + 2], sc.z, sh.z); x[4 * k + 3] = fmaf(x[4 * k + 3], sc.w, sh.w);
+              }
+            }
+            float hi[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (a.relu) x[j] = fmaxf(x[j], 0.f);
+              uint32_t tb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tb) : "f"(x[j]));
+              hi[j] = __uint_as_float(tb);
+            }
+            float4* ph = reinterpret_cast<float4*>(a.act_hi + r * a.act_ld + o0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) ph[k] = make_float4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+            if (a.act_lo) {
+              float4* pl = reinterpret_cast<float4*>(a.act_lo + r * a.act_ld + o0);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) pl[k] = make_float4(x[4 * k] - hi[4 * k], x[4 * k + 1] - hi[4 * k + 1], x[4 * k + 2] - hi[4 * k + 2], x[4 * k + 3] - hi[4 * k + 3]);
+            }
+          }
+        } else if (r < a.R) {
           // running-maximum mode: all 16 previous maxima of this chunk are loaded BEFORE any update.  Round 1 read them one by one
           // between the stores (same array: the compiler may not hoist a load above a store), i.e. 256 serialised L2 round trips
           // per thread and tile - the all-pairs GEMMs were bound by that chain, not by the tensor pipe (run c7: 355 us per launch
