@@ -14,6 +14,7 @@ the device (counter-based RNG), so poses agree with the host-RNG plugins statist
 matcher) and the yohoo estimator are per-pair network paths and stay with their plugins.
 """
 import concurrent.futures as cf
+import os
 import threading
 import numpy as np
 import torch
@@ -41,18 +42,38 @@ class AsyncWriter:
         self.pending = []
 
 
-def _read_npy_into(path, dst):
-    """Read a C-ordered .npy file straight into `dst` (a NumPy view of pinned host memory): header parsed with numpy.lib.format,
-    payload read with readinto - one copy (page cache -> pinned buffer), the GIL released while it runs."""
+def _open_npy(path, dst):
+    """Open a C-ordered .npy file whose array must match `dst` (dtype, shape); returns (fd, payload offset).  Header parsed with
+    numpy.lib.format."""
     with open(path, "rb") as f:
         major, _ = np.lib.format.read_magic(f)
         shape, fortran, dtype = (np.lib.format.read_array_header_1_0 if major == 1 else np.lib.format.read_array_header_2_0)(f)
         if fortran or dtype != dst.dtype or tuple(shape) != tuple(dst.shape):
             raise ValueError(f"{path}: {dtype} {shape} (fortran={fortran}), expected C-ordered {dst.dtype} {dst.shape}")
-        buf = dst.reshape(-1).view(np.uint8)
-        got = f.readinto(memoryview(buf))
-        if got != buf.nbytes:
-            raise ValueError(f"{path}: truncated ({got} of {buf.nbytes} bytes)")
+        return os.open(path, os.O_RDONLY), f.tell()
+
+
+def _pread_into(fd, buf, off, path):
+    """pread the whole of `buf` (a uint8 NumPy view) from file offset `off`; the GIL is released while the kernel copies."""
+    mv, done = memoryview(buf), 0
+    while done < len(mv):
+        got = os.preadv(fd, [mv[done:]], off + done)
+        if got <= 0:
+            raise ValueError(f"{path}: truncated ({off + done} of {off + len(mv)} bytes)")
+        done += got
+
+
+READ_CHUNK = 8 << 20      # bytes per reader task: one ~40 MB cloud is split over five threads, so clouds arrive in order and early
+
+
+def _read_npy_into(path, dst):
+    """Read a C-ordered .npy file straight into `dst` (a NumPy view of pinned host memory): one copy (page cache -> pinned
+    buffer).  Single-threaded form of what SceneLoader does with its reader pool."""
+    fd, off = _open_npy(path, dst)
+    try:
+        _pread_into(fd, dst.reshape(-1).view(np.uint8), off, path)
+    finally:
+        os.close(fd)
 
 
 class SceneLoader(threading.Thread):
@@ -109,40 +130,54 @@ class SceneLoader(threading.Thread):
         if self.on_gpu:
             torch.cuda.set_device(self.ctx.device)
 
-        def read(i, b):
+        def submit(pool, i, b):
+            """Split cloud i's file into READ_CHUNK tasks filling pinned buffer b; returns (fd, futures)."""
+            path = self.lay.yoho_desc(ids[i])
             try:
-                _read_npy_into(self.lay.yoho_desc(ids[i]), views[b])
+                fd, off = _open_npy(path, views[b])
             except ValueError as e:
                 raise ValueError(f"cloud {ids[i]}: {e} (the arena holds clouds of {n} keypoints; the reference's caches are 5000 per cloud)")
-            return i
+            flat = views[b].reshape(-1).view(np.uint8)
+            return fd, [pool.submit(_pread_into, fd, flat[o:o + READ_CHUNK], off + o, path) for o in range(0, flat.nbytes, READ_CHUNK)]
 
         with cf.ThreadPoolExecutor(max_workers=self.readers) as pool:
             pending = {}
             nxt = 0
-            for b in range(ring):                               # prime the ring
-                pending[b] = pool.submit(read, nxt, b); nxt += 1
-            for done in range(len(ids)):
-                b = done % ring                                 # buffers complete in submission order
-                i = pending.pop(b).result()
-                k = self.dataset.get_kps(ids[i])
-                if k.shape != (n, 3):
-                    raise ValueError(f"cloud {ids[i]}: {k.shape} keypoints, the arena holds clouds of {n} keypoints")
-                kt = torch.from_numpy(np.ascontiguousarray(k, np.float64))
-                if self.on_gpu:
-                    with torch.cuda.stream(self.side):
-                        self.desc[i].copy_(self.pinned[b], non_blocking=True)
-                        self.keys[i].copy_(kt)
-                        free[b].record(self.side)
-                        self.uploaded[i].record(self.side)
-                else:
-                    self.desc[i].copy_(self.pinned[b]); self.keys[i].copy_(kt)
-                with self.cv:
-                    self.count = done + 1
-                    self.cv.notify_all()
-                if nxt < len(ids):
+            try:
+                for b in range(ring):                               # prime the ring (tasks run in submission order: cloud 0 first)
+                    pending[b] = submit(pool, nxt, b); nxt += 1
+                for done in range(len(ids)):
+                    b = done % ring                                 # buffers complete in submission order
+                    fd, futs = pending.pop(b)
+                    try:
+                        for f in futs:
+                            f.result()
+                    finally:
+                        os.close(fd)
+                    i = done
+                    k = self.dataset.get_kps(ids[i])
+                    if k.shape != (n, 3):
+                        raise ValueError(f"cloud {ids[i]}: {k.shape} keypoints, the arena holds clouds of {n} keypoints")
+                    kt = torch.from_numpy(np.ascontiguousarray(k, np.float64))
                     if self.on_gpu:
-                        free[b].synchronize()                   # the copy out of this buffer has finished: refill it
-                    pending[b] = pool.submit(read, nxt, b); nxt += 1
+                        with torch.cuda.stream(self.side):
+                            self.desc[i].copy_(self.pinned[b], non_blocking=True)
+                            self.keys[i].copy_(kt)
+                            free[b].record(self.side)
+                            self.uploaded[i].record(self.side)
+                    else:
+                        self.desc[i].copy_(self.pinned[b]); self.keys[i].copy_(kt)
+                    with self.cv:
+                        self.count = done + 1
+                        self.cv.notify_all()
+                    if nxt < len(ids):
+                        if self.on_gpu:
+                            free[b].synchronize()                   # the copy out of this buffer has finished: refill it
+                        pending[b] = submit(pool, nxt, b); nxt += 1
+            finally:
+                for fd, futs in pending.values():                   # error path: let the outstanding reads finish, then close
+                    cf.wait(futs)
+                    os.close(fd)
 
     def wait(self, k):
         """Block until clouds [0, k) are enqueued for upload; the current stream then waits for the last of them."""

@@ -24,9 +24,9 @@ def context(cfg=None):
 
 
 def make_non_exists_dir(fn):
-    """utils/utils.py:9-11"""
-    if not os.path.exists(fn):
-        os.makedirs(fn)
+    """utils/utils.py:9-11; exist_ok because several ranks of a sharded run create the same result directories at the same time
+    (the reference's check-then-create is single-process)."""
+    os.makedirs(fn, exist_ok=True)
 
 
 def feature_dataset_name(dataset):

@@ -72,17 +72,22 @@ def test_scene_driver_rd_sampling_on_host(tmp_path, monkeypatch):
 def _worker(rank, world, port, cache, q):
     import sys
     sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import traceback
     import torch.distributed as dist
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
-    dist.init_process_group("gloo", rank=rank, world_size=world)
-    import _host_ctx as hc
-    from roreg_b200 import scene, synth as sy
-    ds = sy.SynthDataset([86, 87, 88], n=200, name="synth/sharded", with_fcgf=False)
-    np.random.seed(5)
-    res = scene.register_scene(_cfg(cache), ds, keynum=200, max_iter=100, batch_pairs=1, nn_mode=0, ctx=hc.HostContext())
-    q.put((rank, res["lo"], res["hi"], res["poses"]))
-    dist.barrier()
-    dist.destroy_process_group()
+    try:
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        import _host_ctx as hc
+        from roreg_b200 import scene, synth as sy
+        ds = sy.SynthDataset([86, 87, 88], n=200, name="synth/sharded", with_fcgf=False)
+        np.random.seed(5)
+        res = scene.register_scene(_cfg(cache), ds, keynum=200, max_iter=100, batch_pairs=1, nn_mode=0, ctx=hc.HostContext())
+        q.put((rank, res["lo"], res["hi"], res["poses"]))
+        dist.barrier()
+        dist.destroy_process_group()
+    except BaseException:
+        q.put((rank, "error", traceback.format_exc(), None))       # a failing rank is reported at once, not by the queue's timeout
+        raise
 
 
 def test_scene_driver_world2_gloo(tmp_path):
@@ -93,8 +98,10 @@ def test_scene_driver_world2_gloo(tmp_path):
     port = 31500 + (os.getpid() % 2000)
     procs = [ctx.Process(target=_worker, args=(r, 2, port, cache, q)) for r in range(2)]
     for p in procs: p.start()
-    res = sorted([q.get(timeout=300) for _ in procs])
+    res = [q.get(timeout=300) for _ in procs]
     for p in procs: p.join(timeout=120)
+    assert not [r for r in res if r[1] == "error"], "\n".join(r[2] for r in res if r[1] == "error")
+    res = sorted(res, key=lambda r: r[0])
     assert [(r[1], r[2]) for r in res] == [(0, 2), (2, 3)]                 # 3 pairs over 2 ranks
     _check_contract(cache, ds, 200, 100)                                   # every pair's files + rank 0's pre.log
     for rank, lo, hi, poses in res:
