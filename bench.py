@@ -422,6 +422,7 @@ def scene_e2e(args, ctx, rank, world, barrier):
     n_clouds, n_pairs = (8, 12) if args.value_only else (args.scene_clouds, args.scene_pairs)
     cores = len(os.sched_getaffinity(0))
     readers = max(2, min(12, cores // max(1, world) - 1))        # file-reader threads of this rank (the ranks share the host's cores)
+    readers = int(os.environ.get("ROREG_SCENE_READERS", readers))
     need = n_clouds * args.n * 7680 * 1.1
     root = None
     for cand in ("/dev/shm", tempfile.gettempdir()):

@@ -525,9 +525,8 @@ static inline int gemm_tc_launch(roreg_ctx* c, const float* A_hi, const float* A
   const long long tiles = (long long)n_mt * a.n_ntiles;
   const int grid = (int)(tiles < c->sm_count ? tiles : c->sm_count);
   // gathered operand: cp.async loader by default; ROREG_GEMM_GATHER=tma selects the TMA tile::gather4 producer (A/B runs)
-  static int gcp = -1;
-  if (gcp < 0) { const char* e = getenv("ROREG_GEMM_GATHER"); gcp = (e && !strcmp(e, "tma")) ? 0 : 1; }
-  a.g_cpasync = gather ? gcp : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
+  const char* gsel = gather ? getenv("ROREG_GEMM_GATHER") : nullptr;        // read per launch: the tests flip it
+  a.g_cpasync = (gather && !(gsel && !strcmp(gsel, "tma"))) ? 1 : 0; a.g_act_hi = A_hi; a.g_act_lo = A_lo ? A_lo : A_hi;
   // timeline of one gather launch (debugging only): ROREG_DEBUG_GEMM_TRACE=<file>, ROREG_DEBUG_GEMM_TRACE_LAUNCH=<index among the gather launches>
   static int trace_seen = 0; long long* d_trace = nullptr; const char* trace_fn = getenv("ROREG_DEBUG_GEMM_TRACE");
   if (trace_fn && gather) {

@@ -73,6 +73,27 @@ def test_gf_net_single_pass_tf32(ctx, tables):
     assert np.abs(got - ref).max() < 5e-3            # one TF32 pass: the reference's own cuDNN arithmetic class, not parity-grade
 
 
+@pytest.mark.parametrize("npass", [1, 3])
+def test_gather_producers_agree_bitwise(ctx, npass, monkeypatch):
+    """The implicit group convolution's two operand producers (cp.async row copies - the default - and TMA tile::gather4) fill the
+    same shared-memory image: every layer output must be IDENTICAL, at a size with several tiles per CTA, ragged last tile, and
+    three chunks (the cp.async data reaches the tensor core through a proxy fence: a missed fence would show here as stale rows)."""
+    from roreg_b200 import nets
+    sd = O.random_state_dict("GF", 33)
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((1111, 32, 60)).astype(np.float32); x /= np.linalg.norm(x, axis=1, keepdims=True)
+    xd = ctx.dev(x)
+    net = nets.GFNet(ctx, sd, npass=npass, chunk=400)
+    monkeypatch.delenv("ROREG_GEMM_GATHER", raising=False)
+    a = [net.forward(xd).clone() for _ in range(3)]
+    monkeypatch.setenv("ROREG_GEMM_GATHER", "tma")
+    b = net.forward(xd).clone()
+    monkeypatch.delenv("ROREG_GEMM_GATHER", raising=False)
+    assert torch.equal(a[0], a[1]) and torch.equal(a[0], a[2])      # run-to-run
+    assert torch.equal(a[0], b)                                      # producer-to-producer
+    assert bool(torch.isfinite(a[0]).all())
+
+
 def test_et_net_against_oracle(ctx, tables):
     from roreg_b200 import nets
     pr = synth.make_pair(33, n=500, with_fcgf=True, max_res_deg=2.0)
