@@ -5,8 +5,8 @@
 // Activations live channel-LAST: act[(item*60 + g)][c], split into tf32 hi / lo parts by the producing
 // epilogue.  A group convolution  out[o,g] = b[o] + sum_{c,k} W[o,c,k] act[c, N[g,k]]  is the GEMM of
 //   A[(item, g)][(k, c)] = act[(item*60 + N[g,k])][c]        (the 13 group neighbours of g)
-// with W_flat[o][(k,c)].  A is IMPLICIT: the GEMM's producer warp gathers the activation rows with
-// cp.async.bulk.tensor tile::gather4 (kernels_gemm_tc.cuh, GemmArgs.g_*) - round 1 materialised it with an im2col
+// with W_flat[o][(k,c)].  A is IMPLICIT: the GEMM's loader warps gather the activation rows with
+// cp.async (kernels_gemm_tc.cuh, GemmArgs.g_*) - round 1 materialised it with an im2col
 // pass (13x the activation bytes written and read back).  Only the output group elements a later stage needs are
 // computed (`gset`), which is how ET's "only g = 0 of the head is used" (network/eqv_trans.py:136) prunes the two last layers.
 #pragma once
