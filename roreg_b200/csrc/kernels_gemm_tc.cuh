@@ -30,7 +30,7 @@ template <int NPASS> struct GemmCfg {
   static constexpr int STAGES = NPASS == 3 ? 2 : 4;
   static constexpr int A_IMAGES = NPASS == 3 ? 2 : 1;
   static constexpr int STAGE_BYTES = A_IMAGES * (GM_A_BYTES + GM_W_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256;      // the dynamic array is declared 1024-byte aligned: no slack needed
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 8 * 2048;      // stages | barriers | 8 epilogue staging blocks (the dynamic array is declared 1024-byte aligned: no slack needed)
   static constexpr int OFF_ALO = GM_A_BYTES;                         // 3-pass only
   static constexpr int OFF_WHI = A_IMAGES * GM_A_BYTES;
   static constexpr int OFF_WLO = OFF_WHI + GM_W_BYTES;               // 3-pass only
@@ -79,6 +79,8 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 //   warp 16     MMA issuer (one lane); warp 17 box producer (one lane: W, and A in plain mode); 18-19 idle   56 registers
 constexpr int GM_LOADERS = 8, GM_EPI_WARPS = 8, GM_EPI0 = GM_LOADERS, GM_MMA_WARP = GM_LOADERS + GM_EPI_WARPS, GM_BOX_WARP = GM_MMA_WARP + 1;
 constexpr int GM_THREADS = (GM_LOADERS + GM_EPI_WARPS + 4) * 32;      // 640
+constexpr int GM_STG_BYTES = 32 * 64;                                 // per epilogue warp: 32 rows x 16 floats
+static_assert(GM_EPI_WARPS * GM_STG_BYTES == 8 * 2048, "GemmCfg::SMEM_BYTES reserves 8 staging blocks of 2 KB");
 
 template <int NPASS>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_constant__ CUtensorMap mapAlo,
@@ -86,8 +88,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
                                                          GemmArgs a) {
   using Cfg = GemmCfg<NPASS>;
   constexpr int LANES = 32 / GM_LOADERS;                      // gather4 lanes per loader warp
-  // Shared-memory budget: static (~1.4 KB, rounded up to the array's 1 KB alignment) + 192 KB of stages + barriers = 194.3 KiB,
-  // i.e. under the 196 KiB carve-out step (+1 KiB the system reserves per CTA) - see the note at nei_s.
+  // Shared-memory budget: static (~1.4 KB, rounded up to the array's 1 KB alignment) + 192 KB of stages + barriers + 16 KB of
+  // epilogue staging = 210.3 KiB.  That is past the 196 KiB carve-out step, i.e. the L1 is ~28 KB instead of ~60 KB: acceptable
+  // since the epilogue no longer leans on L1 (residual / running-maximum rows come with 16-byte ld.cg, stores are staged); while it
+  // did (round-2 run c7) crossing the step cost the all-pairs launches 45 %.
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw;
   if ((smem_u32(smem_raw) & 1023u) != 0) { if (threadIdx.x == 0) printf("roreg: gemm_tc_kernel: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -95,9 +99,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   // barriers: 0..3 full, 4..7 empty, 8..9 tmem_full, 10..11 tmem_empty
   __shared__ uint32_t tmem_base_s;
   __shared__ uint16_t acols_s[256];
-  // byte tables: together with the dynamic buffers the CTA must stay under the 196 KiB shared-memory carve-out - the next step
-  // (228 KiB) halves the L1 that the epilogue's row-strided loads live in (run c7: 3.4 KB of int32 tables cost the all-pairs
-  // GEMMs 45 %)
+  // byte tables (the CTA's total must stay under the 227 KiB limit)
   __shared__ uint8_t nei_s[60 * 13];
   __shared__ uint8_t gset_s[64];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,6 +285,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int q = warp & 3, half = (warp - GM_EPI0) >> 2;     // TMEM lane quadrant of this warp (warp id % 4); chunk parity
     const int row_in_tile = q * 32 + lane;
+    uint8_t* stg = smem + Cfg::STAGES * Cfg::STAGE_BYTES + 256 + (warp - GM_EPI0) * GM_STG_BYTES;     // this warp's 32 x 64-byte store staging block
     // 16-byte accesses of whole chunks are possible when every row pitch is a multiple of 4 floats and every base is 16-byte aligned
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
     const bool vec_ok = !a.amax_arg && ((a.NT & 15) == 0) &&
@@ -302,10 +305,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       // one 16-column chunk of the accumulator row (v) -> bias / residual / running max / BN / ReLU / split -> global
       auto process = [&](const uint32_t (&v)[16], const int c0) {
         const int o0 = nt * a.NT + c0;
-        if (r < a.R && vec_ok && o0 + 16 <= a.O) {
-          // Fast path (whole chunk in range, 16-byte aligned rows, no running maximum): ~150 instructions.  The general path below
-          // tests every element and loads every bias / BN parameter on its own - 1840 instructions per chunk (ncu source view,
-          // run c23), which made the epilogue (60-76 k clk per tile) the limit of every layer with fewer than ~90 k-chunks.
+        if (vec_ok && o0 + 16 <= a.O) {
+          // Fast path (whole chunk in range, 16-byte aligned rows, no running maximum; warp-uniform): ~200 instructions.  The general
+          // path below tests every element and loads every bias / BN parameter on its own - 1840 instructions per chunk (ncu source
+          // view, run c23), which made the epilogue (60-76 k clk per tile) the limit of every layer with fewer than ~90 k-chunks.
+          // Stores go through a 32-row x 64-byte staging block per warp so that four lanes write one row's 64 contiguous bytes (two
+          // full sectors): thread-per-row stores are 32 half-sector writes per instruction, and with every SM in its epilogue
+          // those (~100 sector writes per clock chip-wide) were what a 24 k-clk tile epilogue waited for (run c24 / c29).
           float x[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
@@ -314,16 +320,28 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
 #pragma unroll
             for (int k = 0; k < 4; ++k) { const float4 w = __ldg(pb + k); x[4 * k] += w.x; x[4 * k + 1] += w.y; x[4 * k + 2] += w.z; x[4 * k + 3] += w.w; }
           }
-          if (a.residual) {
+          if (a.residual && r < a.R) {
             const float4* pr = reinterpret_cast<const float4*>(a.residual + r * a.res_ld + o0);
 #pragma unroll
             for (int k = 0; k < 4; ++k) { const float4 w = __ldcg(pr + k); x[4 * k] += w.x; x[4 * k + 1] += w.y; x[4 * k + 2] += w.z; x[4 * k + 3] += w.w; }
           }
-          if (a.raw_out) {
-            float4* po = reinterpret_cast<float4*>(a.raw_out + r * a.raw_ld + o0);
+          // rows of the warp's block -> global, transposed through the staging block (XOR on the 16-byte piece index: conflict-free
+          // for the row-wise writes and for the 4-lanes-per-row reads)
+          auto stage_store = [&](float* base, int ld, const float (&y)[16]) {
+            float4* srow = reinterpret_cast<float4*>(stg + lane * 64);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) po[k] = make_float4(x[4 * k], x[4 * k + 1], x[4 * k + 2], x[4 * k + 3]);
-          }
+            for (int k = 0; k < 4; ++k) srow[k ^ ((lane >> 1) & 3)] = make_float4(y[4 * k], y[4 * k + 1], y[4 * k + 2], y[4 * k + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int rr = 8 * k + (lane >> 2), pc = lane & 3;
+              const float4 w = reinterpret_cast<const float4*>(stg + rr * 64)[pc ^ ((rr >> 1) & 3)];
+              const long long grow = r - lane + rr;
+              if (grow < a.R) *reinterpret_cast<float4*>(base + grow * ld + o0 + 4 * pc) = w;
+            }
+            __syncwarp();
+          };
+          if (a.raw_out) stage_store(a.raw_out, a.raw_ld, x);
           if (a.act_hi) {
             if (a.bn_scale) {
               const float4* ps = reinterpret_cast<const float4*>(a.bn_scale + o0);
@@ -342,13 +360,11 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
               uint32_t tb; asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tb) : "f"(x[j]));
               hi[j] = __uint_as_float(tb);
             }
-            float4* ph = reinterpret_cast<float4*>(a.act_hi + r * a.act_ld + o0);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) ph[k] = make_float4(hi[4 * k], hi[4 * k + 1], hi[4 * k + 2], hi[4 * k + 3]);
+            stage_store(a.act_hi, a.act_ld, hi);
             if (a.act_lo) {
-              float4* pl = reinterpret_cast<float4*>(a.act_lo + r * a.act_ld + o0);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) pl[k] = make_float4(x[4 * k] - hi[4 * k], x[4 * k + 1] - hi[4 * k + 1], x[4 * k + 2] - hi[4 * k + 2], x[4 * k + 3] - hi[4 * k + 3]);
+              for (int j = 0; j < 16; ++j) x[j] -= hi[j];
+              stage_store(a.act_lo, a.act_ld, x);
             }
           }
         } else if (r < a.R) {

@@ -13,7 +13,7 @@ from . import nets
 
 
 class YohooEngine:
-    def __init__(self, ctx, et_state_dict, npass=3, max_iter=1000, ird=0.1, nn_mode=4, et_chunk=4000):
+    def __init__(self, ctx, et_state_dict, npass=3, max_iter=1000, ird=0.1, nn_mode=4, et_chunk=16000):
         self.ctx, self.max_iter, self.ird, self.nn_mode = ctx, max_iter, ird, nn_mode
         self.et = nets.ETNet(ctx, et_state_dict, npass=npass, chunk=et_chunk)
 

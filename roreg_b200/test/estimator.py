@@ -191,7 +191,7 @@ class extractor_localtrans():
         from .extractor import load_state_dict
         from .. import nets
         # strict=False in the reference (:289): the checkpoint also carries an unused PartI_net.* copy
-        self.net = nets.ETNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass, chunk=int(self.test_batch_size))
+        self.net = nets.ETNet(self.ctx, load_state_dict(self.best_model_fn), npass=self.npass, chunk=max(16000, int(self.test_batch_size)))   # bs_ET is the reference's memory knob; the output does not depend on the chunking (eval-mode BN)
 
     def hypotheses(self, quat, pre_idx, Keys0_m, Keys1_m):
         ctx = self.ctx
