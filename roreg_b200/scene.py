@@ -257,6 +257,9 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
     samples_all = draw_samples(cfg, lay, dataset, pairs_all, n, keynum)        # all pairs on every rank: one RNG order for any world size
     lo, hi = shard_pairs(len(pairs_all), rank, world)
     poses = np.zeros((hi - lo, 4, 4)); recall = np.zeros(hi - lo, np.int64); counts = np.zeros(hi - lo, np.int64)
+    whole = (lo, hi) == (0, len(pairs_all))                                    # this rank sees every pose: pre.log text is built pair by pair
+    blocks = [None] * (hi - lo) if whole else None
+    n_clouds = len(dataset.pc_ids)
     # pairs are registered in the order their clouds arrive (a pair is ready when its later cloud is uploaded); results and files
     # are indexed by the pair's position in dataset.pair_ids, so the order is invisible outside
     order = sorted(range(lo, hi), key=lambda p: max(slot[pairs_all[p][0]], slot[pairs_all[p][1]]))
@@ -285,6 +288,8 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
                 else:
                     r += 1                                                      # engine: 0-based id of the winner; reference: 1-based iteration (test/estimator.py:226,236)
                 poses[p - lo] = T; recall[p - lo] = r; counts[p - lo] = k
+                if whole:
+                    blocks[p] = host.trajectory_block(id0, id1, n_clouds, T)
                 writer.submit(_write_pair, lay, max_iter, id0, id1, m, dr, T, r)
         loader.wait(len(loader.ids))
         loader.join()
@@ -293,5 +298,5 @@ def register_scene(cfg, dataset, keynum=5000, max_iter=1000, batch_pairs=64, nn_
     if dist_on:
         dist.barrier()
     if rank == 0:
-        host.write_trajectory(dataset, out_dir, poses if (lo, hi) == (0, len(pairs_all)) else None)
+        host.write_trajectory(dataset, out_dir, blocks=blocks)
     return dict(lo=lo, hi=hi, poses=poses, recall=recall, n_matches=counts)

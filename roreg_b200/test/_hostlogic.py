@@ -82,15 +82,23 @@ def draw_guided_triplets(members, prob, max_iter, max_draws=50000):
     return np.asarray(out, dtype=np.int64).reshape(-1, 3)
 
 
-def write_trajectory(dataset, result_dir, poses=None):
+def trajectory_block(id0, id1, n_clouds, T):
+    """The five pre.log lines of one pair (R_pre_log, test/estimator.py:14-26): 'id0<TAB>id1<TAB>n_clouds', the three pose rows in
+    str() form, the constant last row."""
+    rows = ['\t'.join(str(T[r][c]) for c in range(4)) + '\n' for r in range(3)]
+    return f'{int(id0)}\t{int(id1)}\t{n_clouds}\n' + ''.join(rows) + '0.0\t0.0\t0.0\t1.0\n'
+
+
+def write_trajectory(dataset, result_dir, poses=None, blocks=None):
     """R_pre_log (test/estimator.py:14-26): `pre.log` in the 3DMatch trajectory format read by utils/RR_cal.py:339 - per pair
     'id0<TAB>id1<TAB>n_clouds' then the 4 rows of the pose, last row constant; numbers in str() form.  `poses` (optional,
-    [n_pairs,4,4] in pair order) = the matrices just stored in the .npz files, saving their re-read."""
+    [n_pairs,4,4] in pair order) = the matrices just stored in the .npz files, saving their re-read; `blocks` (optional, one
+    trajectory_block string per pair, in pair order) = the text already formatted while the pairs were being registered."""
     n_clouds = len(dataset.pc_ids)
     with open(f'{result_dir}/pre.log', 'w') as f:
+        if blocks is not None:
+            f.write(''.join(blocks))
+            return
         for i, (id0, id1) in enumerate(dataset.pair_ids):
             T = poses[i] if poses is not None else np.load(f'{result_dir}/{id0}-{id1}.npz', allow_pickle=True)['trans']
-            f.write(f'{int(id0)}\t{int(id1)}\t{n_clouds}\n')
-            for r in range(3):
-                f.write('\t'.join(str(T[r][c]) for c in range(4)) + '\n')
-            f.write('0.0\t0.0\t0.0\t1.0\n')
+            f.write(trajectory_block(id0, id1, n_clouds, T))
