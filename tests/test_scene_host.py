@@ -108,3 +108,33 @@ def test_scene_driver_world2_gloo(tmp_path):
         for i in range(lo, hi):
             id0, id1 = ds.pair_ids[i]
             assert np.array_equal(poses[i - lo], np.load(f"{cache}/{ds.name}/match_200/yohoc/100iters/{id0}-{id1}.npz")["trans"])
+
+
+def test_scene_loader_chunked_reads_and_error_paths(tmp_path, monkeypatch):
+    """SceneLoader reads every cloud file in READ_CHUNK pieces through its reader pool: the arena must equal np.load of the files
+    for chunk sizes that do not divide the payload, and a truncated or mis-shaped file must surface as a ValueError naming the
+    cloud in wait() (the reference's np.load would raise there too) - not hang the loader thread."""
+    import pytest
+    from roreg_b200 import scene
+    from roreg_b200.test._common import CacheLayout
+    ctx = _host_ctx.install(monkeypatch)
+    ds = synth.SynthDataset([91, 92], n=150, name="synth/loader", with_fcgf=False)
+    cache = str(tmp_path / "c"); ds.write_cache(cache)
+    lay = CacheLayout(_cfg(cache), ds, 150)
+    for chunk in (1 << 20, 100_003, 4096):                                   # one piece; ragged pieces; many small pieces
+        monkeypatch.setattr(scene, "READ_CHUNK", chunk)
+        desc, keys, slot = scene.load_scene(ctx, lay, ds, readers=3, ring=2)
+        for cid in ds.pc_ids:
+            assert np.array_equal(desc[slot[cid]].numpy(), np.load(lay.yoho_desc(cid)))
+            assert np.array_equal(keys[slot[cid]].numpy(), ds.get_kps(cid).astype(np.float64))
+    victim = lay.yoho_desc(ds.pc_ids[2])
+    whole = open(victim, "rb").read()
+    open(victim, "wb").write(whole[:len(whole) // 2])                       # truncated payload
+    with pytest.raises(ValueError, match="truncated"):
+        scene.load_scene(ctx, lay, ds, readers=3, ring=2)
+    np.save(victim, np.zeros((149, 32, 60), np.float32))                      # wrong keypoint count
+    with pytest.raises(ValueError, match=f"cloud {ds.pc_ids[2]}"):
+        scene.load_scene(ctx, lay, ds, readers=3, ring=2)
+    open(victim, "wb").write(whole)
+    desc, _, slot = scene.load_scene(ctx, lay, ds, readers=1, ring=1)      # and the loader works again afterwards
+    assert np.array_equal(desc[slot[ds.pc_ids[2]]].numpy(), np.load(victim))
