@@ -133,7 +133,8 @@ int roreg_pack_descriptors(roreg_ctx* ctx, int n_src, const float* const* src_ho
 /* Group convolution as an IMPLICIT GEMM (data_process + Conv2d(C, O, (1,13)): network/group_feat.py:20-33, ops.py:45-51):
  * out[(item*n_gout+j)][o] = sum_{k,c} act[(item*60 + N[gset[j]][k])][c] W[o][k*C+c] (+ epilogue as roreg_gemm); the
  * 13-neighbour gather happens in the GEMM's operand load (cp.async row copies into the swizzled tile), nothing is materialised.  C % 32 == 0;
- * gset NULL = all 60 group elements (n_gout = 60); act_lo / W_lo / out_lo may be NULL when npass == 1.              */
+ * gset NULL = all 60 group elements (n_gout = 60); act_lo / W_lo / out_lo may be NULL when npass == 1; act_* and W_* bases
+ * 16-byte aligned (ROREG_ERR_ARG otherwise).                                                                       */
 int roreg_gconv_gemm(roreg_ctx* ctx, const float* act_hi, const float* act_lo, int n_items, int C, const int32_t* gset,
                      int n_gout, const float* W_hi, const float* W_lo, int w_rows, int O, int NT, int npass,
                      const float* bias, const float* residual, int res_ld, float* raw_out, int raw_ld, float* out_hi,

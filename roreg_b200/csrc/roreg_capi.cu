@@ -343,6 +343,8 @@ int roreg_gconv_gemm(roreg_ctx* c, const float* act_hi, const float* act_lo, int
                      const float* bn_scale, const float* bn_shift, int relu, void* stream) {
   RR_ARG(c, act_hi && W_hi && n_items >= 0 && C >= 32 && (C % 32) == 0 && n_gout >= 1 && n_gout <= 60 && O >= 1 && NT >= 16 && w_rows >= NT);
   RR_ARG(c, (raw_out || out_hi) && (long long)n_items * 60 < (1LL << 31));
+  // 16-byte row copies (cp.async) and TMA both need 16-byte aligned activation / weight bases
+  RR_ARG(c, (reinterpret_cast<uintptr_t>(act_hi) & 15) == 0 && (reinterpret_cast<uintptr_t>(act_lo) & 15) == 0 && (reinterpret_cast<uintptr_t>(W_hi) & 15) == 0);
   if (n_items == 0) return ROREG_OK;
   GemmArgs a{};
   a.R = n_items * n_gout; a.Kdim = 13 * C; a.O = O; a.NT = NT; a.n_ntiles = (O + NT - 1) / NT; a.npass = npass;
